@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json metric: "distill iters/s (Flickr 100 pairs, syn_steps=8); recall@K eval pairs/s").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one outer distillation iteration per rank on the Flickr-shaped configuration (BASELINE.json configs[2]):
+N = B = 100 synthetic pairs, syn_steps = 8, 768 -> 2304 text_projection head, one expert segment
+(theta_start, theta_target) per rank: K-step unroll, matching loss, reverse sweep to the synthetic-data gradients,
+gradient all-reduce across ranks (N > 1), momentum-SGD update of the synthetic pairs and the student lr.
+`value` = segment-iterations per second summed over all ranks, inputs already resident in HBM.
+`e2e`   = the same iteration through the public Python API with the segment coming from pinned HOST memory
+          (H2D of theta_start/theta_target/perms inside the timed region, loss read back D2H every step).
+The retrieval metric (pairs/s, configs[0] shape 1000 x 5000 x 768) is reported on the same line under "retrieval".
+
+`--impl reference` times the reference's own mechanism on the host CPU: the oracle restatement of
+distill.py:509-606 (torch autograd, create_graph=True double backward, all host threads).  distill.py itself is not
+importable (clip/timm/kornia/BERT download), see oracle/distill_ref.py.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(N=100, B=100, K=8, dt=768, d=2304, experts=4, snapshots=3)
+RET = dict(I=1000, C=5, D=768)
+METRIC = "distill iters/s (Flickr 100 pairs, syn_steps=8)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf=p["bf16_tflops_sustained"], src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf=1590.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.stop_flag, self.index = [], False, index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def make_experts(seed):
+    from multimodal_dataset_distillation_b200 import distill
+    return distill.synthetic_experts(CFG["experts"], CFG["snapshots"], CFG["dt"], CFG["d"], seed=seed, step=0.01)
+
+
+def make_pairs(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    U = torch.randn(CFG["N"], CFG["d"], generator=g)
+    Y = torch.randn(CFG["N"], CFG["dt"], generator=g) * 0.5253 - 0.0094
+    return U, Y
+
+
+def bench_args():
+    from multimodal_dataset_distillation_b200 import distill
+    return distill.parse_args(["--syn_steps", str(CFG["K"]), "--expert_epochs", "1", "--max_start_epoch", "2",
+                               "--num_queries", str(CFG["N"]), "--mini_batch_size", str(CFG["B"]), "--lr_img", "1000",
+                               "--lr_txt", "1000", "--lr_lr", "0.01", "--logit_scale_mode", "upstream"])
+
+
+def kernel_launches_per_iteration(K):
+    # forward step: 7 GEMMs + 8 row/elementwise kernels + 2 gathers; reverse step: 9 GEMMs + 11; 4 per-call kernels
+    # (row normalise, match fwd, match bwd, normalise bwd); 3 momentum-SGD launches in the outer update.
+    return 17 * K + 20 * K + 4 + 3
+
+
+def algorithmic_bytes_per_iteration(K, P):
+    # forward unroll reads theta_k and writes theta_{k+1} (2K passes), matching loss reads 3
+    # vectors, reverse sweep reads theta_k, a_{k+1}, writes a_k plus one extra weight pass (4K)
+    return 4 * P * (2 * K + 3 + 4 * K)
+
+
+def run_ours(opt):
+    import torch.distributed as dist
+    from multimodal_dataset_distillation_b200 import distill, ops, epoch
+    from multimodal_dataset_distillation_b200._lib import lib
+    lib()                                            # fail loudly here if the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args = bench_args()
+    U, Y = make_pairs(0)                             # replicated synthetic set
+    experts_host = make_experts(100 + rank)          # each rank owns different expert trajectories
+    experts = experts_host.to(dev)
+    eng = distill.DistillEngine(U, Y, experts, args, dev)
+    K, B, N = CFG["K"], CFG["B"], CFG["N"]
+    g = torch.Generator().manual_seed(rank)
+    perm_sets = [torch.stack([torch.randperm(N, generator=g)[:B] for _ in range(K)]).to(dev) for _ in range(8)]
+
+    def step(i):
+        e, s = i % CFG["experts"], (i // CFG["experts"]) % 2          # rotate segments: inputs (4 x 3 x 28 MB) exceed L2
+        loss = eng.segment_loss(e, s, perm_sets[i % 8])
+        eng.outer_step(loss)
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(opt.warmup):
+        step(i)
+    sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        sync()
+        ev0.record()
+        for i in range(opt.steps):
+            step(opt.warmup + i)
+        ev1.record()
+        sync()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    ms_per_step = ms / opt.steps
+    value = world * opt.steps / (ms / 1e3)
+
+    # ---- end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ----
+    P = ops.head_numel(CFG["dt"], CFG["d"])
+    pinned = experts_host.pin_memory()
+    perms_host = [p.cpu().pin_memory() for p in perm_sets]
+    th0_d, tgt_d = torch.empty(P, device=dev), torch.empty(P, device=dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        e, s = i % CFG["experts"], (i // CFG["experts"]) % 2
+        th0_d.copy_(pinned[e, s], non_blocking=True)
+        tgt_d.copy_(pinned[e, s + 1], non_blocking=True)
+        perms = perms_host[i % 8].to(dev, non_blocking=True)
+        scale = eng.fixed_scale
+        loss = distill.UnrolledMatch.apply(eng.Y, eng.U, eng.syn_lr_txt, scale, th0_d, tgt_d, perms, None, eng.ws)
+        eng.outer_step(loss)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()                        # the user reads the loss every iteration
+        return float(loss_host)
+
+    for i in range(opt.warmup):
+        e2e_step(i)
+    sync()
+    t0 = time.perf_counter()
+    for i in range(opt.steps):
+        e2e_step(opt.warmup + i)
+    sync()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * opt.steps / float(te)
+    h2d = 2 * P * 4 + K * B * 8
+    d2h = 4
+
+    out = None
+    if rank == 0:
+        pk = peaks()
+        abytes = algorithmic_bytes_per_iteration(K, P)
+        achieved = abytes / (ms_per_step / 1e3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[2]: full distill inner loop, Flickr30K-shaped (N=B=100 pairs, syn_steps=8, "
+                                   "expert_epochs=1, max_start_epoch=2, text_projection 768->2304, image side = frozen "
+                                   "2304-d embeddings)",
+                       "unit_of_work": "one expert segment: 8-step unroll + matching loss + reverse sweep + outer SGD; "
+                                       "one segment per rank per step, grads all-reduced (NCCL) when n_gpus > 1",
+                       "l2_policy": "inputs larger than L2: steps rotate over 4 experts x 2 start epochs (340 MB of "
+                                    "snapshots) and the per-iteration working set is ~450 MB vs 126 MB L2",
+                       "parallelism": f"dp{world} (one expert segment per GPU)"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "segment (theta_start, theta_target, perms) copied from pinned host memory every step; loss read back"},
+            "gpu_launches": kernel_launches_per_iteration(K) * opt.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+                         "traffic": None, "peak_source": pk["src"],
+                         "kernel": "whole iteration (all launches of vldd_unrolled_match); algorithmic bytes = 4*P*(2K+3+4K)",
+                         "algorithmic_bytes_per_step": abytes},
+        }
+        out["retrieval"] = bench_retrieval(dev, opt)
+        out["cpu_baseline"] = cpu_baseline_distill(max_seconds=20.0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def bench_retrieval(dev, opt):
+    """Secondary metric: recall@K eval pairs/s at Flickr test shape (configs[0])."""
+    from multimodal_dataset_distillation_b200 import ops
+    from oracle import retrieval_ref as RR
+    I, C, D = RET["I"], RET["C"], RET["D"]
+    T = I * C
+    img, txt = RR.synthetic_retrieval(I, C, D, seed=0)
+    txt2img, img2txt = RR.flickr_maps(I, C)
+    t2i, ptr, idx = ops.maps_to_arrays(txt2img, img2txt, I, T)
+    d = lambda a: torch.from_numpy(a).to(dev)
+    img_d, txt_d, t2i_d, ptr_d, idx_d = d(img), d(txt), d(t2i), d(ptr), d(idx)
+    ws = torch.empty(ops.lib().vldd_sim_rank_workspace_bytes(I, T, D), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    reps = max(5, opt.steps)
+    for _ in range(3):
+        ops.sim_rank(img_d, txt_d, t2i_d, ptr_d, idx_d, 14.285714, ws)
+    tot = 0.0
+    for _ in range(reps):
+        flush.zero_()                                   # L2 flush between timed iterations (inputs are < L2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r1, r2 = ops.sim_rank(img_d, txt_d, t2i_d, ptr_d, idx_d, 14.285714, ws)
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / reps
+    # e2e: the reference's itm_eval signature with HOST score matrices (pinned), ranks + recall back on the host
+    S = (np.float32(14.285714) * img) @ txt.T
+    s1 = torch.from_numpy(S).pin_memory()
+    s2 = torch.from_numpy(np.ascontiguousarray(S.T)).pin_memory()
+    for _ in range(2):
+        ops.itm_eval_host(s1.numpy(), s2.numpy(), t2i, ptr, idx)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = ops.itm_eval_host(s1.numpy(), s2.numpy(), t2i, ptr, idx)
+    e2e_s = (time.perf_counter() - t0) / reps
+    # CPU baseline: the oracle restatement of itm_eval on the same matrices (single thread, numpy)
+    t0 = time.perf_counter()
+    ref = RR.recall_dict(RR.ranks_vectorised(S, ptr, idx), RR.ranks_vectorised(np.ascontiguousarray(S.T), np.arange(T + 1, dtype=np.int32), t2i))
+    cpu_s = time.perf_counter() - t0
+    return {"metric": "recall@K eval pairs/s", "workload": f"configs[0]: {I} images x {T} captions, {D}-d",
+            "value": I * T / (ms / 1e3), "unit": "pairs/s", "ms": ms,
+            "what": "embeddings resident in HBM -> similarity GEMM -> ranks of both directions (vldd_sim_rank)",
+            "e2e": {"value": I * T / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": 2 * I * T * 4 + (T + I + 1 + T) * 4,
+                    "d2h_bytes_per_step": 32, "what": "itm_eval(host score matrices) through vldd_itm_eval_host"},
+            "cpu_baseline": {"value": I * T / cpu_s, "unit": "pairs/s", "cores": 1, "kind": "port",
+                             "sample": "oracle itm_eval restatement (numpy) on the same 1000x5000 matrices, ranking only"},
+            "r_mean": res["r_mean"], "r_mean_cpu": ref["r_mean"]}
+
+
+def cpu_baseline_distill(max_seconds=20.0, max_iters=8):
+    """Oracle (torch CPU restatement of distill.py:509-606, autograd double backward) on the host cores."""
+    from oracle import distill_ref as R
+    pr = R.make_problem(N=CFG["N"], B=CFG["B"], K=CFG["K"], dt=CFG["dt"], d=CFG["d"], seed=0)
+    R.unrolled_match_autograd(**pr)                       # warm-up (thread pools, allocator)
+    n, t0 = 0, time.perf_counter()
+    while n < max_iters and (time.perf_counter() - t0) < max_seconds:
+        R.unrolled_match_autograd(**pr)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "iters/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} full iterations of the same Flickr-shaped workload (oracle/distill_ref.py::unrolled_match_autograd, "
+                      f"torch {torch.__version__} CPU, {torch.get_num_threads()} threads of {os.cpu_count()} cpus)"}
+
+
+def run_reference(opt):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    from oracle import distill_ref as R
+    pr = R.make_problem(N=CFG["N"], B=CFG["B"], K=CFG["K"], dt=CFG["dt"], d=CFG["d"], seed=0)
+    steps = min(opt.steps, 10)
+    warm = min(opt.warmup, 2)
+    for _ in range(max(warm, 1)):
+        R.unrolled_match_autograd(**pr)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R.unrolled_match_autograd(**pr)
+    dt = time.perf_counter() - t0
+    v = steps / dt
+    sample = (f"{steps} full iterations (bounded from --steps {opt.steps}) of the Flickr-shaped workload on the host CPU: "
+              f"oracle restatement of distill.py:509-606 with torch autograd double backward")
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": opt.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2]: full distill inner loop, Flickr30K-shaped (N=B=100 pairs, syn_steps=8)"},
+            "cpu_baseline": {"value": v, "unit": "iters/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    opt = ap.parse_args()
+    opt.warmup = max(opt.warmup, 3) if opt.impl == "ours" else opt.warmup
+    out = run_reference(opt) if opt.impl == "reference" else run_ours(opt)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

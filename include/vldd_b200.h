@@ -1,0 +1,121 @@
+/* vldd_b200 -- C ABI of the B200-native hot path of vision-language trajectory-matching distillation.
+ *
+ * The reference (kushal-bhargav/multimodal_dataset_distillation) has no FFI / operator interface: its hot
+ * path is inline Python.  Each entry point below therefore cites the reference
+ * LINES it replaces; the Python names that sit on top of it (ReparamModule, itm_eval, epoch_test,
+ * evaluate_synset, the distill.py CLI) are mirrored in multimodal_dataset_distillation_b200/*.py and bind
+ * these symbols through ctypes (INTEGRATION.md shows the stub a maintainer adds to the reference).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 / int32 / int64 data unless the name ends in
+ *     `_host`; scalars that the reference keeps as tensors (syn_lr, logit scale) are device scalars so no
+ *     call synchronises the host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only enqueue work,
+ *     except the `*_host` entry points, which copy in, run, copy out and synchronise `stream`;
+ *   - return value: 0 on success, negative on error (VLDD_ERR_*); vldd_last_error() gives the message of
+ *     the calling thread's last failure.  There is no CPU fallback: without a CUDA device calls fail.
+ *   - the library owns no memory across calls except a grow-only device scratch used by `*_host` calls;
+ *     workspaces are caller-provided (sizes from the matching *_workspace_bytes function).
+ */
+#ifndef VLDD_B200_H_
+#define VLDD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLDD_ERR_ARG (-1)
+#define VLDD_ERR_CUDA (-2)
+#define VLDD_ERR_WORKSPACE (-3)
+
+int vldd_version(void);
+const char* vldd_last_error(void);
+
+/* ---- flat-parameter streaming ops --------------------------------------------------------------- */
+
+/* out = theta - (*lr) * grad.   distill.py:582-583 (`student_params[-1] - syn_lr * grad`).  12 B/param. */
+int vldd_flat_sgd_step(const float* theta, const float* grad, const float* lr, float* out, int64_t n, void* stream);
+
+/* out3 = {sum (theta_K-theta_tgt)^2, sum (theta_0-theta_tgt)^2, their ratio}.   distill.py:588-598
+ * (4x mse_loss(reduction="sum") + division).  `scratch`: vldd_match_loss_scratch_bytes() bytes whose first 16 bytes
+ * are zero before the first use.  12 B/param, deterministic. */
+size_t vldd_match_loss_scratch_bytes(void);
+int vldd_match_loss_fwd(const float* theta_K, const float* theta_tgt, const float* theta_0, int64_t n, float* out3,
+                        void* scratch, void* stream);
+/* a = g * 2 (theta_K - theta_tgt) / den, g = gout ? *gout : 1; num_den = out3 of the forward.   distill.py:606. */
+int vldd_match_loss_bwd(const float* theta_K, const float* theta_tgt, const float* num_den, const float* gout, float* a,
+                        int64_t n, void* stream);
+
+/* buf = first ? g : momentum*buf + g;  p -= lr*buf   (in place).   torch.optim.SGD(momentum=0.5) built at
+ * distill.py:233-241 and stepped at distill.py:611-613. */
+int vldd_momentum_sgd(float* p, const float* g, float* buf, float lr, float momentum, int first, int64_t n, void* stream);
+
+/* ---- retrieval scoring --------------------------------------------------------------------------- */
+
+/* Ranks of the ground truth for both directions given the two score matrices.   epoch.py:219-244 /
+ * epoch_original.py:115-161 (`itm_eval`), rank = #{s_j > s_gt} + #{j < gt : s_j == s_gt}, i2t = min over the
+ * image's captions.  img2txt is CSR (ptr[I+1], idx[]); txt2img[T].  Either direction may be skipped by passing
+ * NULL scores.  Integer results: bit-exact. */
+int vldd_ranks_from_scores(const float* scores_i2t, const float* scores_t2i, int n_img, int n_txt,
+                           const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx,
+                           int32_t* ranks_i2t, int32_t* ranks_t2i, void* stream);
+/* counts3 = {#ranks<1, #ranks<5, #ranks<10}.   epoch.py:227-229,236-238. */
+int vldd_recall_counts(const int32_t* ranks, int n, int32_t* counts3, void* stream);
+/* S_i2t[I,T] = scale * img @ txt^T and/or S_t2i[T,I] (either may be NULL).   epoch_original.py:94,101. */
+int vldd_sim_scores(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale, float* scores_i2t,
+                    float* scores_t2i, void* stream);
+/* out = S with every row's k largest kept and the rest := fill.   epoch_original.py:95-99, 102-105 (k=128, -100). */
+int vldd_topk_fill(const float* scores, float* out, int rows, int cols, int k, float fill, void* stream);
+/* Embeddings -> ranks of both directions (similarity + ranking without returning the score matrices).
+ * epoch_original.py:94 + itm_eval.  workspace: vldd_sim_rank_workspace_bytes(). */
+size_t vldd_sim_rank_workspace_bytes(int n_img, int n_txt, int dim);
+int vldd_sim_rank(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale,
+                  const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx, int32_t* ranks_i2t,
+                  int32_t* ranks_t2i, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Host-buffer drop-in for `itm_eval(scores_i2t, scores_t2i, txt2img, img2txt)` (numpy arrays in the reference):
+ * copies the matrices to the device, ranks, copies ranks back and fills result9 in the reference's key order
+ * {txt_r1, txt_r5, txt_r10, txt_r_mean, img_r1, img_r5, img_r10, img_r_mean, r_mean}.  ranks_*_host may be NULL. */
+int vldd_itm_eval_host(const float* scores_i2t_host, const float* scores_t2i_host, int n_img, int n_txt,
+                       const int32_t* txt2img_host, const int32_t* img2txt_ptr_host, const int32_t* img2txt_idx_host,
+                       int32_t* ranks_i2t_host, int32_t* ranks_t2i_host, double* result9, void* stream);
+
+/* ---- text_projection head + InfoNCE + unroll ------------------------------------------------------ */
+/* Flat layout of theta (reparam_module.py:28-51 applied to networks.py:625-646):
+ *   [projection.weight d x dt | projection.bias d | fc.weight d x d | fc.bias d | layer_norm.weight d | layer_norm.bias d] */
+
+/* z = ProjectionHead(Y) (networks.py:639-646; mask = pre-scaled dropout mask or NULL for eval), zn = z/|z|
+ * (epoch_original.py:78).  z or zn may be NULL. */
+size_t vldd_proj_head_workspace_bytes(int rows, int dt, int d);
+int vldd_proj_head_forward(const float* theta, const float* Y, const float* mask, int rows, int dt, int d, float* z,
+                           float* zn, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One contrastive step on a whole batch: loss and first-order gradients.   distill.py:524-551 + 562-567
+ * (forward, normalise, logits = scale * Xn Yn^T, (CE + CE^T)/2, grad wrt the flat text parameters).
+ * U = image-encoder outputs [B,d].  Outputs (any of dY,dU,dscale may be NULL): loss[1], g_theta[P], dY[B,dt],
+ * dU[B,d], dscale[1]. */
+size_t vldd_contrastive_step_workspace_bytes(int B, int dt, int d);
+int vldd_contrastive_step(const float* theta, const float* Y, const float* U, const float* scale, const float* mask,
+                          int B, int dt, int d, float* loss, float* g_theta, float* dY, float* dU, float* dscale,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* The whole inner loop of one expert segment and its backward.   distill.py:509-606:
+ *   for k < K: idx = perms[k] (510-511); g = grad(InfoNCE(head(Y[idx]; theta_k), U[idx]), theta_k) (524-567);
+ *              theta_{k+1} = theta_k - lr g (583);
+ *   loss = |theta_K - theta_tgt|^2 / |theta_0 - theta_tgt|^2 (588-598);  backward to Y, U, lr, scale (606).
+ * perms: int64 [K,B] (unique indices per row);  masks: [K,B,d] pre-scaled dropout masks or NULL.
+ * Outputs: out5 = {num, den, loss, dloss/dlr, dloss/dscale}; ce[K] per-step contrastive losses (nullable);
+ * dY[N,dt]; dU[N,d]; theta_K[P] (nullable). */
+size_t vldd_unrolled_match_workspace_bytes(int N, int B, int K, int dt, int d);
+int vldd_unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, const float* U, const float* lr,
+                        const float* scale, const int64_t* perms, const float* masks, int N, int B, int K, int dt, int d,
+                        float* out5, float* ce, float* dY, float* dU, float* theta_K, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLDD_B200_H_ */

@@ -1,0 +1,234 @@
+// extern "C" surface of libvldd_b200.so (declared in include/vldd_b200.h).  Thin: argument checks, then the
+// C++ launchers.  No torch types cross this boundary.
+#include <mutex>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/vldd_b200.h"
+#include "common.cuh"
+#include "engine.h"
+#include "kernels.h"
+
+namespace vldd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+    return VLDD_ERR_CUDA;
+  }
+  return VLDD_OK;
+}
+
+// grow-only device scratch for the *_host entry points
+static std::mutex g_scratch_mu;
+static void* g_scratch = nullptr;
+static size_t g_scratch_bytes = 0;
+
+static int host_scratch(size_t bytes, void** out) {
+  if (bytes > g_scratch_bytes) {
+    if (g_scratch) cudaFree(g_scratch);
+    g_scratch = nullptr;
+    g_scratch_bytes = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&g_scratch, want);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      return VLDD_ERR_CUDA;
+    }
+    g_scratch_bytes = want;
+  }
+  *out = g_scratch;
+  return VLDD_OK;
+}
+
+}  // namespace vldd
+
+using namespace vldd;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int vldd_version(void) { return 100; }
+const char* vldd_last_error(void) { return g_err; }
+
+int vldd_flat_sgd_step(const float* theta, const float* grad, const float* lr, float* out, int64_t n, void* stream) {
+  VLDD_REQUIRE(n >= 0 && (n == 0 || (theta && grad && lr && out)), "flat_sgd_step: null pointer or negative n");
+  return flat_sgd_step(theta, grad, lr, out, n, S(stream));
+}
+
+size_t vldd_match_loss_scratch_bytes(void) { return (size_t)match_loss_scratch_bytes(); }
+
+int vldd_match_loss_fwd(const float* theta_K, const float* theta_tgt, const float* theta_0, int64_t n, float* out3,
+                        void* scratch, void* stream) {
+  VLDD_REQUIRE(n >= 0 && theta_K && theta_tgt && theta_0 && out3 && scratch, "match_loss_fwd: null pointer");
+  return match_loss_fwd(theta_K, theta_tgt, theta_0, n, out3, scratch, S(stream));
+}
+
+int vldd_match_loss_bwd(const float* theta_K, const float* theta_tgt, const float* num_den, const float* gout, float* a,
+                        int64_t n, void* stream) {
+  VLDD_REQUIRE(n >= 0 && theta_K && theta_tgt && num_den && a, "match_loss_bwd: null pointer");
+  return match_loss_bwd(theta_K, theta_tgt, num_den, gout, a, n, S(stream));
+}
+
+int vldd_momentum_sgd(float* p, const float* g, float* buf, float lr, float momentum, int first, int64_t n,
+                      void* stream) {
+  VLDD_REQUIRE(n >= 0 && (n == 0 || (p && g && buf)), "momentum_sgd: null pointer");
+  return momentum_sgd(p, g, buf, lr, momentum, first, n, S(stream));
+}
+
+int vldd_ranks_from_scores(const float* scores_i2t, const float* scores_t2i, int n_img, int n_txt,
+                           const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx,
+                           int32_t* ranks_i2t, int32_t* ranks_t2i, void* stream) {
+  VLDD_REQUIRE(n_img >= 0 && n_txt >= 0, "ranks_from_scores: negative sizes");
+  if (scores_i2t) {
+    VLDD_REQUIRE(img2txt_ptr && img2txt_idx && ranks_i2t, "ranks_from_scores: i2t needs img2txt CSR and ranks_i2t");
+    int rc = ranks_rows(scores_i2t, n_txt, n_img, n_txt, img2txt_ptr, img2txt_idx, ranks_i2t, S(stream));
+    if (rc) return rc;
+  }
+  if (scores_t2i) {
+    VLDD_REQUIRE(txt2img && ranks_t2i, "ranks_from_scores: t2i needs txt2img and ranks_t2i");
+    int rc = ranks_rows(scores_t2i, n_img, n_txt, n_img, nullptr, txt2img, ranks_t2i, S(stream));
+    if (rc) return rc;
+  }
+  return VLDD_OK;
+}
+
+int vldd_recall_counts(const int32_t* ranks, int n, int32_t* counts3, void* stream) {
+  VLDD_REQUIRE(n >= 0 && counts3 && (n == 0 || ranks), "recall_counts: null pointer");
+  return recall_counts(ranks, n, counts3, S(stream));
+}
+
+int vldd_sim_scores(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale, float* scores_i2t,
+                    float* scores_t2i, void* stream) {
+  VLDD_REQUIRE(n_img >= 0 && n_txt >= 0 && dim > 0 && img && txt, "sim_scores: bad arguments");
+  return sim_scores(img, txt, n_img, n_txt, dim, scale, scores_i2t, scores_t2i, S(stream));
+}
+
+int vldd_topk_fill(const float* scores, float* out, int rows, int cols, int k, float fill, void* stream) {
+  VLDD_REQUIRE(rows >= 0 && cols >= 0 && k >= 0 && scores && out && scores != out, "topk_fill: bad arguments");
+  return topk_fill_rows(scores, out, rows, cols, k, fill, S(stream));
+}
+
+size_t vldd_sim_rank_workspace_bytes(int n_img, int n_txt, int dim) {
+  (void)dim;
+  if (n_img <= 0 || n_txt <= 0) return 256;
+  return 2 * (size_t)n_img * (size_t)n_txt * sizeof(float) + 256;
+}
+
+int vldd_sim_rank(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale,
+                  const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx, int32_t* ranks_i2t,
+                  int32_t* ranks_t2i, void* workspace, size_t workspace_bytes, void* stream) {
+  VLDD_REQUIRE(n_img >= 0 && n_txt >= 0 && dim > 0 && img && txt, "sim_rank: bad arguments");
+  VLDD_REQUIRE(txt2img && img2txt_ptr && img2txt_idx && ranks_i2t && ranks_t2i, "sim_rank: null ground truth / outputs");
+  if (workspace == nullptr || workspace_bytes < vldd_sim_rank_workspace_bytes(n_img, n_txt, dim)) {
+    set_error("sim_rank: workspace too small (need %zu bytes)", vldd_sim_rank_workspace_bytes(n_img, n_txt, dim));
+    return VLDD_ERR_WORKSPACE;
+  }
+  if (n_img == 0 || n_txt == 0) return VLDD_OK;
+  float* s_i2t = reinterpret_cast<float*>(workspace);
+  float* s_t2i = s_i2t + (size_t)n_img * n_txt;
+  int rc = sim_scores(img, txt, n_img, n_txt, dim, scale, s_i2t, s_t2i, S(stream));
+  if (rc) return rc;
+  rc = ranks_rows(s_i2t, n_txt, n_img, n_txt, img2txt_ptr, img2txt_idx, ranks_i2t, S(stream));
+  if (rc) return rc;
+  return ranks_rows(s_t2i, n_img, n_txt, n_img, nullptr, txt2img, ranks_t2i, S(stream));
+}
+
+int vldd_itm_eval_host(const float* scores_i2t_host, const float* scores_t2i_host, int n_img, int n_txt,
+                       const int32_t* txt2img_host, const int32_t* img2txt_ptr_host, const int32_t* img2txt_idx_host,
+                       int32_t* ranks_i2t_host, int32_t* ranks_t2i_host, double* result9, void* stream) {
+  VLDD_REQUIRE(n_img > 0 && n_txt > 0, "itm_eval: empty score matrix (%d x %d)", n_img, n_txt);
+  VLDD_REQUIRE(scores_i2t_host && scores_t2i_host && txt2img_host && img2txt_ptr_host && img2txt_idx_host && result9,
+               "itm_eval: null pointer");
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  cudaStream_t st = S(stream);
+  const size_t IT = (size_t)n_img * n_txt;
+  const int nnz = img2txt_ptr_host[n_img];
+  VLDD_REQUIRE(nnz >= 0, "itm_eval: bad img2txt CSR");
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t o_s1 = 0, o_s2 = o_s1 + al(IT * 4), o_t2i = o_s2 + al(IT * 4), o_ptr = o_t2i + al((size_t)n_txt * 4),
+               o_idx = o_ptr + al((size_t)(n_img + 1) * 4), o_ri = o_idx + al((size_t)nnz * 4 + 4),
+               o_rt = o_ri + al((size_t)n_img * 4), o_cnt = o_rt + al((size_t)n_txt * 4), total = o_cnt + 256;
+  void* base = nullptr;
+  int rc = host_scratch(total, &base);
+  if (rc) return rc;
+  char* b = reinterpret_cast<char*>(base);
+  float* d_s1 = reinterpret_cast<float*>(b + o_s1);
+  float* d_s2 = reinterpret_cast<float*>(b + o_s2);
+  int32_t* d_t2i = reinterpret_cast<int32_t*>(b + o_t2i);
+  int32_t* d_ptr = reinterpret_cast<int32_t*>(b + o_ptr);
+  int32_t* d_idx = reinterpret_cast<int32_t*>(b + o_idx);
+  int32_t* d_ri = reinterpret_cast<int32_t*>(b + o_ri);
+  int32_t* d_rt = reinterpret_cast<int32_t*>(b + o_rt);
+  int32_t* d_cnt = reinterpret_cast<int32_t*>(b + o_cnt);
+  VLDD_CUDA(cudaMemcpyAsync(d_t2i, txt2img_host, (size_t)n_txt * 4, cudaMemcpyHostToDevice, st));
+  VLDD_CUDA(cudaMemcpyAsync(d_ptr, img2txt_ptr_host, (size_t)(n_img + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (nnz) VLDD_CUDA(cudaMemcpyAsync(d_idx, img2txt_idx_host, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+  VLDD_CUDA(cudaMemcpyAsync(d_s1, scores_i2t_host, IT * 4, cudaMemcpyHostToDevice, st));
+  rc = ranks_rows(d_s1, n_txt, n_img, n_txt, d_ptr, d_idx, d_ri, st);
+  if (rc) return rc;
+  VLDD_CUDA(cudaMemcpyAsync(d_s2, scores_t2i_host, IT * 4, cudaMemcpyHostToDevice, st));
+  rc = ranks_rows(d_s2, n_img, n_txt, n_img, nullptr, d_t2i, d_rt, st);
+  if (rc) return rc;
+  rc = recall_counts(d_ri, n_img, d_cnt, st);
+  if (rc) return rc;
+  rc = recall_counts(d_rt, n_txt, d_cnt + 4, st);
+  if (rc) return rc;
+  int32_t cnt[8];
+  VLDD_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  if (ranks_i2t_host) VLDD_CUDA(cudaMemcpyAsync(ranks_i2t_host, d_ri, (size_t)n_img * 4, cudaMemcpyDeviceToHost, st));
+  if (ranks_t2i_host) VLDD_CUDA(cudaMemcpyAsync(ranks_t2i_host, d_rt, (size_t)n_txt * 4, cudaMemcpyDeviceToHost, st));
+  VLDD_CUDA(cudaStreamSynchronize(st));
+  const double tr1 = 100.0 * cnt[0] / n_img, tr5 = 100.0 * cnt[1] / n_img, tr10 = 100.0 * cnt[2] / n_img;
+  const double ir1 = 100.0 * cnt[4] / n_txt, ir5 = 100.0 * cnt[5] / n_txt, ir10 = 100.0 * cnt[6] / n_txt;
+  const double trm = (tr1 + tr5 + tr10) / 3, irm = (ir1 + ir5 + ir10) / 3;
+  result9[0] = tr1; result9[1] = tr5; result9[2] = tr10; result9[3] = trm;
+  result9[4] = ir1; result9[5] = ir5; result9[6] = ir10; result9[7] = irm;
+  result9[8] = (trm + irm) / 2;
+  return VLDD_OK;
+}
+
+size_t vldd_proj_head_workspace_bytes(int rows, int dt, int d) { return proj_head_workspace_bytes(rows, dt, d); }
+
+int vldd_proj_head_forward(const float* theta, const float* Y, const float* mask, int rows, int dt, int d, float* z,
+                           float* zn, void* workspace, size_t workspace_bytes, void* stream) {
+  VLDD_REQUIRE(theta && Y && (z || zn), "proj_head_forward: null pointer");
+  return proj_head_forward(theta, Y, mask, rows, dt, d, z, zn, workspace, workspace_bytes, S(stream));
+}
+
+size_t vldd_contrastive_step_workspace_bytes(int B, int dt, int d) { return contrastive_step_workspace_bytes(B, dt, d); }
+
+int vldd_contrastive_step(const float* theta, const float* Y, const float* U, const float* scale, const float* mask,
+                          int B, int dt, int d, float* loss, float* g_theta, float* dY, float* dU, float* dscale,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  VLDD_REQUIRE(theta && Y && U && scale && loss && g_theta, "contrastive_step: null pointer");
+  return contrastive_step(theta, Y, U, scale, mask, B, dt, d, loss, g_theta, dY, dU, dscale, workspace, workspace_bytes,
+                          S(stream));
+}
+
+size_t vldd_unrolled_match_workspace_bytes(int N, int B, int K, int dt, int d) {
+  return unrolled_match_workspace_bytes(N, B, K, dt, d);
+}
+
+int vldd_unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, const float* U, const float* lr,
+                        const float* scale, const int64_t* perms, const float* masks, int N, int B, int K, int dt, int d,
+                        float* out5, float* ce, float* dY, float* dU, float* theta_K, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  VLDD_REQUIRE(theta0 && theta_tgt && Y && U && lr && scale && (K == 0 || perms) && out5 && dY && dU,
+               "unrolled_match: null pointer");
+  return unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks, N, B, K, dt, d, out5, ce, dY, dU, theta_K,
+                        workspace, workspace_bytes, S(stream));
+}
+
+}  // extern "C"

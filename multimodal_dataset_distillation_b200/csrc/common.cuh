@@ -1,0 +1,109 @@
+// Shared device/host helpers for the vldd_b200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define VLDD_OK 0
+#ifndef VLDD_ERR_ARG
+#define VLDD_ERR_ARG (-1)
+#define VLDD_ERR_CUDA (-2)
+#define VLDD_ERR_WORKSPACE (-3)
+#endif
+
+namespace vldd {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define VLDD_REQUIRE(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      vldd::set_error(__VA_ARGS__);             \
+      return VLDD_ERR_ARG;                      \
+    }                                           \
+  } while (0)
+
+#define VLDD_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      vldd::set_error("%s failed: %s", #call, cudaGetErrorString(e__));        \
+      return VLDD_ERR_CUDA;                                                    \
+    }                                                                          \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- warp / block reductions (all threads of the block must call) -------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum, result broadcast to every thread. `scratch` holds >= 33 elements of T.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect scratch reuse across consecutive calls
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    T t = lane < nw ? scratch[lane] : T(0);
+    t = warp_sum(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < nw ? scratch[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+// ---- streaming loads/stores: 128-bit, bypass L1 allocation for touch-once data -------------------
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// ---- exact-erf GELU pieces (networks.py:634 nn.GELU() default) -----------------------------------
+__device__ __forceinline__ void gelu_parts(float p, float& phi, float& dphi, float& ddphi) {
+  const float cdf = 0.5f * (1.0f + erff(p * 0.70710678118654752440f));
+  const float pdf = expf(-0.5f * p * p) * 0.39894228040143267794f;
+  phi = p * cdf;
+  dphi = cdf + p * pdf;
+  ddphi = pdf * (2.0f - p * p);
+}
+
+}  // namespace vldd

@@ -1,0 +1,378 @@
+// Unroll engine (Path 1): K flat-parameter SGD steps of the text_projection head on the bidirectional InfoNCE
+// loss, the normalised parameter-matching loss, and the hand-written reverse sweep that replaces
+// `grand_loss.backward()` through `autograd.grad(create_graph=True)`.
+//
+//   reference sites: distill.py:509-583 (unroll), 584-598 (matching loss), 606 (backward through the unroll)
+//   algorithm:       DESIGN.md section 4 == oracle/distill_ref.py::unrolled_match_manual
+//
+// Forward sweep, step k:   g_k = dL/dtheta(theta_k; Y_b, Xn_b, s),  theta_{k+1} = theta_k - lr g_k   (update fused
+//                          into the dW GEMM epilogues; every activation of the step is kept -- ~12 MB/step)
+// Reverse sweep, step k:   with v = a_{k+1}:  tangent pass of the whole first-order step along theta_dot = v gives
+//                          L_dot = <g_k, v>, H_k v, d/dY, d/dXn, d/ds;   a_k = a_{k+1} - lr H_k v (fused into the
+//                          tangent dW GEMM epilogues), dlr -= L_dot, dY[perm] -= lr dY_dot, ...
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "head_kernels.cuh"
+#include "kernels.h"
+#include "engine.h"
+
+namespace vldd {
+
+namespace {
+
+struct Dims {
+  int N, B, K, dt, d;
+  int64_t P, oW1, ob1, oW2, ob2, og, obt;
+};
+
+Dims make_dims(int N, int B, int K, int dt, int d) {
+  Dims m;
+  m.N = N; m.B = B; m.K = K; m.dt = dt; m.d = d;
+  m.oW1 = 0;
+  m.ob1 = (int64_t)d * dt;
+  m.oW2 = m.ob1 + d;
+  m.ob2 = m.oW2 + (int64_t)d * d;
+  m.og = m.ob2 + d;
+  m.obt = m.og + d;
+  m.P = m.obt + d;
+  return m;
+}
+
+int pick_splits(int M, int N, int Ktot) {
+  const int tiles = ceil_div(M, GBM) * ceil_div(N, GBN);
+  const int nkb = ceil_div(Ktot, GBK);
+  int s = (kNumSMs + tiles - 1) / tiles;
+  const int max_s = nkb / 2 > 0 ? nkb / 2 : 1;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  return s;
+}
+
+struct Saved {  // activations of one forward step, all fp32
+  float *Yb, *Xb, *p, *h, *rhat, *yn, *dyn, *dz, *dr, *df, *dh, *dp;  // [B,dt] [B,d] then [B,d] x10
+  float *rstd, *nz, *q, *lse_r, *lse_c;                               // [B]
+  float *S, *G;                                                       // [B,B]
+};
+
+struct Bump {
+  char* base; size_t off, cap;
+  float* f(size_t n) {
+    size_t bytes = ((n * sizeof(float) + 255) / 256) * 256;
+    float* r = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += bytes;
+    return r;
+  }
+};
+
+struct Work {
+  Saved sv[64];
+  float *traj, *adj0, *adj1, *Xn, *un, *dXn;
+  float *pa, *pb;                      // GEMM partial slabs / raw outputs
+  float *pd, *hd, *rhatd, *ynd, *dzd, *drd, *dfd, *dpd, *t, *nzd, *Sd, *Gd, *rho, *kap, *rowA, *rowB;
+  float *neg_one;                      // device constant -1 (first-order API)
+  void* ml_scratch;
+  size_t bytes;
+};
+
+size_t partial_floats(const Dims& m) {
+  const int B = m.B, d = m.d, dt = m.dt;
+  size_t mx = 0;
+  auto upd = [&](int M, int N, int Kt) {
+    size_t v = (size_t)pick_splits(M, N, Kt) * M * N;
+    if (v > mx) mx = v;
+  };
+  upd(B, d, dt); upd(B, d, d); upd(B, d, 2 * d); upd(B, B, d); upd(B, d, B); upd(B, d, 2 * B); upd(B, dt, d);
+  upd(B, dt, 2 * d);
+  return mx;
+}
+
+void carve(Work& w, const Dims& m, void* base) {
+  Bump b{reinterpret_cast<char*>(base), 0, 0};
+  const size_t Bd = (size_t)m.B * m.d, BB = (size_t)m.B * m.B;
+  w.traj = b.f((size_t)(m.K + 1) * m.P);
+  w.adj0 = b.f(m.P);
+  w.adj1 = b.f(m.P);
+  w.Xn = b.f((size_t)m.N * m.d);
+  w.un = b.f(m.N);
+  w.dXn = b.f((size_t)m.N * m.d);
+  for (int k = 0; k < m.K; ++k) {
+    Saved& s = w.sv[k];
+    s.Yb = b.f((size_t)m.B * m.dt);
+    s.Xb = b.f(Bd); s.p = b.f(Bd); s.h = b.f(Bd); s.rhat = b.f(Bd); s.yn = b.f(Bd); s.dyn = b.f(Bd);
+    s.dz = b.f(Bd); s.dr = b.f(Bd); s.df = b.f(Bd); s.dh = b.f(Bd); s.dp = b.f(Bd);
+    s.rstd = b.f(m.B); s.nz = b.f(m.B); s.q = b.f(m.B); s.lse_r = b.f(m.B); s.lse_c = b.f(m.B);
+    s.S = b.f(BB); s.G = b.f(BB);
+  }
+  const size_t pf = partial_floats(m);
+  w.pa = b.f(pf);
+  w.pb = b.f(pf);
+  w.pd = b.f(Bd); w.hd = b.f(Bd); w.rhatd = b.f(Bd); w.ynd = b.f(Bd); w.dzd = b.f(Bd); w.drd = b.f(Bd);
+  w.dfd = b.f(Bd); w.dpd = b.f(Bd);
+  w.t = b.f(m.B); w.nzd = b.f(m.B); w.rho = b.f(m.B); w.kap = b.f(m.B); w.rowA = b.f(m.B); w.rowB = b.f(m.B);
+  w.Sd = b.f(BB); w.Gd = b.f(BB);
+  w.neg_one = b.f(4);
+  w.ml_scratch = b.f((size_t)match_loss_scratch_bytes() / sizeof(float) + 8);
+  w.bytes = b.off;
+}
+
+__global__ void fill_kernel(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void reduce_slabs_kernel(const float* __restrict__ part, int splits, size_t stride, size_t n,
+                                    float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = sum_slabs(part, splits, stride, i);
+}
+__global__ void __launch_bounds__(256) dot_over_scale_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                             size_t n, const float* __restrict__ scale,
+                                                             float* __restrict__ out) {
+  __shared__ float scratch[34];
+  float acc = 0.f;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) acc = fmaf(a[i], b[i], acc);
+  acc = block_sum<float>(acc, scratch);
+  if (threadIdx.x == 0) *out = acc / (*scale);
+}
+
+inline int ew_grid(size_t n) {
+  size_t g = (n + 255) / 256;
+  const size_t cap = (size_t)kNumSMs * 8;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+#define CHECK_RC(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// One forward (first-order) step.  th_src/th_dst: theta_k -> theta_{k+1} (th_src == nullptr: dst = -lr*g).
+// ---------------------------------------------------------------------------------------------------
+int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float* upd_src, float* upd_dst,
+                 const float* lr, const float* scale, const float* mask, float* ce_out, cudaStream_t st) {
+  const int B = m.B, d = m.d, dt = m.dt;
+  const size_t Bd = (size_t)B * d;
+  const float *W1 = th + m.oW1, *b1 = th + m.ob1, *W2 = th + m.oW2, *b2 = th + m.ob2, *gam = th + m.og, *bet = th + m.obt;
+  // p = Yb W1^T + b1 ; h = gelu(p)
+  int sp = pick_splits(B, d, dt);
+  launch_gemm<true, true>(gemm_ops(s.Yb, dt, W1, dt, B, d, dt), sp, w.pa, EpiStore{}, st);
+  epi_p_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, b1, B, d, s.p, s.h);
+  // f = h W2^T + b2 ; r = mask f + p ; LN ; normalise
+  sp = pick_splits(B, d, d);
+  launch_gemm<true, true>(gemm_ops(s.h, d, W2, d, B, d, d), sp, w.pa, EpiStore{}, st);
+  ln_fwd_kernel<<<B, 256, d * sizeof(float), st>>>(w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr, s.yn,
+                                                   s.rstd, s.nz);
+  // S = scale * Xb Yn^T ; lse ; G ; loss
+  sp = pick_splits(B, B, d);
+  launch_gemm<true, true>(gemm_ops(s.Xb, d, s.yn, d, B, B, d), sp, w.pa, EpiStore{}, st);
+  nce_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, (size_t)B * B, scale, B, s.S, s.lse_r);
+  nce_cols_kernel<<<B, 128, 0, st>>>(s.S, B, s.lse_c);
+  nce_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, B, s.G, ce_out);
+  // dyn_raw[j,:] = sum_i G[i,j] Xb[i,:]
+  launch_gemm<false, false>(gemm_ops(s.G, B, s.Xb, d, B, d, B), 1, nullptr, EpiStore{w.pb, d, 1.0f}, st);
+  norm_ln_bwd_kernel<<<B, 256, 0, st>>>(w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d, s.dyn, s.q, s.dz, s.dr,
+                                        s.df);
+  // dh = df W2 ; dp = dh gelu'(p) + dr
+  sp = pick_splits(B, d, d);
+  launch_gemm<true, false>(gemm_ops(s.df, d, W2, d, B, d, d), sp, w.pa, EpiStore{}, st);
+  epi_dp_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, s.p, s.dr, Bd, s.dh, s.dp);
+  // theta_{k+1}[W2] = theta_k[W2] - lr df^T h ; [W1] = ... - lr dp^T Yb ; small params
+  launch_gemm<false, false>(gemm_ops(s.df, d, s.h, d, d, d, B), 1, nullptr,
+                            EpiAxpy{upd_src ? upd_src + m.oW2 : nullptr, upd_dst + m.oW2, d, lr}, st);
+  launch_gemm<false, false>(gemm_ops(s.dp, d, s.Yb, dt, d, dt, B), 1, nullptr,
+                            EpiAxpy{upd_src ? upd_src + m.oW1 : nullptr, upd_dst + m.oW1, dt, lr}, st);
+  colsum_update_kernel<<<ceil_div(d, 128), 128, 0, st>>>(
+      s.dp, s.df, s.dz, s.rhat, B, d, lr, upd_src ? upd_src + m.ob1 : nullptr, upd_dst + m.ob1,
+      upd_src ? upd_src + m.ob2 : nullptr, upd_dst + m.ob2, upd_src ? upd_src + m.og : nullptr, upd_dst + m.og,
+      upd_src ? upd_src + m.obt : nullptr, upd_dst + m.obt);
+  return check_launch("forward_step");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One reverse step: tangent of the first-order step along theta_dot = v (= a_{k+1}); writes a_k = v - lr H v
+// and accumulates dlr, dscale, dY, dXn.
+// ---------------------------------------------------------------------------------------------------
+int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const float* v, float* a_out,
+                 const float* lr, const float* scale, const float* mask, const int64_t* perm, float* dY, float* dlr,
+                 float* dscale, cudaStream_t st) {
+  const int B = m.B, d = m.d, dt = m.dt;
+  const size_t Bd = (size_t)B * d, BB = (size_t)B * B;
+  const float *W1 = th + m.oW1, *W2 = th + m.oW2, *gam = th + m.og;
+  const float *V1 = v + m.oW1, *c1 = v + m.ob1, *V2 = v + m.oW2, *c2 = v + m.ob2, *gamd = v + m.og, *betd = v + m.obt;
+  // pd = Yb V1^T + c1 ; hd = gelu'(p) pd
+  int sp = pick_splits(B, d, dt);
+  launch_gemm<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), sp, w.pa, EpiStore{}, st);
+  epi_pd_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, c1, s.p, B, d, w.pd, w.hd);
+  // fd = hd W2^T + h V2^T + c2 ; LN / normalise tangents
+  sp = pick_splits(B, d, 2 * d);
+  launch_gemm<true, true>(gemm_ops2(w.hd, d, W2, d, d, s.h, d, V2, d, d, B, d), sp, w.pa, EpiStore{}, st);
+  ln_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz, gam,
+                                                       gamd, betd, d, w.rhatd, w.ynd, w.t, w.nzd);
+  // Sd = scale Xb Ynd^T ; rho, kappa, Gd ; L_dot ; dlr, dscale
+  sp = pick_splits(B, B, d);
+  launch_gemm<true, true>(gemm_ops(s.Xb, d, w.ynd, d, B, B, d), sp, w.pa, EpiStore{}, st);
+  nce_t_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, BB, scale, s.S, s.lse_r, s.G, B, w.Sd, w.rho, w.rowA);
+  nce_t_cols_kernel<<<B, 128, 0, st>>>(s.S, s.lse_c, w.Sd, B, w.kap);
+  nce_t_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, w.Sd, w.rho, w.kap, B, w.Gd, w.rowB);
+  nce_t_finish_kernel<<<1, 128, 0, st>>>(w.rowA, w.rowB, B, lr, scale, dlr, dscale);
+  // dXn_dot = scale (Gd Yn + G Ynd)  ->  dXn[perm] -= lr * scale * raw
+  launch_gemm<true, false>(gemm_ops2(w.Gd, B, s.yn, d, B, s.G, B, w.ynd, d, B, B, d), 1, nullptr,
+                           EpiStore{w.pa, d, 1.0f}, st);
+  scatter_add_rows_kernel<<<B, 256, 0, st>>>(w.pa, 1, Bd, perm, d, lr, scale, w.dXn);
+  // dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
+  launch_gemm<false, false>(gemm_ops(w.Gd, B, s.Xb, d, B, d, B), 1, nullptr, EpiStore{w.pb, d, 1.0f}, st);
+  norm_ln_bwd_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd,
+                                                                s.dz, s.rhat, w.rhatd, s.rstd, w.t, s.dr, gam, gamd,
+                                                                mask, d, w.dzd, w.drd, w.dfd);
+  // dhd = dfd W2 + df V2 ; dpd
+  sp = pick_splits(B, d, 2 * d);
+  launch_gemm<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), sp, w.pa, EpiStore{}, st);
+  epi_dpd_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, s.p, w.pd, s.dh, w.drd, Bd, w.dpd);
+  // dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.)
+  sp = pick_splits(B, dt, 2 * d);
+  launch_gemm<true, false>(gemm_ops2(w.dpd, d, W1, dt, d, s.dp, d, V1, dt, d, B, dt), sp, w.pb, EpiStore{}, st);
+  scatter_add_rows_kernel<<<B, 256, 0, st>>>(w.pb, sp, (size_t)B * dt, perm, dt, lr, nullptr, dY);
+  // a_k = a_{k+1} - lr * H v   (W2, W1 tiles fused into the GEMM epilogues; small params by column sums)
+  launch_gemm<false, false>(gemm_ops2(w.dfd, d, s.h, d, B, s.df, d, w.hd, d, B, d, d), 1, nullptr,
+                            EpiAxpy{v + m.oW2, a_out + m.oW2, d, lr}, st);
+  launch_gemm<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), 1, nullptr,
+                            EpiAxpy{v + m.oW1, a_out + m.oW1, dt, lr}, st);
+  colsum_tangent_update_kernel<<<ceil_div(d, 128), 128, 0, st>>>(
+      w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
+      v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
+  return check_launch("tangent_step");
+}
+
+int validate(int N, int B, int K, int dt, int d) {
+  VLDD_REQUIRE(N > 0 && B > 0 && B <= N, "need 0 < B <= N (got N=%d B=%d)", N, B);
+  VLDD_REQUIRE(K >= 0 && K <= 64, "syn_steps K=%d out of range [0,64]", K);
+  VLDD_REQUIRE(dt > 0 && d > 0, "bad dims dt=%d d=%d", dt, d);
+  VLDD_REQUIRE((size_t)d * sizeof(float) <= 48 * 1024, "projection dim d=%d too large for the row kernels", d);
+  return VLDD_OK;
+}
+
+}  // namespace
+
+size_t unrolled_match_workspace_bytes(int N, int B, int K, int dt, int d) {
+  if (validate(N, B, K, dt, d)) return 0;
+  Work w;
+  carve(w, make_dims(N, B, K, dt, d), nullptr);
+  return w.bytes;
+}
+
+int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, const float* U, const float* lr,
+                   const float* scale, const int64_t* perms, const float* masks, int N, int B, int K, int dt, int d,
+                   float* out5, float* ce, float* dY, float* dU, float* theta_K, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st) {
+  CHECK_RC(validate(N, B, K, dt, d));
+  const Dims m = make_dims(N, B, K, dt, d);
+  Work w;
+  carve(w, m, workspace);
+  if (workspace == nullptr || workspace_bytes < w.bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return VLDD_ERR_WORKSPACE;
+  }
+  const size_t Bd = (size_t)B * d;
+  // one-time set-up of this call
+  VLDD_CUDA(cudaMemsetAsync(w.ml_scratch, 0, 16, st));
+  VLDD_CUDA(cudaMemsetAsync(out5 + 3, 0, 2 * sizeof(float), st));
+  VLDD_CUDA(cudaMemsetAsync(dY, 0, (size_t)N * dt * sizeof(float), st));
+  VLDD_CUDA(cudaMemsetAsync(w.dXn, 0, (size_t)N * d * sizeof(float), st));
+  VLDD_CUDA(cudaMemcpyAsync(w.traj, theta0, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  row_normalise_kernel<<<N, 256, 0, st>>>(U, d, w.Xn, w.un);
+  // forward unroll
+  for (int k = 0; k < K; ++k) {
+    Saved& s = w.sv[k];
+    const int64_t* perm = perms + (size_t)k * B;
+    gather_rows_kernel<<<B, 256, 0, st>>>(Y, perm, dt, s.Yb);
+    gather_rows_kernel<<<B, 256, 0, st>>>(w.Xn, perm, d, s.Xb);
+    const float* th = w.traj + (size_t)k * m.P;
+    CHECK_RC(forward_step(m, w, s, th, th, w.traj + (size_t)(k + 1) * m.P, lr, scale, masks ? masks + k * Bd : nullptr,
+                          ce ? ce + k : nullptr, st));
+  }
+  const float* thK = w.traj + (size_t)K * m.P;
+  CHECK_RC(match_loss_fwd(thK, theta_tgt, theta0, m.P, out5, w.ml_scratch, st));
+  CHECK_RC(match_loss_bwd(thK, theta_tgt, out5, nullptr, w.adj0, m.P, st));
+  if (theta_K) VLDD_CUDA(cudaMemcpyAsync(theta_K, thK, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // reverse sweep
+  float* a_cur = w.adj0;
+  float* a_nxt = w.adj1;
+  for (int k = K - 1; k >= 0; --k) {
+    const float* th = w.traj + (size_t)k * m.P;
+    CHECK_RC(tangent_step(m, w, w.sv[k], th, a_cur, a_nxt, lr, scale, masks ? masks + k * Bd : nullptr,
+                          perms + (size_t)k * B, dY, out5 + 3, out5 + 4, st));
+    float* t = a_cur; a_cur = a_nxt; a_nxt = t;
+  }
+  row_normalise_bwd_kernel<<<N, 256, 0, st>>>(w.Xn, w.un, w.dXn, nullptr, d, dU);
+  return check_launch("unrolled_match");
+}
+
+// First-order contrastive step on the whole batch (config 2): loss, g_theta, dY, dU, dscale.
+size_t contrastive_step_workspace_bytes(int B, int dt, int d) { return unrolled_match_workspace_bytes(B, B, 1, dt, d); }
+
+int contrastive_step(const float* theta, const float* Y, const float* U, const float* scale, const float* mask, int B,
+                     int dt, int d, float* loss, float* g_theta, float* dY, float* dU, float* dscale, void* workspace,
+                     size_t workspace_bytes, cudaStream_t st) {
+  CHECK_RC(validate(B, B, 1, dt, d));
+  const Dims m = make_dims(B, B, 1, dt, d);
+  Work w;
+  carve(w, m, workspace);
+  if (workspace == nullptr || workspace_bytes < w.bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return VLDD_ERR_WORKSPACE;
+  }
+  Saved& s = w.sv[0];
+  const size_t Bd = (size_t)B * d;
+  fill_kernel<<<1, 32, 0, st>>>(w.neg_one, -1.0f, 4);
+  row_normalise_kernel<<<B, 256, 0, st>>>(U, d, w.Xn, w.un);
+  VLDD_CUDA(cudaMemcpyAsync(s.Yb, Y, (size_t)B * dt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  VLDD_CUDA(cudaMemcpyAsync(s.Xb, w.Xn, Bd * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CHECK_RC(forward_step(m, w, s, theta, nullptr, g_theta, w.neg_one, scale, mask, loss, st));
+  // dY = dp W1
+  if (dY) {
+    const int sp = pick_splits(B, dt, d);
+    launch_gemm<true, false>(gemm_ops(s.dp, d, theta + m.oW1, dt, B, dt, d), sp, w.pa, EpiStore{}, st);
+    reduce_slabs_kernel<<<ew_grid((size_t)B * dt), 256, 0, st>>>(w.pa, sp, (size_t)B * dt, (size_t)B * dt, dY);
+  }
+  // dU = normalise_bwd(scale * G Yn)
+  if (dU) {
+    launch_gemm<true, false>(gemm_ops(s.G, B, s.yn, d, B, d, B), 1, nullptr, EpiStore{w.pb, d, 1.0f}, st);
+    row_normalise_bwd_kernel<<<B, 256, 0, st>>>(w.Xn, w.un, w.pb, scale, d, dU);
+  }
+  // dscale = sum(G * S) / scale
+  if (dscale) dot_over_scale_kernel<<<1, 256, 0, st>>>(s.G, s.S, (size_t)B * B, scale, dscale);
+  return check_launch("contrastive_step");
+}
+
+// text_projection forward over `rows` embeddings (eval-mode when mask == nullptr): z = LN(...), zn = z/|z|.
+//   reference: epoch_original.py:77-78 (text head over the cached BERT test embeddings, then normalise)
+size_t proj_head_workspace_bytes(int rows, int dt, int d) {
+  if (rows <= 0 || dt <= 0 || d <= 0) return 0;
+  const size_t Rd = (size_t)rows * d;
+  const size_t s1 = (size_t)pick_splits(rows, d, dt) * Rd, s2 = (size_t)pick_splits(rows, d, d) * Rd;
+  const size_t part = s1 > s2 ? s1 : s2;
+  return (part + 2 * Rd) * sizeof(float) + 1024;
+}
+
+int proj_head_forward(const float* theta, const float* Y, const float* mask, int rows, int dt, int d, float* z,
+                      float* zn, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  VLDD_REQUIRE(rows > 0 && dt > 0 && d > 0, "bad dims rows=%d dt=%d d=%d", rows, dt, d);
+  VLDD_REQUIRE((size_t)d * sizeof(float) <= 48 * 1024, "projection dim d=%d too large for the row kernels", d);
+  const size_t need = proj_head_workspace_bytes(rows, dt, d);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    return VLDD_ERR_WORKSPACE;
+  }
+  const Dims m = make_dims(rows, rows, 0, dt, d);
+  const size_t Rd = (size_t)rows * d;
+  float* p = reinterpret_cast<float*>(workspace);
+  float* h = p + Rd;
+  float* part = h + Rd;
+  int sp = pick_splits(rows, d, dt);
+  launch_gemm<true, true>(gemm_ops(Y, dt, theta + m.oW1, dt, rows, d, dt), sp, part, EpiStore{}, st);
+  epi_p_kernel<<<ew_grid(Rd), 256, 0, st>>>(part, sp, Rd, theta + m.ob1, rows, d, p, h);
+  sp = pick_splits(rows, d, d);
+  launch_gemm<true, true>(gemm_ops(h, d, theta + m.oW2, d, rows, d, d), sp, part, EpiStore{}, st);
+  ln_fwd_kernel<<<rows, 256, d * sizeof(float), st>>>(part, sp, Rd, theta + m.ob2, mask, p, theta + m.og,
+                                                      theta + m.obt, d, nullptr, z, zn, nullptr, nullptr);
+  return check_launch("proj_head_forward");
+}
+
+}  // namespace vldd

@@ -1,0 +1,491 @@
+// Row-wise / element-wise kernels of the text_projection head and the bidirectional InfoNCE loss, in primal
+// and tangent (forward-over-reverse) form.  Every formula is the one in oracle/distill_ref.py
+// (step_first_order / step_tangent), which is checked against torch double-backward in float64.
+//
+//   reference sites: networks.py:639-646 (ProjectionHead.forward), distill.py:546 (row normalise),
+//   distill.py:548-551 (logits + 2x cross_entropy), distill.py:562-567 (autograd.grad create_graph=True).
+//
+// GEMM results arrive as split-K partial slabs [splits][rows*cols]; the consumer sums the slabs in fixed
+// order (deterministic) and applies the fused math.
+#pragma once
+#include "common.cuh"
+
+namespace vldd {
+
+constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default (networks.py:637)
+
+__device__ __forceinline__ float sum_slabs(const float* __restrict__ part, int splits, size_t stride, size_t idx) {
+  float v = part[idx];
+  for (int s = 1; s < splits; ++s) v += part[(size_t)s * stride + idx];
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// primal, forward
+// ------------------------------------------------------------------------------------------------
+// p = Y W1^T + b1 ; h = gelu(p)                                   [rows x d]
+__global__ void __launch_bounds__(256) epi_p_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                    const float* __restrict__ b1, int rows, int d,
+                                                    float* __restrict__ p, float* __restrict__ h) {
+  const size_t n = (size_t)rows * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d);
+    const float pv = sum_slabs(part, splits, stride, i) + b1[c];
+    float phi, d1, d2;
+    gelu_parts(pv, phi, d1, d2);
+    p[i] = pv;
+    h[i] = phi;
+  }
+}
+
+// r = mask*(h W2^T + b2) + p ; rhat = LN-normalised r ; z = gamma*rhat + beta ; yn = z/|z|        one CTA per row
+// outputs: rhat (nullable), z (nullable), yn (nullable), rstd[row], nz[row] (nullable)
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                     const float* __restrict__ b2, const float* __restrict__ mask,
+                                                     const float* __restrict__ p, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, int d,
+                                                     float* __restrict__ rhat, float* __restrict__ z_out,
+                                                     float* __restrict__ yn, float* __restrict__ rstd_out,
+                                                     float* __restrict__ nz_out) {
+  extern __shared__ float rbuf[];  // d floats
+  __shared__ float scratch[34];
+  const int row = blockIdx.x;
+  const size_t base = (size_t)row * d;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float f = sum_slabs(part, splits, stride, base + j) + b2[j];
+    if (mask) f *= mask[base + j];
+    const float r = f + p[base + j];
+    rbuf[j] = r;
+    s += r;
+  }
+  const float mu = block_sum<float>(s, scratch) / d;
+  float v = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float c = rbuf[j] - mu;
+    v = fmaf(c, c, v);
+  }
+  const float rstd = rsqrtf(block_sum<float>(v, scratch) / d + kLnEps);
+  float zz = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float rh = (rbuf[j] - mu) * rstd;
+    const float z = fmaf(gamma[j], rh, beta[j]);
+    if (rhat) rhat[base + j] = rh;
+    rbuf[j] = z;
+    zz = fmaf(z, z, zz);
+  }
+  const float nz = sqrtf(block_sum<float>(zz, scratch));
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float z = rbuf[j];
+    if (z_out) z_out[base + j] = z;
+    if (yn) yn[base + j] = z / nz;
+  }
+  if (threadIdx.x == 0) {
+    if (rstd_out) rstd_out[row] = rstd;
+    if (nz_out) nz_out[row] = nz;
+  }
+}
+
+// x / |x| per row (distill.py:533 on the image-encoder output); also stores |x|
+__global__ void __launch_bounds__(256) row_normalise_kernel(const float* __restrict__ x, int d, float* __restrict__ xn,
+                                                            float* __restrict__ norm_out) {
+  __shared__ float scratch[34];
+  const size_t base = (size_t)blockIdx.x * d;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) s = fmaf(x[base + j], x[base + j], s);
+  const float n = sqrtf(block_sum<float>(s, scratch));
+  for (int j = threadIdx.x; j < d; j += blockDim.x) xn[base + j] = x[base + j] / n;
+  if (threadIdx.x == 0 && norm_out) norm_out[blockIdx.x] = n;
+}
+
+// dU = c (dXn - xn <xn, dXn>) / |u|  with c = scale ? *scale : 1      backward of the row normalisation
+__global__ void __launch_bounds__(256) row_normalise_bwd_kernel(const float* __restrict__ xn,
+                                                                const float* __restrict__ norm,
+                                                                const float* __restrict__ dxn,
+                                                                const float* __restrict__ scale, int d,
+                                                                float* __restrict__ dx) {
+  __shared__ float scratch[34];
+  const size_t base = (size_t)blockIdx.x * d;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) s = fmaf(xn[base + j], dxn[base + j], s);
+  const float q = block_sum<float>(s, scratch);
+  const float inv = (scale ? *scale : 1.0f) / norm[blockIdx.x];
+  for (int j = threadIdx.x; j < d; j += blockDim.x) dx[base + j] = (dxn[base + j] - xn[base + j] * q) * inv;
+}
+
+// dst[b,:] = src[idx[b],:]
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                                                          int cols, float* __restrict__ dst) {
+  const size_t s = (size_t)idx[blockIdx.x] * cols, t = (size_t)blockIdx.x * cols;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[t + j] = src[s + j];
+}
+
+// dst[idx[b],:] += coef * sum_slabs(part)[b,:]   with coef = -(*lr) * (scale ? *scale : 1)
+// (indices inside one step are unique -- randperm -- so no atomics are needed)
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                               const int64_t* __restrict__ idx, int cols,
+                                                               const float* __restrict__ lr,
+                                                               const float* __restrict__ scale,
+                                                               float* __restrict__ dst) {
+  const float coef = -(*lr) * (scale ? *scale : 1.0f);
+  const size_t s = (size_t)blockIdx.x * cols, t = (size_t)idx[blockIdx.x] * cols;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[t + j] += coef * sum_slabs(part, splits, stride, s + j);
+}
+
+// ------------------------------------------------------------------------------------------------
+// InfoNCE, primal.  S = scale * Xn Yn^T  (B x B, small, L2-resident)
+// ------------------------------------------------------------------------------------------------
+// row i: S[i,:] = scale * sum_slabs ; lse_r[i]
+__global__ void __launch_bounds__(128) nce_rows_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                       const float* __restrict__ scale, int B, float* __restrict__ S,
+                                                       float* __restrict__ lse_r) {
+  __shared__ float scratch[34];
+  const int i = blockIdx.x;
+  const float sc = *scale;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    const float v = sc * sum_slabs(part, splits, stride, (size_t)i * B + j);
+    S[(size_t)i * B + j] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = block_max(mx, scratch);
+  float se = 0.f;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) se += expf(S[(size_t)i * B + j] - mx);
+  se = block_sum<float>(se, scratch);
+  if (threadIdx.x == 0) lse_r[i] = mx + logf(se);
+}
+// column j: lse_c[j]
+__global__ void __launch_bounds__(128) nce_cols_kernel(const float* __restrict__ S, int B, float* __restrict__ lse_c) {
+  __shared__ float scratch[34];
+  const int j = blockIdx.x;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) mx = fmaxf(mx, S[(size_t)i * B + j]);
+  mx = block_max(mx, scratch);
+  float se = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) se += expf(S[(size_t)i * B + j] - mx);
+  se = block_sum<float>(se, scratch);
+  if (threadIdx.x == 0) lse_c[j] = mx + logf(se);
+}
+// G = (softmax_rows + softmax_cols - 2I) / (2B); block 0 also writes the loss
+__global__ void __launch_bounds__(128) nce_grad_kernel(const float* __restrict__ S, const float* __restrict__ lse_r,
+                                                       const float* __restrict__ lse_c, int B, float* __restrict__ G,
+                                                       float* __restrict__ loss_out) {
+  __shared__ float scratch[34];
+  const int i = blockIdx.x;
+  const float inv2B = 0.5f / B, lr_i = lse_r[i];
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    const float s = S[(size_t)i * B + j];
+    float g = expf(s - lr_i) + expf(s - lse_c[j]);
+    if (j == i) g -= 2.0f;
+    G[(size_t)i * B + j] = g * inv2B;
+  }
+  if (blockIdx.x == 0) {
+    float acc = 0.f;
+    for (int r = threadIdx.x; r < B; r += blockDim.x) acc += (lse_r[r] - S[(size_t)r * B + r]) + (lse_c[r] - S[(size_t)r * B + r]);
+    acc = block_sum<float>(acc, scratch);
+    if (threadIdx.x == 0 && loss_out) *loss_out = acc * inv2B;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// primal, backward
+// ------------------------------------------------------------------------------------------------
+// dyn = scale * raw ; q = <yn,dyn> ; dz = (dyn - yn q)/nz ; drhat = gamma dz ; dr = rstd (drhat - m1 - rhat m2) ; df = mask dr
+__global__ void __launch_bounds__(256) norm_ln_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ scale,
+                                                          const float* __restrict__ yn, const float* __restrict__ nz_p,
+                                                          const float* __restrict__ rhat, const float* __restrict__ rstd_p,
+                                                          const float* __restrict__ gamma, const float* __restrict__ mask,
+                                                          int d, float* __restrict__ dyn, float* __restrict__ q_out,
+                                                          float* __restrict__ dz, float* __restrict__ dr,
+                                                          float* __restrict__ df) {
+  __shared__ float scratch[34];
+  const int row = blockIdx.x;
+  const size_t base = (size_t)row * d;
+  const float sc = *scale, nz = nz_p[row], rstd = rstd_p[row];
+  float s = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float v = sc * raw[base + j];
+    dyn[base + j] = v;
+    s = fmaf(yn[base + j], v, s);
+  }
+  const float q = block_sum<float>(s, scratch);
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float v = (dyn[base + j] - yn[base + j] * q) / nz;
+    dz[base + j] = v;
+    const float drh = gamma[j] * v;
+    s1 += drh;
+    s2 = fmaf(drh, rhat[base + j], s2);
+  }
+  const float m1 = block_sum<float>(s1, scratch) / d;
+  const float m2 = block_sum<float>(s2, scratch) / d;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float drh = gamma[j] * dz[base + j];
+    const float v = rstd * (drh - m1 - rhat[base + j] * m2);
+    dr[base + j] = v;
+    df[base + j] = mask ? v * mask[base + j] : v;
+  }
+  if (threadIdx.x == 0) q_out[row] = q;
+}
+
+// dh = df W2 ; dp = dh * gelu'(p) + dr
+__global__ void __launch_bounds__(256) epi_dp_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                     const float* __restrict__ p, const float* __restrict__ dr,
+                                                     size_t n, float* __restrict__ dh, float* __restrict__ dp) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = sum_slabs(part, splits, stride, i);
+    float phi, d1, d2;
+    gelu_parts(p[i], phi, d1, d2);
+    dh[i] = v;
+    dp[i] = fmaf(v, d1, dr[i]);
+  }
+}
+
+// Column sums over the batch and the fused update of the small parameters:
+//   db1 = sum dp ; db2 = sum df ; dgamma = sum dz*rhat ; dbeta = sum dz ;  dst = src - lr * grad   (src nullable = 0)
+__global__ void __launch_bounds__(128) colsum_update_kernel(const float* __restrict__ dp, const float* __restrict__ df,
+                                                            const float* __restrict__ dz, const float* __restrict__ rhat,
+                                                            int B, int d, const float* __restrict__ lr,
+                                                            const float* __restrict__ src_b1, float* __restrict__ dst_b1,
+                                                            const float* __restrict__ src_b2, float* __restrict__ dst_b2,
+                                                            const float* __restrict__ src_g, float* __restrict__ dst_g,
+                                                            const float* __restrict__ src_b, float* __restrict__ dst_b) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d) return;
+  float a1 = 0.f, a2 = 0.f, ag = 0.f, ab = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const size_t i = (size_t)b * d + n;
+    a1 += dp[i];
+    a2 += df[i];
+    const float z = dz[i];
+    ag = fmaf(z, rhat[i], ag);
+    ab += z;
+  }
+  const float l = *lr;
+  dst_b1[n] = (src_b1 ? src_b1[n] : 0.f) - l * a1;
+  dst_b2[n] = (src_b2 ? src_b2[n] : 0.f) - l * a2;
+  dst_g[n] = (src_g ? src_g[n] : 0.f) - l * ag;
+  dst_b[n] = (src_b ? src_b[n] : 0.f) - l * ab;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tangent, forward
+// ------------------------------------------------------------------------------------------------
+// pd = Y V1^T + c1 ; hd = gelu'(p) pd
+__global__ void __launch_bounds__(256) epi_pd_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                     const float* __restrict__ c1, const float* __restrict__ p, int rows,
+                                                     int d, float* __restrict__ pd, float* __restrict__ hd) {
+  const size_t n = (size_t)rows * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d);
+    const float v = sum_slabs(part, splits, stride, i) + c1[c];
+    float phi, d1, d2;
+    gelu_parts(p[i], phi, d1, d2);
+    pd[i] = v;
+    hd[i] = d1 * v;
+  }
+}
+
+// fd = (hd W2^T + h V2^T) + c2 ; rd = mask fd + pd ; t = mean(rhat rd) ; rhatd = rstd (rd - mean rd - rhat t)
+// zd = gammad rhat + gamma rhatd + betad ; nzd = <yn, zd> ; ynd = (zd - yn nzd)/nz
+__global__ void __launch_bounds__(256) ln_tangent_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                         const float* __restrict__ c2, const float* __restrict__ mask,
+                                                         const float* __restrict__ pd, const float* __restrict__ rhat,
+                                                         const float* __restrict__ rstd_p, const float* __restrict__ yn,
+                                                         const float* __restrict__ nz_p, const float* __restrict__ gamma,
+                                                         const float* __restrict__ gammad, const float* __restrict__ betad,
+                                                         int d, float* __restrict__ rhatd, float* __restrict__ ynd,
+                                                         float* __restrict__ t_out, float* __restrict__ nzd_out) {
+  extern __shared__ float buf[];  // d floats
+  __shared__ float scratch[34];
+  const int row = blockIdx.x;
+  const size_t base = (size_t)row * d;
+  const float rstd = rstd_p[row], nz = nz_p[row];
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float f = sum_slabs(part, splits, stride, base + j) + c2[j];
+    if (mask) f *= mask[base + j];
+    const float rd = f + pd[base + j];
+    buf[j] = rd;
+    s1 += rd;
+    s2 = fmaf(rhat[base + j], rd, s2);
+  }
+  const float mrd = block_sum<float>(s1, scratch) / d;
+  const float t = block_sum<float>(s2, scratch) / d;
+  float s3 = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float rh = rhat[base + j];
+    const float rhd = rstd * (buf[j] - mrd - rh * t);
+    rhatd[base + j] = rhd;
+    const float zd = gammad[j] * rh + gamma[j] * rhd + betad[j];
+    buf[j] = zd;
+    s3 = fmaf(yn[base + j], zd, s3);
+  }
+  const float nzd = block_sum<float>(s3, scratch);
+  for (int j = threadIdx.x; j < d; j += blockDim.x) ynd[base + j] = (buf[j] - yn[base + j] * nzd) / nz;
+  if (threadIdx.x == 0) { t_out[row] = t; nzd_out[row] = nzd; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// InfoNCE, tangent
+// ------------------------------------------------------------------------------------------------
+// row i: Sd[i,:] = scale * slabs ; rho_i = sum_j Pr_ij Sd_ij ; rowLd[i] = sum_j G_ij Sd_ij
+__global__ void __launch_bounds__(128) nce_t_rows_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                         const float* __restrict__ scale, const float* __restrict__ S,
+                                                         const float* __restrict__ lse_r, const float* __restrict__ G,
+                                                         int B, float* __restrict__ Sd, float* __restrict__ rho,
+                                                         float* __restrict__ rowLd) {
+  __shared__ float scratch[34];
+  const int i = blockIdx.x;
+  const float sc = *scale, l = lse_r[i];
+  float a = 0.f, b = 0.f;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    const size_t ij = (size_t)i * B + j;
+    const float v = sc * sum_slabs(part, splits, stride, ij);
+    Sd[ij] = v;
+    a = fmaf(expf(S[ij] - l), v, a);
+    b = fmaf(G[ij], v, b);
+  }
+  a = block_sum<float>(a, scratch);
+  b = block_sum<float>(b, scratch);
+  if (threadIdx.x == 0) { rho[i] = a; rowLd[i] = b; }
+}
+// column j: kap_j = sum_i Pc_ij Sd_ij
+__global__ void __launch_bounds__(128) nce_t_cols_kernel(const float* __restrict__ S, const float* __restrict__ lse_c,
+                                                         const float* __restrict__ Sd, int B, float* __restrict__ kap) {
+  __shared__ float scratch[34];
+  const int j = blockIdx.x;
+  const float l = lse_c[j];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const size_t ij = (size_t)i * B + j;
+    a = fmaf(expf(S[ij] - l), Sd[ij], a);
+  }
+  a = block_sum<float>(a, scratch);
+  if (threadIdx.x == 0) kap[j] = a;
+}
+// Gd = (Pr (Sd - rho_i) + Pc (Sd - kap_j)) / (2B) ; rowGdS[i] = sum_j Gd_ij S_ij
+__global__ void __launch_bounds__(128) nce_t_grad_kernel(const float* __restrict__ S, const float* __restrict__ lse_r,
+                                                         const float* __restrict__ lse_c, const float* __restrict__ Sd,
+                                                         const float* __restrict__ rho, const float* __restrict__ kap,
+                                                         int B, float* __restrict__ Gd, float* __restrict__ rowGdS) {
+  __shared__ float scratch[34];
+  const int i = blockIdx.x;
+  const float inv2B = 0.5f / B, l = lse_r[i], rh = rho[i];
+  float a = 0.f;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    const size_t ij = (size_t)i * B + j;
+    const float s = S[ij], sd = Sd[ij];
+    const float g = (expf(s - l) * (sd - rh) + expf(s - lse_c[j]) * (sd - kap[j])) * inv2B;
+    Gd[ij] = g;
+    a = fmaf(g, s, a);
+  }
+  a = block_sum<float>(a, scratch);
+  if (threadIdx.x == 0) rowGdS[i] = a;
+}
+// one block: Ld = sum rowLd ; dlr -= Ld ; dscale -= lr * (sum rowGdS + Ld) / scale
+__global__ void __launch_bounds__(128) nce_t_finish_kernel(const float* __restrict__ rowLd,
+                                                           const float* __restrict__ rowGdS, int B,
+                                                           const float* __restrict__ lr, const float* __restrict__ scale,
+                                                           float* __restrict__ dlr, float* __restrict__ dscale) {
+  __shared__ float scratch[34];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) { a += rowLd[i]; b += rowGdS[i]; }
+  a = block_sum<float>(a, scratch);
+  b = block_sum<float>(b, scratch);
+  if (threadIdx.x == 0) {
+    *dlr -= a;
+    *dscale -= (*lr) * (b + a) / (*scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tangent, backward
+// ------------------------------------------------------------------------------------------------
+// dynd = scale*raw ; qd = <ynd,dyn> + <yn,dynd> ; dzd = (dynd - ynd q - yn qd)/nz - dz nzd/nz
+// drhatd = gammad dz + gamma dzd ; drd = -(rstd t) dr + rstd (drhatd - m1d - rhatd m2 - rhat m2d) ; dfd = mask drd
+__global__ void __launch_bounds__(256) norm_ln_bwd_tangent_kernel(
+    const float* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ yn,
+    const float* __restrict__ ynd, const float* __restrict__ dyn, const float* __restrict__ q_p,
+    const float* __restrict__ nz_p, const float* __restrict__ nzd_p, const float* __restrict__ dz,
+    const float* __restrict__ rhat, const float* __restrict__ rhatd, const float* __restrict__ rstd_p,
+    const float* __restrict__ t_p, const float* __restrict__ dr, const float* __restrict__ gamma,
+    const float* __restrict__ gammad, const float* __restrict__ mask, int d, float* __restrict__ dzd,
+    float* __restrict__ drd, float* __restrict__ dfd) {
+  extern __shared__ float buf[];  // d floats (dynd, then drhatd)
+  __shared__ float scratch[34];
+  const int row = blockIdx.x;
+  const size_t base = (size_t)row * d;
+  const float sc = *scale, nz = nz_p[row], nzd = nzd_p[row], q = q_p[row], rstd = rstd_p[row], t = t_p[row];
+  float s = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float v = sc * raw[base + j];
+    buf[j] = v;
+    s = fmaf(ynd[base + j], dyn[base + j], s);
+    s = fmaf(yn[base + j], v, s);
+  }
+  const float qd = block_sum<float>(s, scratch);
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const float inz = 1.0f / nz;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float dzv = dz[base + j];
+    const float v = (buf[j] - ynd[base + j] * q - yn[base + j] * qd) * inz - dzv * (nzd * inz);
+    dzd[base + j] = v;
+    const float drh = gamma[j] * dzv;
+    const float drhd = gammad[j] * dzv + gamma[j] * v;
+    buf[j] = drhd;
+    s1 += drhd;
+    s2 = fmaf(drhd, rhat[base + j], s2);
+    s2 = fmaf(drh, rhatd[base + j], s2);
+    s3 = fmaf(drh, rhat[base + j], s3);
+  }
+  const float m1d = block_sum<float>(s1, scratch) / d;
+  const float m2d = block_sum<float>(s2, scratch) / d;
+  const float m2 = block_sum<float>(s3, scratch) / d;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float v = -(rstd * t) * dr[base + j] + rstd * (buf[j] - m1d - rhatd[base + j] * m2 - rhat[base + j] * m2d);
+    drd[base + j] = v;
+    dfd[base + j] = mask ? v * mask[base + j] : v;
+  }
+}
+
+// dhd = dfd W2 + df V2 ; dpd = dhd gelu'(p) + dh gelu''(p) pd + drd
+__global__ void __launch_bounds__(256) epi_dpd_kernel(const float* __restrict__ part, int splits, size_t stride,
+                                                      const float* __restrict__ p, const float* __restrict__ pd,
+                                                      const float* __restrict__ dh, const float* __restrict__ drd,
+                                                      size_t n, float* __restrict__ dpd) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = sum_slabs(part, splits, stride, i);
+    float phi, d1, d2;
+    gelu_parts(p[i], phi, d1, d2);
+    dpd[i] = fmaf(v, d1, fmaf(dh[i] * d2, pd[i], drd[i]));
+  }
+}
+
+// db1d = sum dpd ; db2d = sum dfd ; dgammad = sum (dzd rhat + dz rhatd) ; dbetad = sum dzd ;  dst = src - lr * (.)
+__global__ void __launch_bounds__(128) colsum_tangent_update_kernel(
+    const float* __restrict__ dpd, const float* __restrict__ dfd, const float* __restrict__ dzd,
+    const float* __restrict__ dz, const float* __restrict__ rhat, const float* __restrict__ rhatd, int B, int d,
+    const float* __restrict__ lr, const float* __restrict__ src_b1, float* __restrict__ dst_b1,
+    const float* __restrict__ src_b2, float* __restrict__ dst_b2, const float* __restrict__ src_g,
+    float* __restrict__ dst_g, const float* __restrict__ src_b, float* __restrict__ dst_b) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d) return;
+  float a1 = 0.f, a2 = 0.f, ag = 0.f, ab = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const size_t i = (size_t)b * d + n;
+    a1 += dpd[i];
+    a2 += dfd[i];
+    const float zd = dzd[i];
+    ag = fmaf(zd, rhat[i], ag);
+    ag = fmaf(dz[i], rhatd[i], ag);
+    ab += zd;
+  }
+  const float l = *lr;
+  dst_b1[n] = src_b1[n] - l * a1;
+  dst_b2[n] = src_b2[n] - l * a2;
+  dst_g[n] = src_g[n] - l * ag;
+  dst_b[n] = src_b[n] - l * ab;
+}
+
+}  // namespace vldd

@@ -1,0 +1,26 @@
+// Internal C++ launcher declarations (the public C ABI is include/vldd_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vldd {
+
+// streaming.cu
+int flat_sgd_step(const float* theta, const float* grad, const float* lr, float* out, int64_t n, cudaStream_t st);
+int64_t match_loss_scratch_bytes();
+int match_loss_fwd(const float* thK, const float* tgt, const float* th0, int64_t n, float* out3, void* scratch,
+                   cudaStream_t st);
+int match_loss_bwd(const float* thK, const float* tgt, const float* num_den, const float* gout, float* a, int64_t n,
+                   cudaStream_t st);
+int momentum_sgd(float* p, const float* g, float* buf, float lr, float momentum, int first, int64_t n,
+                 cudaStream_t st);
+
+// retrieval.cu
+int ranks_rows(const float* S, int64_t ld, int nrows, int ncols, const int32_t* gt_ptr, const int32_t* gt_idx,
+               int32_t* ranks, cudaStream_t st);
+int recall_counts(const int32_t* ranks, int n, int32_t* counts3, cudaStream_t st);
+int sim_scores(const float* img, const float* txt, int I, int T, int D, float scale, float* S_i2t, float* S_t2i,
+               cudaStream_t st);
+int topk_fill_rows(const float* S, float* out, int nrows, int ncols, int k, float fill, cudaStream_t st);
+
+}  // namespace vldd

@@ -1,0 +1,212 @@
+// Retrieval scoring (Path 2): rank of the ground-truth item per query row, recall@{1,5,10} counts,
+// the similarity GEMM and the reference's top-k/-100 fill.
+//
+//   reference sites: epoch.py:219-244 / epoch_original.py:115-161 (itm_eval), epoch_original.py:94-105 (sims, topk fill)
+//
+// Rank definition (deterministic form of np.argsort(row)[::-1], ties broken by index -- see oracle/retrieval_ref.py):
+//   rank(c) = #{j : s_j > s_c} + #{j < c : s_j == s_c};  i2t takes the minimum over the image's GT captions,
+//   which is the rank of the GT caption with the highest score (lowest index among equals).
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels.h"
+
+namespace vldd {
+
+// One CTA per query row.  The row is read from HBM exactly once (4 B / pair); the <=C ground-truth entries are
+// gathered first (a few extra sectors).  Integer result => bit-exact by construction.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) ranks_rows_kernel(const float* __restrict__ S, int64_t ld, int ncols,
+                                                             const int32_t* __restrict__ gt_ptr,
+                                                             const int32_t* __restrict__ gt_idx,
+                                                             int32_t* __restrict__ ranks, int vec) {
+  __shared__ int scratch[34];
+  __shared__ float s_best;
+  __shared__ int c_best;
+  const int r = blockIdx.x;
+  const float* __restrict__ row = S + (size_t)r * ld;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int beg = gt_ptr ? gt_ptr[r] : r, end = gt_ptr ? gt_ptr[r + 1] : r + 1;
+    float bs = -INFINITY;
+    int bc = INT_MAX;
+    bool any = false;
+    for (int e = beg + lane; e < end; e += 32) {
+      const int c = gt_idx[e];
+      if (c < 0 || c >= ncols) continue;
+      const float s = row[c];
+      if (!any || s > bs || (s == bs && c < bc)) { bs = s; bc = c; any = true; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      const bool oa = __shfl_xor_sync(0xffffffffu, (int)any, o);
+      if (oa && (!any || os > bs || (os == bs && oc < bc))) { bs = os; bc = oc; any = true; }
+    }
+    if (lane == 0) { s_best = bs; c_best = any ? bc : -1; }
+  }
+  __syncthreads();
+  const float sg = s_best;
+  const int cg = c_best;
+  if (cg < 0) {  // no valid ground truth for this row: never retrieved
+    if (threadIdx.x == 0) ranks[r] = ncols;
+    return;
+  }
+  int cnt = 0;
+  if (vec) {
+    const int n4 = ncols >> 2;
+    for (int i = threadIdx.x; i < n4; i += THREADS) {
+      const float4 v = ldg_stream4(row + 4 * i);
+      const int j = 4 * i;
+      cnt += (v.x > sg) + (v.x == sg && j + 0 < cg);
+      cnt += (v.y > sg) + (v.y == sg && j + 1 < cg);
+      cnt += (v.z > sg) + (v.z == sg && j + 2 < cg);
+      cnt += (v.w > sg) + (v.w == sg && j + 3 < cg);
+    }
+    for (int j = (n4 << 2) + threadIdx.x; j < ncols; j += THREADS) {
+      const float v = row[j];
+      cnt += (v > sg) + (v == sg && j < cg);
+    }
+  } else {
+    for (int j = threadIdx.x; j < ncols; j += THREADS) {
+      const float v = row[j];
+      cnt += (v > sg) + (v == sg && j < cg);
+    }
+  }
+  const int total = block_sum<int>(cnt, scratch);
+  if (threadIdx.x == 0) ranks[r] = total;
+}
+
+int ranks_rows(const float* S, int64_t ld, int nrows, int ncols, const int32_t* gt_ptr, const int32_t* gt_idx,
+               int32_t* ranks, cudaStream_t st) {
+  if (nrows <= 0) return VLDD_OK;
+  const int vec = aligned16(S) && (ld % 4 == 0);
+  if (ncols > 4096)
+    ranks_rows_kernel<256><<<nrows, 256, 0, st>>>(S, ld, ncols, gt_ptr, gt_idx, ranks, vec);
+  else
+    ranks_rows_kernel<128><<<nrows, 128, 0, st>>>(S, ld, ncols, gt_ptr, gt_idx, ranks, vec);
+  return check_launch("ranks_rows");
+}
+
+// counts3 += (#ranks<1, #ranks<5, #ranks<10)     (epoch.py:227-229,236-238)
+__global__ void __launch_bounds__(256) recall_counts_kernel(const int32_t* __restrict__ ranks, int n,
+                                                            int32_t* __restrict__ counts3) {
+  __shared__ int scratch[34];
+  int c1 = 0, c5 = 0, c10 = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = ranks[i];
+    c1 += r < 1; c5 += r < 5; c10 += r < 10;
+  }
+  c1 = block_sum<int>(c1, scratch);
+  c5 = block_sum<int>(c5, scratch);
+  c10 = block_sum<int>(c10, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(counts3 + 0, c1);
+    atomicAdd(counts3 + 1, c5);
+    atomicAdd(counts3 + 2, c10);
+  }
+}
+
+int recall_counts(const int32_t* ranks, int n, int32_t* counts3, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(counts3, 0, 3 * sizeof(int32_t), st);
+  if (e != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); return VLDD_ERR_CUDA; }
+  if (n <= 0) return VLDD_OK;
+  int grid = ceil_div(n, 256);
+  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+  recall_counts_kernel<<<grid, 256, 0, st>>>(ranks, n, counts3);
+  return check_launch("recall_counts");
+}
+
+// S_i2t[i,t] = scale * <img_i, txt_t>;  S_t2i = transpose (second GEMM with swapped operands so both stores coalesce)
+int sim_scores(const float* img, const float* txt, int I, int T, int D, float scale, float* S_i2t, float* S_t2i,
+               cudaStream_t st) {
+  if (I <= 0 || T <= 0) return VLDD_OK;
+  if (S_i2t) {
+    GemmOperands g = gemm_ops(img, D, txt, D, I, T, D);
+    launch_gemm<true, true>(g, 1, nullptr, EpiStore{S_i2t, T, scale}, st);
+    int rc = check_launch("sim_scores i2t");
+    if (rc) return rc;
+  }
+  if (S_t2i) {
+    GemmOperands g = gemm_ops(txt, D, img, D, T, I, D);
+    launch_gemm<true, true>(g, 1, nullptr, EpiStore{S_t2i, I, scale}, st);
+    int rc = check_launch("sim_scores t2i");
+    if (rc) return rc;
+  }
+  return VLDD_OK;
+}
+
+// Keep each row's k largest entries, everything else := fill (epoch_original.py:95-105).
+// Radix select on the order-preserving integer image of the float, 4 passes of 8 bits, one CTA per row;
+// among entries equal to the k-th value the lower column indices are kept (stable, as the oracle does).
+__device__ __forceinline__ unsigned int float_key(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // larger float -> larger key
+}
+
+__global__ void __launch_bounds__(256) topk_fill_rows_kernel(const float* __restrict__ S, float* __restrict__ out,
+                                                             int ncols, int k, float fill) {
+  __shared__ int hist[256];
+  __shared__ unsigned int sel_prefix;
+  __shared__ int sel_remaining;
+  __shared__ int tie_base[257];
+  const float* __restrict__ row = S + (size_t)blockIdx.x * ncols;
+  float* __restrict__ orow = out + (size_t)blockIdx.x * ncols;
+  if (k >= ncols) {
+    for (int j = threadIdx.x; j < ncols; j += blockDim.x) orow[j] = row[j];
+    return;
+  }
+  unsigned int prefix = 0, mask = 0;
+  int remaining = k;  // how many still to take among keys matching the prefix
+  for (int pass = 3; pass >= 0; --pass) {
+    const int shift = pass * 8;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < ncols; j += blockDim.x) {
+      const unsigned int key = float_key(row[j]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int rem = remaining, b = 255;
+      for (; b > 0; --b) {
+        if (hist[b] >= rem) break;
+        rem -= hist[b];
+      }
+      sel_prefix = prefix | ((unsigned int)b << shift);
+      sel_remaining = rem;
+    }
+    __syncthreads();
+    prefix = sel_prefix;
+    remaining = sel_remaining;
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  // prefix == key of the k-th largest; take every key > prefix and the first `remaining` (by column) keys == prefix
+  const int chunk = (ncols + blockDim.x - 1) / blockDim.x;
+  const int j0 = threadIdx.x * chunk, j1 = min(ncols, j0 + chunk);
+  int ties = 0;
+  for (int j = j0; j < j1; ++j) ties += float_key(row[j]) == prefix;
+  tie_base[threadIdx.x + 1] = ties;
+  if (threadIdx.x == 0) tie_base[0] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int t = 1; t <= (int)blockDim.x; ++t) tie_base[t] += tie_base[t - 1];
+  __syncthreads();
+  int seen = tie_base[threadIdx.x];
+  for (int j = j0; j < j1; ++j) {
+    const float v = row[j];
+    const unsigned int key = float_key(v);
+    bool keep = key > prefix;
+    if (key == prefix) { keep = seen < remaining; ++seen; }
+    orow[j] = keep ? v : fill;
+  }
+}
+
+int topk_fill_rows(const float* S, float* out, int nrows, int ncols, int k, float fill, cudaStream_t st) {
+  if (nrows <= 0 || ncols <= 0) return VLDD_OK;
+  topk_fill_rows_kernel<<<nrows, 256, 0, st>>>(S, out, ncols, k, fill);
+  return check_launch("topk_fill_rows");
+}
+
+}  // namespace vldd

@@ -1,0 +1,274 @@
+"""Drop-in mirror of the reference's distill.py for the trajectory-matching inner loop (text tower, Mode A).
+
+What is kept from the reference:
+  * the CLI: every flag of distill.py:625-679 with the same name, type and default, parse_known_args leniency;
+  * the expert-buffer file format  {buffer_path}/txt_replay_buffer_{n}.pt = list[expert] of list[snapshot] of
+    list[param tensors] (buffer.py:64-68,94-112; read at distill.py:255-283);
+  * the semantics of one outer iteration (distill.py:439-613): pick expert / start_epoch, K unrolled student steps
+    on the synthetic pairs, matching loss, backward, three momentum-0.5 SGD updates (image, text, lr).
+
+What is different by design: the whole inner loop + backward is ONE call into the CUDA engine
+(``ops.unrolled_match``) wrapped in ``UnrolledMatch`` (a torch.autograd.Function, so ``grand_loss.backward()``
+still works); expert snapshots live on the device as one flat [experts, snapshots, P] tensor; the image side is the
+image-encoder OUTPUT (frozen-NFNet embeddings, BASELINE.json north_star), not pixels.  Multi-GPU: one process per
+GPU, each rank runs a different expert segment and the synthetic-data gradients are all-reduced (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import datetime
+import glob
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+
+_BOOL = bool  # the reference uses type=bool (any non-empty string is True); kept for CLI compatibility
+
+
+def build_parser() -> argparse.ArgumentParser:
+    """Same flags / types / defaults as distill.py:625-679."""
+    p = argparse.ArgumentParser(description="Parameter Processing")
+    A = p.add_argument
+    A("--distributed", action="store_true")
+    A("--max_files", type=int, default=1)
+    A("--dataset", type=str, default="roco", choices=["roco", "coco", "flickr"])   # README.md:52 uses flickr
+    A("--num_queries", type=int, default=100)
+    A("--lr_img", type=float, default=1000)
+    A("--lr_txt", type=float, default=1000)
+    A("--lr_lr", type=float, default=1e-03)
+    A("--Iteration", type=int, default=50000)
+    A("--eval_it", type=int, default=50)
+    A("--num_eval", type=int, default=5)
+    A("--epoch_eval_train", type=int, default=1)
+    A("--syn_steps", type=int, default=20)
+    A("--mini_batch_size", type=int, default=100)
+    A("--max_start_epoch", type=int, default=25)
+    A("--expert_epochs", type=int, default=3)
+    A("--ipc", type=int, default=1)
+    A("--force_save", action="store_true")
+    A("--draw", type=_BOOL, default=True)
+    A("--transfer", type=_BOOL, default=False)
+    A("--std", type=_BOOL, default=False)
+    A("--disable_wandb", action="store_true")
+    A("--num_experts", type=int, default=100)
+    A("--lr_teacher_img", type=float, default=0.1)
+    A("--lr_teacher_txt", type=float, default=0.1)
+    A("--batch_train", type=int, default=128)
+    A("--dsa", type=str, default="True", choices=["True", "False"])
+    A("--dsa_strategy", type=str, default="color_crop_cutout_flip_scale_rotate")
+    A("--data_path", type=str, default="/kaggle/input/roco-dataset/")
+    A("--buffer_path", type=str, default="/kaggle/working")
+    A("--train_epochs", type=int, default=50)
+    A("--zca", action="store_true")
+    A("--decay", action="store_true")
+    A("--mom", type=float, default=0)
+    A("--l2", type=float, default=0)
+    A("--save_interval", type=int, default=10)
+    A("--name", type=str, default=datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S"))
+    A("--text_pretrained", type=_BOOL, default=True)
+    A("--image_pretrained", type=_BOOL, default=True)
+    A("--text_trainable", type=_BOOL, default=False)
+    A("--image_trainable", type=_BOOL, default=True)
+    A("--batch_size_train", type=int, default=128)
+    A("--batch_size_test", type=int, default=128)
+    A("--image_root", type=str, default="/kaggle/input/roco-dataset/all_data/train/radiology/images/")
+    A("--ann_root", type=str, default="/kaggle/input/roco-dataset/all_data/train/radiologytraindata.csv")
+    A("--image_size", type=int, default=224)
+    A("--k_test", type=int, default=128)
+    A("--load_npy", type=_BOOL, default=False)
+    A("--image_encoder", type=str, default="resnet50",
+      choices=["nfnet", "resnet18_gn", "vit_tiny", "nf_resnet50", "nf_regnet", "resnet50"])
+    A("--text_encoder", type=str, default="bert", choices=["bert", "clip"])
+    A("--margin", default=0.2, type=float)
+    A("--measure", default="cosine")
+    A("--max_violation", action="store_true")
+    A("--only_has_image_projection", type=_BOOL, default=False)
+    A("--grounding", type=_BOOL, default=False)
+    A("--distill", type=_BOOL, default=False)
+    # additions of this implementation (not in the reference)
+    A("--logit_scale_mode", type=str, default="fork", choices=["fork", "upstream"],
+      help="fork: logits scaled by the learnable syn_lr_img (distill.py:548); upstream: fixed log(1/0.07) "
+           "(distill_original.py:103,430)")
+    A("--embed_path", type=str, default=None, help=".npz with image_embed [M,d] and text_embed [M,dt] (frozen encoders)")
+    A("--synthetic", action="store_true", help="run on synthetic Flickr-shaped embeddings and experts")
+    A("--seed", type=int, default=0)
+    return p
+
+
+def parse_args(argv=None):
+    args, unknown = build_parser().parse_known_args(argv)      # distill.py:680-682
+    if unknown:
+        print("Warning: Ignoring unknown arguments:", unknown)
+    return args
+
+
+# ------------------------------------------------------------------------------------------------------
+class UnrolledMatch(torch.autograd.Function):
+    """loss = |theta_K - theta_tgt|^2 / |theta_0 - theta_tgt|^2 after K unrolled steps (distill.py:509-598).
+
+    Differentiable w.r.t. text_syn (Y), image embeddings (U), syn_lr and the logit scale; `.backward()` replays
+    nothing -- the engine already produced the gradients in the same call (reverse sweep).
+    """
+
+    @staticmethod
+    def forward(ctx, Y, U, lr, scale, theta0, theta_tgt, perms, masks, workspace):
+        res = ops.unrolled_match(theta0, theta_tgt, Y.detach(), U.detach(), lr, scale, perms, masks, workspace)
+        ctx.save_for_backward(res["dY"], res["dU"], res["out5"])
+        ctx.lr_shape, ctx.scale_shape = lr.shape, scale.shape
+        ctx.aux = res
+        return res["out5"][2].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        dY, dU, out5 = ctx.saved_tensors
+        return (gout * dY, gout * dU, (gout * out5[3]).reshape(ctx.lr_shape), (gout * out5[4]).reshape(ctx.scale_shape),
+                None, None, None, None, None)
+
+
+def flatten_snapshot(params, device=None) -> torch.Tensor:
+    """torch.cat([p.reshape(-1) ...]) of one snapshot (distill.py:471-476), done once per buffer instead of per iteration."""
+    flat = torch.cat([torch.as_tensor(p).reshape(-1).float() for p in params], 0)
+    return flat.to(device) if device is not None else flat
+
+
+def load_expert_buffers(buffer_path: str, kind: str = "txt", max_files: int | None = None, device="cuda") -> torch.Tensor:
+    """Reads {kind}_replay_buffer_{n}.pt files (buffer.py:104-112) into one [experts, snapshots, P] device tensor."""
+    files = sorted(glob.glob(os.path.join(buffer_path, f"{kind}_replay_buffer_*.pt")),
+                   key=lambda f: int(os.path.splitext(f)[0].rsplit("_", 1)[1]))
+    if not files:
+        raise AssertionError("No buffers detected at {}".format(buffer_path))       # distill_original.py:183-184
+    if max_files:
+        files = files[:max_files]
+    experts = []
+    for f in files:
+        for traj in torch.load(f, map_location="cpu"):
+            experts.append(torch.stack([flatten_snapshot(snap) for snap in traj]))
+    return torch.stack(experts).to(device)
+
+
+class DistillEngine:
+    """State of the distillation: synthetic pairs, learnable student lr(s), outer momentum-SGD, expert segments."""
+
+    def __init__(self, image_embed: torch.Tensor, text_embed: torch.Tensor, experts: torch.Tensor, args,
+                 device="cuda", process_group=None):
+        self.args = args
+        self.dev = torch.device(device)
+        self.U = image_embed.to(self.dev, torch.float32).contiguous().requires_grad_(True)       # "image_syn" (Mode A)
+        self.Y = text_embed.to(self.dev, torch.float32).contiguous().requires_grad_(True)        # text_syn  distill.py:231
+        self.syn_lr_img = torch.tensor(float(args.lr_teacher_img), device=self.dev, requires_grad=True)   # distill.py:235
+        self.syn_lr_txt = torch.tensor(float(args.lr_teacher_txt), device=self.dev, requires_grad=True)   # distill.py:236
+        self.experts = experts                      # [E, S, P] on device
+        self.N, self.dt = self.Y.shape
+        self.d = self.U.shape[1]
+        self.K = int(args.syn_steps)
+        self.B = min(int(args.mini_batch_size), self.N)
+        self.ws = ops.UnrollWorkspace(self.N, self.B, self.K, self.dt, self.d, self.dev)
+        self.bufs = {n: torch.zeros_like(t) for n, t in (("U", self.U), ("Y", self.Y))}
+        self.buf_lr = torch.zeros(2, device=self.dev)
+        self.first = True
+        self.pg = process_group
+        self.gen = torch.Generator().manual_seed(int(getattr(args, "seed", 0)))
+        self.expert_idx = 0
+        self.fixed_scale = torch.tensor(ops.LOGIT_SCALE_UPSTREAM, device=self.dev)
+
+    # -- one expert segment -> loss and grads (distill.py:466-606) --
+    def segment_loss(self, expert: int, start_epoch: int, perms: torch.Tensor | None = None, masks=None):
+        a = self.args
+        theta0 = self.experts[expert, start_epoch]
+        theta_tgt = self.experts[expert, start_epoch + int(a.expert_epochs)]
+        if perms is None:                                           # distill.py:510-511
+            perms = torch.stack([torch.randperm(self.N, generator=self.gen)[: self.B] for _ in range(self.K)])
+        perms = perms.to(self.dev)
+        fork = getattr(a, "logit_scale_mode", "fork") == "fork"
+        scale = self.syn_lr_img if fork else self.fixed_scale
+        return UnrolledMatch.apply(self.Y, self.U, self.syn_lr_txt, scale, theta0, theta_tgt, perms, masks, self.ws)
+
+    def sample_segment(self):
+        """distill.py:450-470: experts are consumed in order, start_epoch ~ U{0..max_start_epoch-1}."""
+        e = self.expert_idx
+        self.expert_idx = (self.expert_idx + 1) % self.experts.shape[0]
+        hi = min(int(self.args.max_start_epoch), self.experts.shape[1] - int(self.args.expert_epochs))
+        s = int(torch.randint(0, max(hi, 1), (1,), generator=self.gen))
+        return e, s
+
+    def outer_step(self, loss: torch.Tensor):
+        """zero_grad / backward / all-reduce / three SGD(momentum=0.5) steps (distill.py:603-613)."""
+        for t in (self.U, self.Y, self.syn_lr_img, self.syn_lr_txt):
+            t.grad = None
+        loss.backward()
+        g_lr = torch.stack([self.syn_lr_img.grad if self.syn_lr_img.grad is not None else torch.zeros((), device=self.dev),
+                            self.syn_lr_txt.grad])
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            packed = torch.cat([self.U.grad.reshape(-1), self.Y.grad.reshape(-1), g_lr])
+            torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            nU, nY = self.U.numel(), self.Y.numel()
+            self.U.grad.copy_(packed[:nU].view_as(self.U))
+            self.Y.grad.copy_(packed[nU:nU + nY].view_as(self.Y))
+            g_lr = packed[nU + nY:]
+        a = self.args
+        with torch.no_grad():
+            ops.momentum_sgd_(self.U, self.U.grad, self.bufs["U"], float(a.lr_img), 0.5, self.first)
+            ops.momentum_sgd_(self.Y, self.Y.grad, self.bufs["Y"], float(a.lr_txt), 0.5, self.first)
+            lrs = torch.stack([self.syn_lr_img.detach(), self.syn_lr_txt.detach()])
+            ops.momentum_sgd_(lrs, g_lr.contiguous(), self.buf_lr, float(a.lr_lr), 0.5, self.first)
+            self.syn_lr_img.copy_(lrs[0])
+            self.syn_lr_txt.copy_(lrs[1])
+        self.first = False
+
+    def iteration(self):
+        e, s = self.sample_segment()
+        loss = self.segment_loss(e, s)
+        self.outer_step(loss)
+        return loss
+
+
+def synthetic_experts(n_experts: int, n_snapshots: int, dt: int, d: int, seed: int = 0, step: float = 0.01) -> torch.Tensor:
+    """Random-walk expert trajectories of ProjectionHead shape (no checkpoints are available offline)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_experts):
+        b1, b2 = 1.0 / math.sqrt(dt), 1.0 / math.sqrt(d)
+        th = torch.cat([(torch.rand(d * dt, generator=g) * 2 - 1) * b1, (torch.rand(d, generator=g) * 2 - 1) * b1,
+                        (torch.rand(d * d, generator=g) * 2 - 1) * b2, (torch.rand(d, generator=g) * 2 - 1) * b2,
+                        torch.ones(d), torch.zeros(d)])
+        snaps = [th]
+        for _ in range(n_snapshots - 1):
+            snaps.append(snaps[-1] + step * torch.randn(th.shape, generator=g))
+        out.append(torch.stack(snaps))
+    return torch.stack(out)
+
+
+def main(args):
+    if not torch.cuda.is_available():
+        raise RuntimeError("distill needs a CUDA device (sm_100a); there is no CPU path")
+    args.device = "cuda"                                                     # distill.py:214
+    dev = torch.device("cuda")
+    N = int(args.num_queries)
+    if args.synthetic or args.embed_path is None:
+        g = torch.Generator().manual_seed(args.seed)
+        dt, d = 768, 2304
+        img = torch.randn(N, d, generator=g)
+        txt = torch.randn(N, dt, generator=g) * 0.5253 - 0.0094             # distill_original.py:147
+        experts = synthetic_experts(2, int(args.max_start_epoch) + int(args.expert_epochs) + 1, dt, d, args.seed).to(dev)
+    else:
+        z = np.load(args.embed_path)
+        sel = np.random.default_rng(args.seed).permutation(len(z["image_embed"]))[:N]   # distill.py:231 random real pairs
+        img, txt = torch.from_numpy(z["image_embed"][sel]), torch.from_numpy(z["text_embed"][sel])
+        experts = load_expert_buffers(args.buffer_path, "txt", args.max_files, dev)
+    eng = DistillEngine(img, txt, experts, args, dev)
+    for it in range(int(args.Iteration) + 1):
+        loss = eng.iteration()
+        if it % 10 == 0:
+            v = float(loss)
+            if math.isnan(v):                                                # distill.py:599-600
+                break
+            print("%s iter = %04d, loss = %.4f" % (datetime.datetime.now().strftime("[%Y-%m-%d %H:%M:%S]"), it, v))
+    return eng
+
+
+if __name__ == "__main__":
+    main(parse_args())

@@ -1,0 +1,281 @@
+"""torch-tensor front end of the C ABI: argument checking, output allocation, stream plumbing.
+
+torch is used for device memory and streams only; all arithmetic happens in libvldd_b200.so.  Every function
+raises on non-CUDA input -- there is no CPU path (BASELINE.json north_star: "no CPU fallback").
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+
+LOGIT_SCALE_EVAL = float(np.exp(np.log(1 / 0.07)))      # epoch_original.py:70,94 / networks.py:878  (= 14.2857...)
+LOGIT_SCALE_UPSTREAM = float(np.log(1 / 0.07))          # distill_original.py:103,430 (used un-exponentiated)
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (this library has no CPU path), got device {t.device}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _scalar(v, device, name: str) -> torch.Tensor:
+    """Scalars the reference keeps as tensors (syn_lr, logit scale) stay on the device: no host sync."""
+    if isinstance(v, torch.Tensor):
+        t = v.detach()
+        if t.numel() != 1:
+            raise ValueError(f"{name}: expected one element, got shape {tuple(t.shape)}")
+        return t.to(device=device, dtype=torch.float32).reshape(1).contiguous()
+    return torch.full((1,), float(v), dtype=torch.float32, device=device)
+
+
+def head_numel(dt: int, d: int) -> int:
+    return d * dt + d + d * d + d + d + d
+
+
+# --------------------------------------------------------------------------------------------------
+# streaming
+# --------------------------------------------------------------------------------------------------
+def flat_sgd_step(theta: torch.Tensor, grad: torch.Tensor, lr, out: torch.Tensor | None = None) -> torch.Tensor:
+    """theta - lr * grad  (distill.py:582-583)."""
+    theta = _req(torch.squeeze(theta), "theta")
+    grad = _req(torch.squeeze(grad), "grad")
+    if theta.shape != grad.shape:
+        raise ValueError(f"theta {tuple(theta.shape)} and grad {tuple(grad.shape)} differ")
+    out = torch.empty_like(theta) if out is None else _req(out, "out")
+    lr_t = _scalar(lr, theta.device, "lr")
+    check(lib().vldd_flat_sgd_step(_ptr(theta), _ptr(grad), _ptr(lr_t), _ptr(out), theta.numel(), _stream()),
+          "flat_sgd_step")
+    return out
+
+
+def match_loss(theta_K: torch.Tensor, theta_tgt: torch.Tensor, theta_0: torch.Tensor) -> torch.Tensor:
+    """Returns a device tensor [num, den, num/den]  (distill.py:588-598)."""
+    a, b, c = (_req(torch.squeeze(t), n) for t, n in ((theta_K, "theta_K"), (theta_tgt, "theta_tgt"), (theta_0, "theta_0")))
+    if not (a.shape == b.shape == c.shape):
+        raise ValueError("match_loss: shape mismatch")
+    out = torch.empty(3, dtype=torch.float32, device=a.device)
+    scratch = torch.zeros(lib().vldd_match_loss_scratch_bytes(), dtype=torch.uint8, device=a.device)
+    check(lib().vldd_match_loss_fwd(_ptr(a), _ptr(b), _ptr(c), a.numel(), _ptr(out), _ptr(scratch), _stream()),
+          "match_loss_fwd")
+    return out
+
+
+def match_loss_bwd(theta_K: torch.Tensor, theta_tgt: torch.Tensor, num_den: torch.Tensor, gout=None) -> torch.Tensor:
+    a, b = _req(torch.squeeze(theta_K), "theta_K"), _req(torch.squeeze(theta_tgt), "theta_tgt")
+    nd = _req(num_den, "num_den")
+    g = None if gout is None else _scalar(gout, a.device, "gout")
+    out = torch.empty_like(a)
+    check(lib().vldd_match_loss_bwd(_ptr(a), _ptr(b), _ptr(nd), _ptr(g), _ptr(out), a.numel(), _stream()), "match_loss_bwd")
+    return out
+
+
+def momentum_sgd_(param: torch.Tensor, grad: torch.Tensor, buf: torch.Tensor, lr: float, momentum: float, first: bool) -> None:
+    """In-place torch.optim.SGD(momentum, dampening=0) step (distill.py:233-241, 611-613)."""
+    for t, n in ((param, "param"), (grad, "grad"), (buf, "buf")):
+        _req(t, n)
+        if not t.is_contiguous():
+            raise ValueError(f"{n} must be contiguous for the in-place update")
+    check(lib().vldd_momentum_sgd(_ptr(param), _ptr(grad), _ptr(buf), float(lr), float(momentum), int(bool(first)),
+                                  param.numel(), _stream()), "momentum_sgd")
+
+
+# --------------------------------------------------------------------------------------------------
+# retrieval
+# --------------------------------------------------------------------------------------------------
+def maps_to_arrays(txt2img, img2txt, n_img: int, n_txt: int):
+    """dict[int->int], dict[int->list[int]] (flickr30k_dataset.py:110-118) -> (txt2img[T], ptr[I+1], idx[]) int32."""
+    t2i = np.empty(n_txt, dtype=np.int32)
+    if isinstance(txt2img, dict):
+        for t in range(n_txt):
+            t2i[t] = txt2img[t]
+    else:
+        t2i[:] = np.asarray(txt2img, dtype=np.int32)[:n_txt]
+    ptr = np.zeros(n_img + 1, dtype=np.int32)
+    lists = [np.atleast_1d(np.asarray(img2txt[i], dtype=np.int32)) for i in range(n_img)]
+    for i, l in enumerate(lists):
+        ptr[i + 1] = ptr[i] + len(l)
+    idx = np.concatenate(lists).astype(np.int32) if lists else np.zeros(0, dtype=np.int32)
+    return t2i, ptr, idx
+
+
+def ranks_from_scores(scores_i2t, scores_t2i, txt2img: torch.Tensor, img2txt_ptr: torch.Tensor, img2txt_idx: torch.Tensor):
+    """Device score matrices -> (ranks_i2t[I], ranks_t2i[T]) int32 device tensors."""
+    s1 = None if scores_i2t is None else _req(scores_i2t, "scores_i2t")
+    s2 = None if scores_t2i is None else _req(scores_t2i, "scores_t2i")
+    ref = s1 if s1 is not None else s2
+    if ref is None:
+        raise ValueError("need at least one score matrix")
+    n_img, n_txt = (s1.shape if s1 is not None else s2.shape[::-1])
+    if s1 is not None and s2 is not None and tuple(s2.shape) != (n_txt, n_img):
+        raise ValueError(f"scores_t2i must be [{n_txt},{n_img}], got {tuple(s2.shape)}")
+    t2i = _req(txt2img, "txt2img", torch.int32)
+    ptr = _req(img2txt_ptr, "img2txt_ptr", torch.int32)
+    idx = _req(img2txt_idx, "img2txt_idx", torch.int32)
+    r1 = torch.empty(n_img, dtype=torch.int32, device=ref.device)
+    r2 = torch.empty(n_txt, dtype=torch.int32, device=ref.device)
+    check(lib().vldd_ranks_from_scores(_ptr(s1), _ptr(s2), n_img, n_txt, _ptr(t2i), _ptr(ptr), _ptr(idx), _ptr(r1),
+                                       _ptr(r2), _stream()), "ranks_from_scores")
+    return (r1 if s1 is not None else None), (r2 if s2 is not None else None)
+
+
+def recall_counts(ranks: torch.Tensor) -> torch.Tensor:
+    r = _req(ranks, "ranks", torch.int32)
+    out = torch.empty(3, dtype=torch.int32, device=r.device)
+    check(lib().vldd_recall_counts(_ptr(r), r.numel(), _ptr(out), _stream()), "recall_counts")
+    return out
+
+
+def sim_scores(img: torch.Tensor, txt: torch.Tensor, scale: float = LOGIT_SCALE_EVAL, want_t2i: bool = True):
+    img, txt = _req(img, "img"), _req(txt, "txt")
+    if img.shape[1] != txt.shape[1]:
+        raise ValueError("embedding dims differ")
+    I, T, D = img.shape[0], txt.shape[0], img.shape[1]
+    s1 = torch.empty(I, T, dtype=torch.float32, device=img.device)
+    s2 = torch.empty(T, I, dtype=torch.float32, device=img.device) if want_t2i else None
+    check(lib().vldd_sim_scores(_ptr(img), _ptr(txt), I, T, D, float(scale), _ptr(s1), _ptr(s2), _stream()), "sim_scores")
+    return s1, s2
+
+
+def topk_fill(scores: torch.Tensor, k: int = 128, fill: float = -100.0) -> torch.Tensor:
+    s = _req(scores, "scores")
+    out = torch.empty_like(s)
+    check(lib().vldd_topk_fill(_ptr(s), _ptr(out), s.shape[0], s.shape[1], int(k), float(fill), _stream()), "topk_fill")
+    return out
+
+
+def sim_rank(img: torch.Tensor, txt: torch.Tensor, txt2img: torch.Tensor, img2txt_ptr: torch.Tensor,
+             img2txt_idx: torch.Tensor, scale: float = LOGIT_SCALE_EVAL, workspace: torch.Tensor | None = None):
+    img, txt = _req(img, "img"), _req(txt, "txt")
+    I, T, D = img.shape[0], txt.shape[0], img.shape[1]
+    need = lib().vldd_sim_rank_workspace_bytes(I, T, D)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=img.device)
+    r1 = torch.empty(I, dtype=torch.int32, device=img.device)
+    r2 = torch.empty(T, dtype=torch.int32, device=img.device)
+    check(lib().vldd_sim_rank(_ptr(img), _ptr(txt), I, T, D, float(scale), _ptr(_req(txt2img, "txt2img", torch.int32)),
+                              _ptr(_req(img2txt_ptr, "img2txt_ptr", torch.int32)),
+                              _ptr(_req(img2txt_idx, "img2txt_idx", torch.int32)), _ptr(r1), _ptr(r2), _ptr(workspace),
+                              workspace.numel(), _stream()), "sim_rank")
+    return r1, r2
+
+
+RESULT_KEYS = ("txt_r1", "txt_r5", "txt_r10", "txt_r_mean", "img_r1", "img_r5", "img_r10", "img_r_mean", "r_mean")
+
+
+def itm_eval_host(scores_i2t: np.ndarray, scores_t2i: np.ndarray, t2i: np.ndarray, ptr: np.ndarray, idx: np.ndarray,
+                  want_ranks: bool = False):
+    """Host numpy matrices in, result dict out -- the C-ABI drop-in under epoch.itm_eval."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("itm_eval needs a CUDA device (this library has no CPU path)")
+    s1 = np.ascontiguousarray(scores_i2t, dtype=np.float32)
+    s2 = np.ascontiguousarray(scores_t2i, dtype=np.float32)
+    I, T = s1.shape
+    if s2.shape != (T, I):
+        raise ValueError(f"scores_t2i must be [{T},{I}], got {s2.shape}")
+    res = np.zeros(9, dtype=np.float64)
+    r1 = np.empty(I, dtype=np.int32) if want_ranks else None
+    r2 = np.empty(T, dtype=np.int32) if want_ranks else None
+    vp = lambda a: C.c_void_p(0 if a is None else a.ctypes.data)
+    check(lib().vldd_itm_eval_host(vp(s1), vp(s2), I, T, vp(t2i), vp(ptr), vp(idx), vp(r1), vp(r2), vp(res), _stream()),
+          "itm_eval_host")
+    out = {k: float(v) for k, v in zip(RESULT_KEYS, res)}
+    return (out, r1, r2) if want_ranks else out
+
+
+# --------------------------------------------------------------------------------------------------
+# head / InfoNCE / unroll
+# --------------------------------------------------------------------------------------------------
+def proj_head_forward(theta: torch.Tensor, Y: torch.Tensor, d: int, mask: torch.Tensor | None = None,
+                      normalise: bool = False) -> torch.Tensor:
+    theta = _req(torch.squeeze(theta), "theta")
+    Y = _req(Y, "Y")
+    rows, dt = Y.shape
+    if theta.numel() != head_numel(dt, d):
+        raise ValueError(f"theta has {theta.numel()} elements, expected {head_numel(dt, d)} for dt={dt}, d={d}")
+    mask = None if mask is None else _req(mask, "mask")
+    out = torch.empty(rows, d, dtype=torch.float32, device=Y.device)
+    ws = torch.empty(lib().vldd_proj_head_workspace_bytes(rows, dt, d), dtype=torch.uint8, device=Y.device)
+    z, zn = (None, out) if normalise else (out, None)
+    check(lib().vldd_proj_head_forward(_ptr(theta), _ptr(Y), _ptr(mask), rows, dt, d, _ptr(z), _ptr(zn), _ptr(ws),
+                                       ws.numel(), _stream()), "proj_head_forward")
+    return out
+
+
+def contrastive_step(theta: torch.Tensor, Y: torch.Tensor, U: torch.Tensor, scale, mask: torch.Tensor | None = None):
+    """loss and first-order grads of one step (config 2): returns dict(loss, g_theta, dY, dU, dscale)."""
+    theta, Y, U = _req(torch.squeeze(theta), "theta"), _req(Y, "Y"), _req(U, "U")
+    B, dt = Y.shape
+    d = U.shape[1]
+    if theta.numel() != head_numel(dt, d):
+        raise ValueError(f"theta has {theta.numel()} elements, expected {head_numel(dt, d)}")
+    dev = Y.device
+    sc = _scalar(scale, dev, "scale")
+    mask = None if mask is None else _req(mask, "mask")
+    loss = torch.empty(1, device=dev)
+    g = torch.empty_like(theta)
+    dY, dU, dsc = torch.empty_like(Y), torch.empty_like(U), torch.empty(1, device=dev)
+    ws = torch.empty(lib().vldd_contrastive_step_workspace_bytes(B, dt, d), dtype=torch.uint8, device=dev)
+    check(lib().vldd_contrastive_step(_ptr(theta), _ptr(Y), _ptr(U), _ptr(sc), _ptr(mask), B, dt, d, _ptr(loss), _ptr(g),
+                                      _ptr(dY), _ptr(dU), _ptr(dsc), _ptr(ws), ws.numel(), _stream()), "contrastive_step")
+    return dict(loss=loss[0], g_theta=g, dY=dY, dU=dU, dscale=dsc[0])
+
+
+class UnrollWorkspace:
+    """Caller-owned device workspace of the unroll engine, sized once per (N, B, K, dt, d)."""
+
+    def __init__(self, N: int, B: int, K: int, dt: int, d: int, device):
+        self.key = (N, B, K, dt, d)
+        nbytes = lib().vldd_unrolled_match_workspace_bytes(N, B, K, dt, d)
+        if nbytes == 0:
+            check(-1, "unrolled_match_workspace_bytes")
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, workspace: UnrollWorkspace | None = None,
+                   want_theta_K: bool = False):
+    """distill.py:509-606 for one expert segment.  Returns dict(out5=[num,den,loss,dlr,dscale], ce, dY, dU[, theta_K])."""
+    theta0, theta_tgt = _req(torch.squeeze(theta0), "theta0"), _req(torch.squeeze(theta_tgt), "theta_tgt")
+    Y, U = _req(Y, "Y"), _req(U, "U")
+    perms = _req(perms, "perms", torch.int64)
+    K, B = perms.shape
+    N, dt = Y.shape
+    d = U.shape[1]
+    if U.shape[0] != N:
+        raise ValueError("Y and U must have the same number of rows")
+    if theta0.numel() != head_numel(dt, d) or theta_tgt.numel() != theta0.numel():
+        raise ValueError(f"theta has {theta0.numel()} elements, expected {head_numel(dt, d)}")
+    dev = Y.device
+    lr_t, sc_t = _scalar(lr, dev, "lr"), _scalar(scale, dev, "scale")
+    if masks is not None:
+        masks = _req(masks, "masks")
+        if tuple(masks.shape) != (K, B, d):
+            raise ValueError(f"masks must be [{K},{B},{d}]")
+    if workspace is None or workspace.key != (N, B, K, dt, d):
+        workspace = UnrollWorkspace(N, B, K, dt, d, dev)
+    out5 = torch.empty(5, device=dev)
+    ce = torch.empty(max(K, 1), device=dev)
+    dY, dU = torch.empty_like(Y), torch.empty_like(U)
+    thK = torch.empty_like(theta0) if want_theta_K else None
+    check(lib().vldd_unrolled_match(_ptr(theta0), _ptr(theta_tgt), _ptr(Y), _ptr(U), _ptr(lr_t), _ptr(sc_t), _ptr(perms),
+                                    _ptr(masks), N, B, K, dt, d, _ptr(out5), _ptr(ce), _ptr(dY), _ptr(dU), _ptr(thK),
+                                    _ptr(workspace.buf), workspace.buf.numel(), _stream()), "unrolled_match")
+    res = dict(out5=out5, ce=ce[:K], dY=dY, dU=dU, workspace=workspace)
+    if want_theta_K:
+        res["theta_K"] = thK
+    return res

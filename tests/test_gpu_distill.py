@@ -1,0 +1,181 @@
+"""CUDA head / InfoNCE / unroll engine vs the oracle and the reference-generated goldens, through the C ABI.
+
+Tolerance (BASELINE.json north_star): losses and synthetic-data gradients within 1e-4 relative in fp32.
+For tensors "relative" is norm-wise: max|got - ref| <= 1e-4 * max|ref|.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+from oracle import distill_ref as R
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def rel_err(got, ref):
+    got, ref = torch.as_tensor(got).double().cpu(), torch.as_tensor(ref).double().cpu()
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-300))
+
+
+def to_cuda(pr):
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in pr.items()}
+
+
+@pytest.mark.parametrize("rows,dt,d,drop", [(5, 12, 20, False), (7, 10, 16, True), (100, 768, 2304, False), (130, 768, 2304, True),
+                                            (1, 768, 2304, False)])
+def test_proj_head_forward(rows, dt, d, drop):
+    from multimodal_dataset_distillation_b200 import ops
+    pr = R.make_problem(N=rows, B=rows, K=1, dt=dt, d=d, seed=11, dropout=drop)
+    mask = pr["masks"][0] if drop else None
+    ref = R.head_forward(pr["theta0"].double(), pr["Y"].double(), dt, d, None if mask is None else mask.double())
+    got = ops.proj_head_forward(pr["theta0"].cuda(), pr["Y"].cuda(), d, None if mask is None else mask.cuda())
+    assert rel_err(got, ref) < RTOL
+    gotn = ops.proj_head_forward(pr["theta0"].cuda(), pr["Y"].cuda(), d, None if mask is None else mask.cuda(), normalise=True)
+    assert rel_err(gotn, R.row_normalise(ref)) < RTOL
+
+
+def test_proj_head_forward_matches_reparam_golden():
+    """ReparamModule(ProjectionHead) run by the REFERENCE class in the build container."""
+    from multimodal_dataset_distillation_b200 import ops
+    z = np.load(os.path.join(GOLDEN_DIR, "reparam_small.npz"))
+    got = ops.proj_head_forward(torch.from_numpy(z["theta"]).cuda().unsqueeze(0), torch.from_numpy(z["x"]).cuda(), 20)
+    assert rel_err(got, z["out"]) < RTOL
+
+
+@pytest.mark.parametrize("B,dt,d,scale,drop", [(8, 10, 16, 2.0, False), (24, 32, 48, 14.2857, True),
+                                               (100, 768, 2304, 2.6593, False), (100, 768, 2304, 14.2857, True),
+                                               (100, 768, 2304, 0.1, False)])
+def test_contrastive_step_config2(B, dt, d, scale, drop):
+    from multimodal_dataset_distillation_b200 import ops
+    pr = R.make_problem(N=B, B=B, K=1, dt=dt, d=d, seed=5, dropout=drop, scale=scale)
+    mask = pr["masks"][0] if drop else None
+    th = pr["theta0"].double().requires_grad_(True)
+    Y = pr["Y"].double().requires_grad_(True)
+    U = pr["U"].double().requires_grad_(True)
+    sc = pr["scale"].double().requires_grad_(True)
+    loss = R.infonce(R.row_normalise(U), R.row_normalise(R.head_forward(th, Y, dt, d, None if mask is None else mask.double())), sc)
+    gth, gY, gU, gsc = torch.autograd.grad(loss, (th, Y, U, sc))
+    got = ops.contrastive_step(pr["theta0"].cuda(), pr["Y"].cuda(), pr["U"].cuda(), pr["scale"].cuda(),
+                               None if mask is None else mask.cuda())
+    assert abs(float(got["loss"]) - float(loss)) <= RTOL * abs(float(loss))
+    assert rel_err(got["g_theta"], gth) < RTOL
+    assert rel_err(got["dY"], gY) < RTOL
+    assert rel_err(got["dU"], gU) < RTOL
+    assert abs(float(got["dscale"]) - float(gsc)) <= RTOL * abs(float(gsc)) + 1e-9
+
+
+def _run_engine(pr, want_theta_K=True):
+    from multimodal_dataset_distillation_b200 import ops
+    c = to_cuda(pr)
+    return ops.unrolled_match(c["theta0"], c["theta_tgt"], c["Y"], c["U"], c["lr"], c["scale"], c["perms"], c["masks"],
+                              want_theta_K=want_theta_K)
+
+
+@pytest.mark.parametrize("name", ["small_nodrop", "small_drop", "mid_full_batch"])
+def test_unrolled_match_small_goldens(golden, name):
+    """Goldens made by the reference's ReparamModule + torch double-backward (tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(GOLDEN_DIR, "distill_small.npz"))
+    g = golden["distill"][f"{name}_f64"]
+    pr = R.make_problem(dtype=torch.float32, **g["kw"])
+    res = _run_engine(pr)
+    out5 = res["out5"].cpu()
+    assert abs(out5[2].item() - g["loss"]) <= RTOL * abs(g["loss"])
+    assert abs(out5[0].item() - g["num"]) <= RTOL * abs(g["num"])
+    assert abs(out5[1].item() - g["den"]) <= RTOL * abs(g["den"])
+    assert abs(out5[3].item() - g["dlr"]) <= RTOL * abs(g["dlr"])
+    assert abs(out5[4].item() - g["dscale"]) <= RTOL * abs(g["dscale"])
+    np.testing.assert_allclose(res["ce"].cpu().numpy(), np.asarray(g["ce"]), rtol=RTOL)
+    assert rel_err(res["dY"], z[f"{name}_f64_dY"]) < RTOL
+    assert rel_err(res["dU"], z[f"{name}_f64_dU"]) < RTOL
+    assert rel_err(res["theta_K"], z[f"{name}_f64_thetaK"]) < RTOL
+
+
+@pytest.mark.parametrize("key", ["flickr_upstream_f64", "flickr_fork_f64", "flickr_eval_f64", "flickr_drop_f64"])
+def test_unrolled_match_flickr_goldens(golden, key):
+    """Config 3 (N=B=100, K=8, 768->2304): fp32 engine vs the reference mechanism run in float64."""
+    z = np.load(os.path.join(GOLDEN_DIR, "distill_flickr.npz"))
+    g = golden["distill"][key]
+    pr = R.make_problem(dtype=torch.float32, **g["kw"])
+    res = _run_engine(pr)
+    out5 = res["out5"].cpu()
+    assert abs(out5[2].item() - g["loss"]) <= RTOL * abs(g["loss"])
+    assert abs(out5[1].item() - g["den"]) <= RTOL * abs(g["den"])
+    assert abs(out5[3].item() - g["dlr"]) <= RTOL * abs(g["dlr"]), (out5[3].item(), g["dlr"])
+    assert abs(out5[4].item() - g["dscale"]) <= RTOL * abs(g["dscale"]), (out5[4].item(), g["dscale"])
+    np.testing.assert_allclose(res["ce"].cpu().numpy(), np.asarray(g["ce"]), rtol=RTOL)
+    rows = slice(None) if key == "flickr_upstream_f64" else slice(None, None, 10)
+    assert rel_err(res["dY"][rows], z[key + "_dY"]) < RTOL
+    assert rel_err(res["dU"][rows], z[key + "_dU"]) < RTOL
+    if "thetaK_sample" in g:
+        tk = res["theta_K"].double().cpu()
+        assert abs(float(tk.sum()) - g["thetaK_sum"]) <= 1e-4 * abs(g["thetaK_sqsum"]) ** 0.5
+        np.testing.assert_allclose(tk[::700001].numpy(), np.asarray(g["thetaK_sample"]), rtol=1e-4, atol=1e-6)
+
+
+def test_unrolled_match_fp32_reference_behaviour(golden):
+    """The reference's own fp32 run (torch CPU) and the fp32 engine both sit within 1e-4 of the f64 truth."""
+    g32, g64 = golden["distill"]["flickr_upstream_f32"], golden["distill"]["flickr_upstream_f64"]
+    pr = R.make_problem(dtype=torch.float32, **g32["kw"])
+    out5 = _run_engine(pr, want_theta_K=False)["out5"].cpu()
+    for i, k in ((2, "loss"), (3, "dlr"), (4, "dscale")):
+        assert abs(out5[i].item() - g32[k]) <= RTOL * abs(g64[k])
+
+
+@pytest.mark.parametrize("N,B,K,drop", [(500, 100, 2, False), (120, 100, 3, True), (100, 100, 0, False), (64, 1, 2, False)])
+def test_unrolled_match_subsets_vs_oracle(N, B, K, drop):
+    """COCO-shaped minibatches (B < N: true random subsets, distill.py:511), K=0 and B=1 edge cases."""
+    pr = R.make_problem(N=N, B=B, K=max(K, 1), dt=64, d=96, seed=21, dropout=drop, lr=0.2, scale=5.0, tgt_eps=0.05)
+    if K == 0:
+        pr["perms"] = pr["perms"][:0]
+        pr["masks"] = None
+    ref = R.unrolled_match_manual(**{k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v)
+                                     for k, v in pr.items()})
+    res = _run_engine(pr)
+    out5 = res["out5"].cpu()
+    assert abs(out5[2].item() - float(ref.loss)) <= RTOL * abs(float(ref.loss))
+    if K > 0:
+        assert abs(out5[3].item() - float(ref.dlr)) <= RTOL * abs(float(ref.dlr)) + 1e-12
+        assert abs(out5[4].item() - float(ref.dscale)) <= RTOL * abs(float(ref.dscale)) + 1e-12
+        assert rel_err(res["dY"], ref.dY) < RTOL
+        assert rel_err(res["dU"], ref.dU) < RTOL
+    else:
+        assert float(res["dY"].abs().max()) == 0.0 and float(res["dU"].abs().max()) == 0.0
+    assert rel_err(res["theta_K"], ref.theta_K) < RTOL
+
+
+def test_unrolled_match_is_deterministic():
+    pr = R.make_problem(N=100, B=100, K=2, dt=768, d=2304, seed=3)
+    a, b = _run_engine(pr), _run_engine(pr)
+    assert torch.equal(a["out5"], b["out5"]) and torch.equal(a["dY"], b["dY"]) and torch.equal(a["dU"], b["dU"])
+
+
+def test_autograd_function_and_outer_step():
+    """UnrolledMatch.apply + backward() == engine grads; outer SGD(momentum .5) == torch.optim.SGD (distill.py:603-613)."""
+    from multimodal_dataset_distillation_b200 import distill
+    args = distill.parse_args(["--syn_steps", "2", "--expert_epochs", "1", "--max_start_epoch", "2", "--num_queries", "16",
+                               "--mini_batch_size", "16", "--lr_img", "10", "--lr_txt", "10", "--lr_lr", "0.01",
+                               "--logit_scale_mode", "fork"])
+    dt, d = 24, 40
+    experts = distill.synthetic_experts(1, 3, dt, d, seed=1, step=0.05).cuda()
+    g = torch.Generator().manual_seed(0)
+    img, txt = torch.randn(16, d, generator=g), torch.randn(16, dt, generator=g)
+    eng = distill.DistillEngine(img, txt, experts, args)
+    perms = torch.stack([torch.randperm(16, generator=g) for _ in range(2)])
+    # oracle with the fork's aliasing: scale == syn_lr_img
+    Y = txt.double().requires_grad_(True); U = img.double().requires_grad_(True)
+    lr_i = torch.tensor(0.1, dtype=torch.float64, requires_grad=True); lr_t = torch.tensor(0.1, dtype=torch.float64, requires_grad=True)
+    ref = R.unrolled_match_autograd(experts[0, 0].double().cpu(), experts[0, 1].double().cpu(), Y, U, lr_t, lr_i, perms, None, dt, d)
+    loss = eng.segment_loss(0, 0, perms)
+    assert abs(float(loss) - float(ref.loss)) <= RTOL * float(ref.loss)
+    Y0, U0 = eng.Y.detach().clone(), eng.U.detach().clone()
+    eng.outer_step(loss)
+    assert rel_err(eng.Y.grad, ref.dY) < RTOL and rel_err(eng.U.grad, ref.dU) < RTOL
+    assert abs(float(eng.syn_lr_txt.grad) - float(ref.dlr)) <= RTOL * abs(float(ref.dlr))
+    assert abs(float(eng.syn_lr_img.grad) - float(ref.dscale)) <= RTOL * abs(float(ref.dscale))
+    torch.testing.assert_close(eng.Y.detach(), Y0 - 10 * eng.Y.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(eng.U.detach(), U0 - 10 * eng.U.grad, rtol=1e-5, atol=1e-6)
+    assert abs(float(eng.syn_lr_txt) - (0.1 - 0.01 * float(ref.dlr))) < 1e-6

@@ -1,0 +1,130 @@
+"""CUDA retrieval kernels vs the oracle and the reference-generated goldens, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval_ref as RR
+
+pytestmark = pytest.mark.gpu
+
+
+def _case_inputs(case):
+    img, txt = RR.synthetic_retrieval(case["I"], case["C"], case["D"], seed=case["seed"])
+    S = (np.float32(14.285714) * img) @ txt.T
+    if case["quant"]:
+        S = np.round(S * case["quant"]) / np.float32(case["quant"])
+    S = S.astype(np.float32)
+    St = np.ascontiguousarray(S.T)
+    if case["fill"]:
+        S, St = RR.topk_fill_ref(S, 128), RR.topk_fill_ref(St, 128)
+    return img, txt, S, St, RR.flickr_maps(case["I"], case["C"])
+
+
+def test_itm_eval_matches_reference_goldens(golden):
+    from multimodal_dataset_distillation_b200 import epoch
+    for case in golden["retrieval"]:
+        _, _, S, St, (txt2img, img2txt) = _case_inputs(case)
+        assert abs(float(np.float64(S).sum()) - case["score_checksum"]) < 1e-6 * max(1.0, abs(case["score_checksum"]))
+        res, r_i, r_t = epoch.itm_eval(S, St, txt2img, img2txt, return_ranks=True)
+        for k, v in case["fork"].items():       # recall numbers: exact (integer counts / n)
+            assert res[k] == pytest.approx(v, abs=1e-12), (case["name"], k)
+        for k, v in case["orig"].items():
+            assert res[k] == pytest.approx(v, abs=1e-12), (case["name"], k)
+        if "ranks_i2t" in case:                 # tie-free: the reference's ranks themselves, bit-exact
+            assert np.array_equal(r_i, np.asarray(case["ranks_i2t"], dtype=np.int32)), case["name"]
+            assert np.array_equal(r_t, np.asarray(case["ranks_t2i"], dtype=np.int32)), case["name"]
+        # ties: oracle's deterministic definition, bit-exact
+        assert np.array_equal(r_i, RR.ranks_i2t(S, img2txt)), case["name"]
+        assert np.array_equal(r_t, RR.ranks_t2i(St, txt2img)), case["name"]
+
+
+@pytest.mark.parametrize("I,C,T_extra", [(1, 1, 0), (3, 2, 0), (17, 5, 3), (33, 1, 0), (5, 7, 2)])
+def test_ranks_ragged_and_edge(I, C, T_extra):
+    from multimodal_dataset_distillation_b200 import ops
+    rng = np.random.default_rng(I * 100 + C)
+    T = I * C + T_extra
+    S = rng.integers(-3, 4, size=(I, T)).astype(np.float32)        # heavy ties
+    St = rng.integers(-3, 4, size=(T, I)).astype(np.float32)
+    # ragged ground truth: image i owns a random non-empty subset
+    img2txt = {i: sorted(rng.choice(T, size=rng.integers(1, min(T, 6) + 1), replace=False).tolist()) for i in range(I)}
+    txt2img = {t: int(rng.integers(0, I)) for t in range(T)}
+    t2i, ptr, idx = ops.maps_to_arrays(txt2img, img2txt, I, T)
+    r1, r2 = ops.ranks_from_scores(torch.from_numpy(S).cuda(), torch.from_numpy(St).cuda(), torch.from_numpy(t2i).cuda(),
+                                   torch.from_numpy(ptr).cuda(), torch.from_numpy(idx).cuda())
+    assert np.array_equal(r1.cpu().numpy(), RR.ranks_i2t(S, img2txt))
+    assert np.array_equal(r2.cpu().numpy(), RR.ranks_t2i(St, txt2img))
+
+
+def test_ranks_unaligned_rows():
+    from multimodal_dataset_distillation_b200 import ops
+    rng = np.random.default_rng(9)
+    I, T = 37, 4099                      # odd row length -> scalar path; >4096 -> 256-thread kernel
+    S = rng.standard_normal((I, T)).astype(np.float32)
+    img2txt = {i: [int(rng.integers(0, T))] for i in range(I)}
+    txt2img = {t: 0 for t in range(T)}
+    t2i, ptr, idx = ops.maps_to_arrays(txt2img, img2txt, I, T)
+    r1, _ = ops.ranks_from_scores(torch.from_numpy(S).cuda(), None, torch.from_numpy(t2i).cuda(),
+                                  torch.from_numpy(ptr).cuda(), torch.from_numpy(idx).cuda())
+    assert np.array_equal(r1.cpu().numpy(), RR.ranks_i2t(S, img2txt))
+
+
+def test_recall_counts():
+    from multimodal_dataset_distillation_b200 import ops
+    r = torch.tensor([0, 0, 1, 4, 5, 9, 10, 11, 200, 3], dtype=torch.int32).cuda()
+    assert ops.recall_counts(r).cpu().tolist() == [2, 5, 7]
+    assert ops.recall_counts(torch.zeros(0, dtype=torch.int32).cuda()).cpu().tolist() == [0, 0, 0]
+
+
+def test_sim_scores_and_topk_fill_vs_epoch_test_golden():
+    """epoch_original.epoch_test driven in the build container -> tests/golden/epoch_test_small.npz."""
+    import os
+    from multimodal_dataset_distillation_b200 import ops
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "epoch_test_small.npz"))
+    I, C, D, dt = (int(x) for x in z["dims"])
+    theta = torch.from_numpy(z["theta"]).cuda()
+    txt = ops.proj_head_forward(theta, torch.from_numpy(z["bert"]).cuda(), D, normalise=True)
+    feats = torch.from_numpy(z["feats"]).cuda()
+    img = feats / feats.norm(dim=1, keepdim=True)
+    img = img / img.norm(dim=1, keepdim=True)                         # epoch_original.py:84,92 (normalised twice)
+    s1, s2 = ops.sim_scores(img, txt, ops.LOGIT_SCALE_EVAL)
+    f1, f2 = ops.topk_fill(s1, 128, -100.0).cpu().numpy(), ops.topk_fill(s2, 128, -100.0).cpu().numpy()
+    for got, ref in ((f1, z["s_i2t"]), (f2, z["s_t2i"])):
+        kept_g, kept_r = got > -100, ref > -100
+        assert (kept_g.sum(axis=1) == 128).all()
+        # the kept sets can differ only where the 128th/129th values are within rounding of each other
+        assert (kept_g != kept_r).sum() <= 4
+        both = kept_g & kept_r
+        np.testing.assert_allclose(got[both], ref[both], rtol=2e-5, atol=2e-5)
+
+
+def test_topk_fill_exact_vs_oracle():
+    from multimodal_dataset_distillation_b200 import ops
+    rng = np.random.default_rng(4)
+    for rows, cols, k in [(5, 300, 128), (3, 128, 128), (4, 100, 128), (6, 1000, 7), (2, 513, 1)]:
+        S = rng.standard_normal((rows, cols)).astype(np.float32)
+        S[0, : cols // 2] = 0.25                                       # a big tie block crossing the threshold
+        out = ops.topk_fill(torch.from_numpy(S).cuda(), k, -100.0).cpu().numpy()
+        assert np.array_equal(out, RR.topk_fill_ref(S, k, -100.0)), (rows, cols, k)
+
+
+def test_sim_rank_flickr_shape():
+    from multimodal_dataset_distillation_b200 import ops
+    img, txt = RR.synthetic_retrieval(1000, 5, 768, seed=0)
+    txt2img, img2txt = RR.flickr_maps(1000, 5)
+    t2i, ptr, idx = ops.maps_to_arrays(txt2img, img2txt, 1000, 5000)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    r1, r2 = ops.sim_rank(dev(img), dev(txt), dev(t2i), dev(ptr), dev(idx), 14.285714)
+    # ranks are a function of fp32 scores whose summation order differs from numpy's: compare through the
+    # GPU's own score matrix (bit-exact) and against numpy scores up to near-tie flips
+    s1, s2 = ops.sim_scores(dev(img), dev(txt), 14.285714)
+    assert np.array_equal(r1.cpu().numpy(), RR.ranks_vectorised(s1.cpu().numpy(), ptr, idx))
+    assert np.array_equal(r2.cpu().numpy(), RR.ranks_vectorised(s2.cpu().numpy(), np.arange(5001, dtype=np.int32), t2i))
+    S = (np.float32(14.285714) * img) @ txt.T
+    np.testing.assert_allclose(s1.cpu().numpy(), S, rtol=1e-4, atol=1e-4)
+    ref1 = RR.ranks_vectorised(S, ptr, idx)
+    assert (r1.cpu().numpy() != ref1).mean() < 0.01
+    res_gpu = RR.recall_dict(r1.cpu().numpy(), r2.cpu().numpy())
+    res_ref = RR.recall_dict(ref1, RR.ranks_vectorised(np.ascontiguousarray(S.T), np.arange(5001, dtype=np.int32), t2i))
+    for k in res_ref:
+        assert abs(res_gpu[k] - res_ref[k]) <= 0.2, k
