@@ -34,6 +34,11 @@ def _req(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _flat(t: torch.Tensor) -> torch.Tensor:
+    """Flat-parameter convention: [P] or the DataParallel [1, P] slice (reparam_module.py:149 squeezes it)."""
+    return t.reshape(-1) if isinstance(t, torch.Tensor) else t
+
+
 def _scalar(v, device, name: str) -> torch.Tensor:
     """Scalars the reference keeps as tensors (syn_lr, logit scale) stay on the device: no host sync."""
     if isinstance(v, torch.Tensor):
@@ -53,8 +58,8 @@ def head_numel(dt: int, d: int) -> int:
 # --------------------------------------------------------------------------------------------------
 def flat_sgd_step(theta: torch.Tensor, grad: torch.Tensor, lr, out: torch.Tensor | None = None) -> torch.Tensor:
     """theta - lr * grad  (distill.py:582-583)."""
-    theta = _req(torch.squeeze(theta), "theta")
-    grad = _req(torch.squeeze(grad), "grad")
+    theta = _req(_flat(theta), "theta")
+    grad = _req(_flat(grad), "grad")
     if theta.shape != grad.shape:
         raise ValueError(f"theta {tuple(theta.shape)} and grad {tuple(grad.shape)} differ")
     out = torch.empty_like(theta) if out is None else _req(out, "out")
@@ -66,7 +71,7 @@ def flat_sgd_step(theta: torch.Tensor, grad: torch.Tensor, lr, out: torch.Tensor
 
 def match_loss(theta_K: torch.Tensor, theta_tgt: torch.Tensor, theta_0: torch.Tensor) -> torch.Tensor:
     """Returns a device tensor [num, den, num/den]  (distill.py:588-598)."""
-    a, b, c = (_req(torch.squeeze(t), n) for t, n in ((theta_K, "theta_K"), (theta_tgt, "theta_tgt"), (theta_0, "theta_0")))
+    a, b, c = (_req(_flat(t), n) for t, n in ((theta_K, "theta_K"), (theta_tgt, "theta_tgt"), (theta_0, "theta_0")))
     if not (a.shape == b.shape == c.shape):
         raise ValueError("match_loss: shape mismatch")
     out = torch.empty(3, dtype=torch.float32, device=a.device)
@@ -77,7 +82,7 @@ def match_loss(theta_K: torch.Tensor, theta_tgt: torch.Tensor, theta_0: torch.Te
 
 
 def match_loss_bwd(theta_K: torch.Tensor, theta_tgt: torch.Tensor, num_den: torch.Tensor, gout=None) -> torch.Tensor:
-    a, b = _req(torch.squeeze(theta_K), "theta_K"), _req(torch.squeeze(theta_tgt), "theta_tgt")
+    a, b = _req(_flat(theta_K), "theta_K"), _req(_flat(theta_tgt), "theta_tgt")
     nd = _req(num_den, "num_den")
     g = None if gout is None else _scalar(gout, a.device, "gout")
     out = torch.empty_like(a)
@@ -203,7 +208,7 @@ def itm_eval_host(scores_i2t: np.ndarray, scores_t2i: np.ndarray, t2i: np.ndarra
 # --------------------------------------------------------------------------------------------------
 def proj_head_forward(theta: torch.Tensor, Y: torch.Tensor, d: int, mask: torch.Tensor | None = None,
                       normalise: bool = False) -> torch.Tensor:
-    theta = _req(torch.squeeze(theta), "theta")
+    theta = _req(_flat(theta), "theta")
     Y = _req(Y, "Y")
     rows, dt = Y.shape
     if theta.numel() != head_numel(dt, d):
@@ -219,7 +224,7 @@ def proj_head_forward(theta: torch.Tensor, Y: torch.Tensor, d: int, mask: torch.
 
 def contrastive_step(theta: torch.Tensor, Y: torch.Tensor, U: torch.Tensor, scale, mask: torch.Tensor | None = None):
     """loss and first-order grads of one step (config 2): returns dict(loss, g_theta, dY, dU, dscale)."""
-    theta, Y, U = _req(torch.squeeze(theta), "theta"), _req(Y, "Y"), _req(U, "U")
+    theta, Y, U = _req(_flat(theta), "theta"), _req(Y, "Y"), _req(U, "U")
     B, dt = Y.shape
     d = U.shape[1]
     if theta.numel() != head_numel(dt, d):
@@ -250,7 +255,7 @@ class UnrollWorkspace:
 def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, workspace: UnrollWorkspace | None = None,
                    want_theta_K: bool = False):
     """distill.py:509-606 for one expert segment.  Returns dict(out5=[num,den,loss,dlr,dscale], ce, dY, dU[, theta_K])."""
-    theta0, theta_tgt = _req(torch.squeeze(theta0), "theta0"), _req(torch.squeeze(theta_tgt), "theta_tgt")
+    theta0, theta_tgt = _req(_flat(theta0), "theta0"), _req(_flat(theta_tgt), "theta_tgt")
     Y, U = _req(Y, "Y"), _req(U, "U")
     perms = _req(perms, "perms", torch.int64)
     K, B = perms.shape

@@ -67,6 +67,27 @@ def ranks_vectorised(scores: np.ndarray, gt_ptr: np.ndarray, gt_idx: np.ndarray)
     return out
 
 
+def rank_bounds(scores: np.ndarray, gt_lists) -> tuple:
+    """(optimistic, pessimistic) ranks per row: every tie resolved for / against the ground truth.
+
+    Any argsort -- stable or not, e.g. numpy's SIMD introsort whose tie order is machine-dependent -- yields a rank
+    inside these bounds, so the reference's recall on tied data must lie between the two recalls.
+    """
+    n = scores.shape[0]
+    lo, hi = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+    for r in range(n):
+        row = scores[r]
+        best_lo, best_hi = None, None
+        for c in gt_lists[r]:
+            s = row[int(c)]
+            g = int(np.count_nonzero(row > s))
+            e = int(np.count_nonzero(row == s))
+            best_lo = g if best_lo is None else min(best_lo, g)
+            best_hi = g + e - 1 if best_hi is None else min(best_hi, g + e - 1)
+        lo[r], hi[r] = best_lo, best_hi
+    return lo, hi
+
+
 def recall_dict(ranks_img: np.ndarray, ranks_txt: np.ndarray) -> dict:
     """epoch_original.py:131-161 / epoch.py:227-244: recall@1/5/10 in percent and the three means.
 

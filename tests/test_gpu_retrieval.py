@@ -26,10 +26,20 @@ def test_itm_eval_matches_reference_goldens(golden):
         _, _, S, St, (txt2img, img2txt) = _case_inputs(case)
         assert abs(float(np.float64(S).sum()) - case["score_checksum"]) < 1e-6 * max(1.0, abs(case["score_checksum"]))
         res, r_i, r_t = epoch.itm_eval(S, St, txt2img, img2txt, return_ranks=True)
-        for k, v in case["fork"].items():       # recall numbers: exact (integer counts / n)
-            assert res[k] == pytest.approx(v, abs=1e-12), (case["name"], k)
-        for k, v in case["orig"].items():
-            assert res[k] == pytest.approx(v, abs=1e-12), (case["name"], k)
+        if case["quant"]:
+            # ties near the top: np.argsort's order among equal scores is implementation-defined (SIMD introsort), so
+            # the reference's recall is only pinned to the interval spanned by the two extreme tie resolutions
+            lo_i, hi_i = RR.rank_bounds(S, [img2txt[i] for i in range(case["I"])])
+            lo_t, hi_t = RR.rank_bounds(St, [[txt2img[t]] for t in range(St.shape[0])])
+            best, worst = RR.recall_dict(lo_i, lo_t), RR.recall_dict(hi_i, hi_t)
+            for ref in (case["fork"], case["orig"]):
+                for k, v in ref.items():
+                    assert worst[k] - 1e-9 <= v <= best[k] + 1e-9, (case["name"], k)
+                    assert worst[k] - 1e-9 <= res[k] <= best[k] + 1e-9, (case["name"], k)
+        else:
+            for ref in (case["fork"], case["orig"]):        # recall numbers: exact (integer counts / n)
+                for k, v in ref.items():
+                    assert res[k] == pytest.approx(v, abs=1e-12), (case["name"], k)
         if "ranks_i2t" in case:                 # tie-free: the reference's ranks themselves, bit-exact
             assert np.array_equal(r_i, np.asarray(case["ranks_i2t"], dtype=np.int32)), case["name"]
             assert np.array_equal(r_t, np.asarray(case["ranks_t2i"], dtype=np.int32)), case["name"]
