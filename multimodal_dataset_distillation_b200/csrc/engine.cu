@@ -11,7 +11,7 @@
 //                          L_dot = <g_k, v>, H_k v, d/dY, d/dXn, d/ds;   a_k = a_{k+1} - lr H_k v (fused into the
 //                          tangent dW GEMM epilogues), dlr -= L_dot, dY[perm] -= lr dY_dot, ...
 #include "common.cuh"
-#include "gemm_simt.cuh"
+#include "gemm_dispatch.cuh"
 #include "head_kernels.cuh"
 #include "kernels.h"
 #include "engine.h"
@@ -36,16 +36,6 @@ Dims make_dims(int N, int B, int K, int dt, int d) {
   m.obt = m.og + d;
   m.P = m.obt + d;
   return m;
-}
-
-int pick_splits(int M, int N, int Ktot) {
-  const int tiles = ceil_div(M, GBM) * ceil_div(N, GBN);
-  const int nkb = ceil_div(Ktot, GBK);
-  int s = (kNumSMs + tiles - 1) / tiles;
-  const int max_s = nkb / 2 > 0 ? nkb / 2 : 1;
-  if (s > max_s) s = max_s;
-  if (s < 1) s = 1;
-  return s;
 }
 
 struct Saved {  // activations of one forward step, all fp32
@@ -78,7 +68,7 @@ size_t partial_floats(const Dims& m) {
   const int B = m.B, d = m.d, dt = m.dt;
   size_t mx = 0;
   auto upd = [&](int M, int N, int Kt) {
-    size_t v = (size_t)pick_splits(M, N, Kt) * M * N;
+    size_t v = (size_t)max_splits(M, N, Kt) * M * N;
     if (v > mx) mx = v;
   };
   upd(B, d, dt); upd(B, d, d); upd(B, d, 2 * d); upd(B, B, d); upd(B, d, B); upd(B, d, 2 * B); upd(B, dt, d);
@@ -151,33 +141,30 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   const size_t Bd = (size_t)B * d;
   const float *W1 = th + m.oW1, *b1 = th + m.ob1, *W2 = th + m.oW2, *b2 = th + m.ob2, *gam = th + m.og, *bet = th + m.obt;
   // p = Yb W1^T + b1 ; h = gelu(p)
-  int sp = pick_splits(B, d, dt);
-  launch_gemm<true, true>(gemm_ops(s.Yb, dt, W1, dt, B, d, dt), sp, w.pa, EpiStore{}, st);
+  int sp = 1;
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, W1, dt, B, d, dt), w.pa, &sp, st)));
   epi_p_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, b1, B, d, s.p, s.h);
   // f = h W2^T + b2 ; r = mask f + p ; LN ; normalise
-  sp = pick_splits(B, d, d);
-  launch_gemm<true, true>(gemm_ops(s.h, d, W2, d, B, d, d), sp, w.pa, EpiStore{}, st);
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.h, d, W2, d, B, d, d), w.pa, &sp, st)));
   ln_fwd_kernel<<<B, 256, d * sizeof(float), st>>>(w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr, s.yn,
                                                    s.rstd, s.nz);
   // S = scale * Xb Yn^T ; lse ; G ; loss
-  sp = pick_splits(B, B, d);
-  launch_gemm<true, true>(gemm_ops(s.Xb, d, s.yn, d, B, B, d), sp, w.pa, EpiStore{}, st);
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, s.yn, d, B, B, d), w.pa, &sp, st)));
   nce_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, (size_t)B * B, scale, B, s.S, s.lse_r);
   nce_cols_kernel<<<B, 128, 0, st>>>(s.S, B, s.lse_c);
   nce_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, B, s.G, ce_out);
   // dyn_raw[j,:] = sum_i G[i,j] Xb[i,:]
-  launch_gemm<false, false>(gemm_ops(s.G, B, s.Xb, d, B, d, B), 1, nullptr, EpiStore{w.pb, d, 1.0f}, st);
+  CHECK_RC((gemm_store<false, false>(gemm_ops(s.G, B, s.Xb, d, B, d, B), w.pb, d, 1.0f, st)));
   norm_ln_bwd_kernel<<<B, 256, 0, st>>>(w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d, s.dyn, s.q, s.dz, s.dr,
                                         s.df);
   // dh = df W2 ; dp = dh gelu'(p) + dr
-  sp = pick_splits(B, d, d);
-  launch_gemm<true, false>(gemm_ops(s.df, d, W2, d, B, d, d), sp, w.pa, EpiStore{}, st);
+  CHECK_RC((gemm_partial<true, false>(gemm_ops(s.df, d, W2, d, B, d, d), w.pa, &sp, st)));
   epi_dp_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, s.p, s.dr, Bd, s.dh, s.dp);
   // theta_{k+1}[W2] = theta_k[W2] - lr df^T h ; [W1] = ... - lr dp^T Yb ; small params
-  launch_gemm<false, false>(gemm_ops(s.df, d, s.h, d, d, d, B), 1, nullptr,
-                            EpiAxpy{upd_src ? upd_src + m.oW2 : nullptr, upd_dst + m.oW2, d, lr}, st);
-  launch_gemm<false, false>(gemm_ops(s.dp, d, s.Yb, dt, d, dt, B), 1, nullptr,
-                            EpiAxpy{upd_src ? upd_src + m.oW1 : nullptr, upd_dst + m.oW1, dt, lr}, st);
+  CHECK_RC((gemm_axpy<false, false>(gemm_ops(s.df, d, s.h, d, d, d, B), upd_src ? upd_src + m.oW2 : nullptr,
+                                    upd_dst + m.oW2, d, lr, st)));
+  CHECK_RC((gemm_axpy<false, false>(gemm_ops(s.dp, d, s.Yb, dt, d, dt, B), upd_src ? upd_src + m.oW1 : nullptr,
+                                    upd_dst + m.oW1, dt, lr, st)));
   colsum_update_kernel<<<ceil_div(d, 128), 128, 0, st>>>(
       s.dp, s.df, s.dz, s.rhat, B, d, lr, upd_src ? upd_src + m.ob1 : nullptr, upd_dst + m.ob1,
       upd_src ? upd_src + m.ob2 : nullptr, upd_dst + m.ob2, upd_src ? upd_src + m.og : nullptr, upd_dst + m.og,
@@ -197,43 +184,37 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   const float *W1 = th + m.oW1, *W2 = th + m.oW2, *gam = th + m.og;
   const float *V1 = v + m.oW1, *c1 = v + m.ob1, *V2 = v + m.oW2, *c2 = v + m.ob2, *gamd = v + m.og, *betd = v + m.obt;
   // pd = Yb V1^T + c1 ; hd = gelu'(p) pd
-  int sp = pick_splits(B, d, dt);
-  launch_gemm<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), sp, w.pa, EpiStore{}, st);
+  int sp = 1;
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), w.pa, &sp, st)));
   epi_pd_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, c1, s.p, B, d, w.pd, w.hd);
   // fd = hd W2^T + h V2^T + c2 ; LN / normalise tangents
-  sp = pick_splits(B, d, 2 * d);
-  launch_gemm<true, true>(gemm_ops2(w.hd, d, W2, d, d, s.h, d, V2, d, d, B, d), sp, w.pa, EpiStore{}, st);
+  CHECK_RC((gemm_partial<true, true>(gemm_ops2(w.hd, d, W2, d, d, s.h, d, V2, d, d, B, d), w.pa, &sp, st)));
   ln_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz, gam,
                                                        gamd, betd, d, w.rhatd, w.ynd, w.t, w.nzd);
   // Sd = scale Xb Ynd^T ; rho, kappa, Gd ; L_dot ; dlr, dscale
-  sp = pick_splits(B, B, d);
-  launch_gemm<true, true>(gemm_ops(s.Xb, d, w.ynd, d, B, B, d), sp, w.pa, EpiStore{}, st);
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, w.ynd, d, B, B, d), w.pa, &sp, st)));
   nce_t_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, BB, scale, s.S, s.lse_r, s.G, B, w.Sd, w.rho, w.rowA);
   nce_t_cols_kernel<<<B, 128, 0, st>>>(s.S, s.lse_c, w.Sd, B, w.kap);
   nce_t_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, w.Sd, w.rho, w.kap, B, w.Gd, w.rowB);
   nce_t_finish_kernel<<<1, 128, 0, st>>>(w.rowA, w.rowB, B, lr, scale, dlr, dscale);
   // dXn_dot = scale (Gd Yn + G Ynd)  ->  dXn[perm] -= lr * scale * raw
-  launch_gemm<true, false>(gemm_ops2(w.Gd, B, s.yn, d, B, s.G, B, w.ynd, d, B, B, d), 1, nullptr,
-                           EpiStore{w.pa, d, 1.0f}, st);
+  CHECK_RC((gemm_store<true, false>(gemm_ops2(w.Gd, B, s.yn, d, B, s.G, B, w.ynd, d, B, B, d), w.pa, d, 1.0f, st)));
   scatter_add_rows_kernel<<<B, 256, 0, st>>>(w.pa, 1, Bd, perm, d, lr, scale, w.dXn);
   // dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
-  launch_gemm<false, false>(gemm_ops(w.Gd, B, s.Xb, d, B, d, B), 1, nullptr, EpiStore{w.pb, d, 1.0f}, st);
+  CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, B, s.Xb, d, B, d, B), w.pb, d, 1.0f, st)));
   norm_ln_bwd_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd,
                                                                 s.dz, s.rhat, w.rhatd, s.rstd, w.t, s.dr, gam, gamd,
                                                                 mask, d, w.dzd, w.drd, w.dfd);
   // dhd = dfd W2 + df V2 ; dpd
-  sp = pick_splits(B, d, 2 * d);
-  launch_gemm<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), sp, w.pa, EpiStore{}, st);
+  CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), w.pa, &sp, st)));
   epi_dpd_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, s.p, w.pd, s.dh, w.drd, Bd, w.dpd);
   // dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.)
-  sp = pick_splits(B, dt, 2 * d);
-  launch_gemm<true, false>(gemm_ops2(w.dpd, d, W1, dt, d, s.dp, d, V1, dt, d, B, dt), sp, w.pb, EpiStore{}, st);
+  CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dpd, d, W1, dt, d, s.dp, d, V1, dt, d, B, dt), w.pb, &sp, st)));
   scatter_add_rows_kernel<<<B, 256, 0, st>>>(w.pb, sp, (size_t)B * dt, perm, dt, lr, nullptr, dY);
   // a_k = a_{k+1} - lr * H v   (W2, W1 tiles fused into the GEMM epilogues; small params by column sums)
-  launch_gemm<false, false>(gemm_ops2(w.dfd, d, s.h, d, B, s.df, d, w.hd, d, B, d, d), 1, nullptr,
-                            EpiAxpy{v + m.oW2, a_out + m.oW2, d, lr}, st);
-  launch_gemm<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), 1, nullptr,
-                            EpiAxpy{v + m.oW1, a_out + m.oW1, dt, lr}, st);
+  CHECK_RC((gemm_axpy<false, false>(gemm_ops2(w.dfd, d, s.h, d, B, s.df, d, w.hd, d, B, d, d), v + m.oW2, a_out + m.oW2, d,
+                                    lr, st)));
+  CHECK_RC((gemm_axpy<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), v + m.oW1, a_out + m.oW1, dt, lr, st)));
   colsum_tangent_update_kernel<<<ceil_div(d, 128), 128, 0, st>>>(
       w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
       v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
@@ -327,13 +308,13 @@ int contrastive_step(const float* theta, const float* Y, const float* U, const f
   CHECK_RC(forward_step(m, w, s, theta, nullptr, g_theta, w.neg_one, scale, mask, loss, st));
   // dY = dp W1
   if (dY) {
-    const int sp = pick_splits(B, dt, d);
-    launch_gemm<true, false>(gemm_ops(s.dp, d, theta + m.oW1, dt, B, dt, d), sp, w.pa, EpiStore{}, st);
+    int sp = 1;
+    CHECK_RC((gemm_partial<true, false>(gemm_ops(s.dp, d, theta + m.oW1, dt, B, dt, d), w.pa, &sp, st)));
     reduce_slabs_kernel<<<ew_grid((size_t)B * dt), 256, 0, st>>>(w.pa, sp, (size_t)B * dt, (size_t)B * dt, dY);
   }
   // dU = normalise_bwd(scale * G Yn)
   if (dU) {
-    launch_gemm<true, false>(gemm_ops(s.G, B, s.yn, d, B, d, B), 1, nullptr, EpiStore{w.pb, d, 1.0f}, st);
+    CHECK_RC((gemm_store<true, false>(gemm_ops(s.G, B, s.yn, d, B, d, B), w.pb, d, 1.0f, st)));
     row_normalise_bwd_kernel<<<B, 256, 0, st>>>(w.Xn, w.un, w.pb, scale, d, dU);
   }
   // dscale = sum(G * S) / scale
@@ -346,7 +327,7 @@ int contrastive_step(const float* theta, const float* Y, const float* U, const f
 size_t proj_head_workspace_bytes(int rows, int dt, int d) {
   if (rows <= 0 || dt <= 0 || d <= 0) return 0;
   const size_t Rd = (size_t)rows * d;
-  const size_t s1 = (size_t)pick_splits(rows, d, dt) * Rd, s2 = (size_t)pick_splits(rows, d, d) * Rd;
+  const size_t s1 = (size_t)max_splits(rows, d, dt) * Rd, s2 = (size_t)max_splits(rows, d, d) * Rd;
   const size_t part = s1 > s2 ? s1 : s2;
   return (part + 2 * Rd) * sizeof(float) + 1024;
 }
@@ -365,11 +346,10 @@ int proj_head_forward(const float* theta, const float* Y, const float* mask, int
   float* p = reinterpret_cast<float*>(workspace);
   float* h = p + Rd;
   float* part = h + Rd;
-  int sp = pick_splits(rows, d, dt);
-  launch_gemm<true, true>(gemm_ops(Y, dt, theta + m.oW1, dt, rows, d, dt), sp, part, EpiStore{}, st);
+  int sp = 1;
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(Y, dt, theta + m.oW1, dt, rows, d, dt), part, &sp, st)));
   epi_p_kernel<<<ew_grid(Rd), 256, 0, st>>>(part, sp, Rd, theta + m.ob1, rows, d, p, h);
-  sp = pick_splits(rows, d, d);
-  launch_gemm<true, true>(gemm_ops(h, d, theta + m.oW2, d, rows, d, d), sp, part, EpiStore{}, st);
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(h, d, theta + m.oW2, d, rows, d, d), part, &sp, st)));
   ln_fwd_kernel<<<rows, 256, d * sizeof(float), st>>>(part, sp, Rd, theta + m.ob2, mask, p, theta + m.og,
                                                       theta + m.obt, d, nullptr, z, zn, nullptr, nullptr);
   return check_launch("proj_head_forward");

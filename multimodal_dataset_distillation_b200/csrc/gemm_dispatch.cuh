@@ -1,0 +1,63 @@
+// GEMM front end of the engine: tcgen05 (3xTF32, TMA-fed) when the operands satisfy the tensor-map constraints,
+// fp32 CUDA-core kernel otherwise (tiny test shapes, unaligned leading dimensions, MN-major extents not % 32).
+// VLDD_GEMM=simt forces the CUDA-core kernel (A/B runs and debugging).
+#pragma once
+#include <cstdlib>
+#include <cstring>
+
+#include "gemm_simt.cuh"
+#include "tc_gemm_host.cuh"
+
+namespace vldd {
+
+inline bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLDD_GEMM");
+    v = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+inline int simt_pick_splits(int M, int N, int Ktot) {
+  const int tiles = ceil_div(M, GBM) * ceil_div(N, GBN);
+  const int nkb = ceil_div(Ktot, GBK);
+  int s = (kNumSMs + tiles - 1) / tiles;
+  const int max_s = nkb / 2 > 0 ? nkb / 2 : 1;
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
+}
+// upper bound of the split count either backend may choose (workspace sizing)
+inline int max_splits(int M, int N, int Ktot) {
+  const int a = simt_pick_splits(M, N, Ktot), b = tc::pick_splits(M, N, Ktot);
+  return a > b ? a : b;
+}
+
+// partial slabs: part[z][M*N], returns the split count through *splits
+template <bool AK, bool BKm>
+inline int gemm_partial(const GemmOperands& g, float* part, int* splits, cudaStream_t st) {
+  const int Kt = g.K0 + g.K1;
+  if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) {
+    *splits = tc::pick_splits(g.M, g.N, Kt);
+    return tc::launch<AK, BKm, 3>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st);
+  }
+  *splits = simt_pick_splits(g.M, g.N, Kt);
+  launch_gemm<AK, BKm>(g, *splits, part, EpiStore{}, st);
+  return VLDD_OK;
+}
+// C = alpha * A B
+template <bool AK, bool BKm>
+inline int gemm_store(const GemmOperands& g, float* C, int ldc, float alpha, cudaStream_t st) {
+  if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) return tc::launch<AK, BKm, 3>(g, 1, tc::EpiScale{C, ldc, alpha}, st);
+  launch_gemm<AK, BKm>(g, 1, nullptr, EpiStore{C, ldc, alpha}, st);
+  return VLDD_OK;
+}
+// dst = src - (*lr) * A B      (src nullable)
+template <bool AK, bool BKm>
+inline int gemm_axpy(const GemmOperands& g, const float* src, float* dst, int ld, const float* lr, cudaStream_t st) {
+  if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) return tc::launch<AK, BKm, 3>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st);
+  launch_gemm<AK, BKm>(g, 1, nullptr, EpiAxpy{src, dst, ld, lr}, st);
+  return VLDD_OK;
+}
+
+}  // namespace vldd

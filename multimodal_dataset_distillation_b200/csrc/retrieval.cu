@@ -7,7 +7,7 @@
 //   rank(c) = #{j : s_j > s_c} + #{j < c : s_j == s_c};  i2t takes the minimum over the image's GT captions,
 //   which is the rank of the GT caption with the highest score (lowest index among equals).
 #include "common.cuh"
-#include "gemm_simt.cuh"
+#include "gemm_dispatch.cuh"
 #include "kernels.h"
 
 namespace vldd {
@@ -123,14 +123,16 @@ int sim_scores(const float* img, const float* txt, int I, int T, int D, float sc
   if (I <= 0 || T <= 0) return VLDD_OK;
   if (S_i2t) {
     GemmOperands g = gemm_ops(img, D, txt, D, I, T, D);
-    launch_gemm<true, true>(g, 1, nullptr, EpiStore{S_i2t, T, scale}, st);
-    int rc = check_launch("sim_scores i2t");
+    int rc = gemm_store<true, true>(g, S_i2t, T, scale, st);
+    if (rc) return rc;
+    rc = check_launch("sim_scores i2t");
     if (rc) return rc;
   }
   if (S_t2i) {
     GemmOperands g = gemm_ops(txt, D, img, D, T, I, D);
-    launch_gemm<true, true>(g, 1, nullptr, EpiStore{S_t2i, I, scale}, st);
-    int rc = check_launch("sim_scores t2i");
+    int rc = gemm_store<true, true>(g, S_t2i, I, scale, st);
+    if (rc) return rc;
+    rc = check_launch("sim_scores t2i");
     if (rc) return rc;
   }
   return VLDD_OK;

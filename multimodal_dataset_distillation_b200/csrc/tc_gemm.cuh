@@ -1,0 +1,336 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a with fp32-grade accuracy (3xTF32 operand split).
+//
+//   C[m,n] = sum_k opA(A)[m,k] * opB(B)[k,n]      (+ optional second K segment A1/B1, same shapes)
+//
+// One 128x128 output tile per CTA, K range split across blockIdx.z (partial slabs) or fused epilogue.
+// Warp roles (192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor loads of the fp32 A/B k-blocks (128 x 32 floats each, SWIZZLE_128B)
+//   warp 1      TMEM allocator + MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8, accumulator in TMEM
+//   warps 2..5  operand splitter, then epilogue.  tf32 keeps 10 mantissa bits, so every fp32 operand x is split in
+//               shared memory into hi = rna_tf32(x) (written in place) and lo = x - hi (second buffer, same swizzled
+//               offsets); the MMA warp issues hi*hi + lo*hi + hi*lo -> error ~2^-21 per product instead of 2^-11.
+//               Afterwards the same warps drain TMEM with tcgen05.ld (32 lanes x 32 columns per instruction) and run
+//               the epilogue (partial-slab store / alpha store / theta - lr*acc).
+// Operand layouts: K-major  = row-major [rows, K]  (2-D tensor map, box 32 x 128);
+//                  MN-major = row-major [K, rows]  (3-D tensor map {32, K, rows/32}, box 32 x 32 x 4), used for
+//                  dH = dF W2 and the weight-gradient GEMMs dW = dF^T H, whose operands are contiguous along M/N.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace vldd {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;          // BK floats = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;                           // tf32
+constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB per operand per stage
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 128;
+
+template <int kSplit>
+struct Cfg {
+  static constexpr int kStages = kSplit == 3 ? 3 : 6;
+  static constexpr int kStageBytes = (kSplit == 3 ? 4 : 2) * TILE_BYTES;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors --------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version bit set (cute::UMMA::SmemDescriptor layout)
+//   layout_type 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only legal layout for MN-major
+//   tf32 operands: 128-byte rows whose four 32-byte segments are XOR-ed with (row & 3), TMA SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor layout)
+__host__ __device__ constexpr uint32_t instr_desc_tf32(bool a_mn_major, bool b_mn_major, int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- epilogues -------------------------------------------------------------------------------------------
+struct EpiPartial {   // raw fp32 tile -> slab z of [splits][M*N]
+  float* part; long long stride;
+  __device__ __forceinline__ float* row_ptr(int m, int N, int z) const { return part + (size_t)z * stride + (size_t)m * N; }
+  __device__ __forceinline__ float apply(float acc, const float*, int) const { return acc; }
+  __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
+};
+struct EpiScale {     // C = alpha * acc
+  float* C; int ldc; float alpha;
+  __device__ __forceinline__ float* row_ptr(int m, int, int) const { return C + (size_t)m * ldc; }
+  __device__ __forceinline__ float apply(float acc, const float*, int) const { return alpha * acc; }
+  __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
+};
+struct EpiAxpyTC {    // dst = src - (*lr) * acc   (src nullable = 0)
+  const float* src; float* dst; int ld; const float* lr;
+  __device__ __forceinline__ float* row_ptr(int m, int, int) const { return dst + (size_t)m * ld; }
+  __device__ __forceinline__ const float* src_row(int m) const { return src ? src + (size_t)m * ld : nullptr; }
+  __device__ __forceinline__ float apply(float acc, const float* srow, int n) const {
+    return (srow ? srow[n] : 0.f) - (*lr) * acc;
+  }
+};
+
+#ifdef VLDD_TC_DEBUG
+__constant__ uint32_t g_dbg[4];   // {lbo, sbo, step, unused} overrides for MN-major operands (developer harness only)
+#endif
+
+struct Maps {
+  CUtensorMap a0, b0, a1, b1;
+};
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, Epi epi) {
+  using C = Cfg<kSplit>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;                       // TMA landed
+  uint64_t* ready = bars + C::kStages;         // split done (kSplit == 3 only)
+  uint64_t* empty = bars + 2 * C::kStages;     // MMAs reading the stage have completed
+  uint64_t* tmem_full = bars + 3 * C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb0 = (K0 + BK - 1) / BK, nkb1 = (K1 + BK - 1) / BK, nkb = nkb0 + nkb1;
+  const int splits = gridDim.z;
+  const int per = (nkb + splits - 1) / splits;
+  const int kb_begin = blockIdx.z * per, kb_end = min(nkb, kb_begin + per);
+  const int my_kb = max(kb_end - kb_begin, 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a0);
+    tma_prefetch_desc(&maps.b0);
+    if (K1 > 0) { tma_prefetch_desc(&maps.a1); tma_prefetch_desc(&maps.b1); }
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < my_kb; ++i) {
+        const int s = i % C::kStages, round = i / C::kStages;
+        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+        const int kb = kb_begin + i;
+        const bool seg1 = kb >= nkb0;
+        const int k = (seg1 ? kb - nkb0 : kb) * BK;
+        const CUtensorMap* ma = seg1 ? &maps.a1 : &maps.a0;
+        const CUtensorMap* mb = seg1 ? &maps.b1 : &maps.b0;
+        uint8_t* sa = smem + s * C::kStageBytes;
+        uint8_t* sb = sa + TILE_BYTES;
+        mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+        if (A_KMAJOR) tma_load_2d(sa, ma, &full[s], k, m0); else tma_load_3d(sa, ma, &full[s], 0, k, m0 / 32);
+        if (B_KMAJOR) tma_load_2d(sb, mb, &full[s], k, n0); else tma_load_3d(sb, mb, &full[s], 0, k, n0 / 32);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_tf32(!A_KMAJOR, !B_KMAJOR, BM, BN);
+      // K-major  (SWIZZLE_128B):         8-row groups 1024 B apart (SBO), k-step of 8 floats = +32 B inside the row
+      // MN-major (SWIZZLE_128B_BASE32B): 32-wide MN chunks 4096 B apart (LBO), 4-k-row groups 512 B apart (SBO),
+      //                                  k-step of 8 k-rows = +1024 B
+#ifdef VLDD_TC_DEBUG
+      const uint32_t a_lbo = A_KMAJOR ? 16 : g_dbg[0], a_sbo = A_KMAJOR ? 1024 : g_dbg[1], a_step = A_KMAJOR ? 32 : g_dbg[2];
+      const uint32_t b_lbo = B_KMAJOR ? 16 : g_dbg[0], b_sbo = B_KMAJOR ? 1024 : g_dbg[1], b_step = B_KMAJOR ? 32 : g_dbg[2];
+#else
+      constexpr uint32_t a_lbo = A_KMAJOR ? 16 : 4096, a_sbo = A_KMAJOR ? 1024 : 512, a_step = A_KMAJOR ? 32 : 1024;
+      constexpr uint32_t b_lbo = B_KMAJOR ? 16 : 4096, b_sbo = B_KMAJOR ? 1024 : 512, b_step = B_KMAJOR ? 32 : 1024;
+#endif
+      constexpr uint32_t a_lt = A_KMAJOR ? 2 : 1, b_lt = B_KMAJOR ? 2 : 1;
+      uint32_t accumulate = 0;
+      for (int i = 0; i < my_kb; ++i) {
+        const int s = i % C::kStages, round = i / C::kStages;
+        mbar_wait(kSplit == 3 ? &ready[s] : &full[s], round & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * C::kStageBytes), sb = sa + TILE_BYTES;
+        const uint32_t sal = sb + TILE_BYTES, sbl = sal + TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt), db = smem_desc(sb + k * b_step, b_lbo, b_sbo, b_lt);
+          if (kSplit == 3) {
+            const uint64_t dal = smem_desc(sal + k * a_step, a_lbo, a_sbo, a_lt), dbl = smem_desc(sbl + k * b_step, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_base, dal, db, idesc, accumulate);
+            umma_tf32(tmem_base, da, dbl, idesc, 1);
+            umma_tf32(tmem_base, da, db, idesc, 1);
+          } else {
+            umma_tf32(tmem_base, da, db, idesc, accumulate);
+          }
+          accumulate = 1;
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ===== operand splitter (kSplit == 3), then epilogue =====
+    const int t = threadIdx.x - 64;   // 0..127
+    if (kSplit == 3) {
+      for (int i = 0; i < my_kb; ++i) {
+        const int s = i % C::kStages, round = i / C::kStages;
+        mbar_wait(&full[s], round & 1);
+        float4* hi = reinterpret_cast<float4*>(smem + s * C::kStageBytes);           // A then B, 2 x 16 KB contiguous
+        float4* lo = reinterpret_cast<float4*>(smem + s * C::kStageBytes + 2 * TILE_BYTES);
+#pragma unroll 4
+        for (int j = t; j < 2 * TILE_BYTES / 16; j += 128) {
+          const float4 v = hi[j];
+          float4 h, l;
+          uint32_t u;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
+          hi[j] = h;
+          lo[j] = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(&ready[s]);
+      }
+    }
+    // epilogue: TMEM lane quadrant is fixed by warp index % 4
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int m = m0 + row;
+    float* out_row = (m < M) ? epi.row_ptr(m, N, blockIdx.z) : nullptr;
+    const float* src_row = (m < M) ? epi.src_row(m) : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
+      if (my_kb > 0) {
+        tmem_ld_32x32(taddr, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (out_row != nullptr) {
+        const int nb = n0 + c;
+        if (nb + 31 < N && ((reinterpret_cast<uintptr_t>(out_row + nb) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = epi.apply(v[j + 0], src_row, nb + j + 0);
+            o.y = epi.apply(v[j + 1], src_row, nb + j + 1);
+            o.z = epi.apply(v[j + 2], src_row, nb + j + 2);
+            o.w = epi.apply(v[j + 3], src_row, nb + j + 3);
+            *reinterpret_cast<float4*>(out_row + nb + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < N) out_row[nb + j] = epi.apply(v[j], src_row, nb + j);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace tc
+}  // namespace vldd

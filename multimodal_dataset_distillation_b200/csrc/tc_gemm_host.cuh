@@ -1,0 +1,137 @@
+// Host side of the tcgen05 GEMM: tensor-map construction (cached: operands live at fixed workspace addresses, so
+// each map is encoded once), eligibility checks and the launcher.
+#pragma once
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm_simt.cuh"
+#include "tc_gemm.cuh"
+
+namespace vldd {
+namespace tc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int rows, K, ld, kmajor;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && K == o.K && ld == o.ld && kmajor == o.kmajor; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= (size_t)k.K * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= (size_t)(k.ld * 2 + k.kmajor) * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+// operand with `rows` = its M or N extent.  kmajor: element (row,k) at ptr[row*ld + k]; else at ptr[k*ld + row].
+inline bool operand_ok(const float* ptr, int rows, int K, int ld, bool kmajor) {
+  if (ptr == nullptr || !aligned16(ptr) || ld % 4 != 0 || K <= 0 || rows <= 0) return false;
+  if (!kmajor && rows % 32 != 0) return false;
+  return true;
+}
+
+inline int get_map(const float* ptr, int rows, int K, int ld, bool kmajor, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, rows, K, ld, kmajor ? 1 : 0};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return VLDD_OK; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VLDD_ERR_CUDA; }
+  CUtensorMap m;
+  CUresult r;
+  if (kmajor) {
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    const cuuint32_t es[2] = {1, 1};
+    r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, es,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[3] = {32, (cuuint64_t)K, (cuuint64_t)(rows / 32)};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+    const cuuint32_t box[3] = {32, (cuuint32_t)BK, 4};
+    const cuuint32_t es[3] = {1, 1, 1};
+    r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, es,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for rows=%d K=%d ld=%d kmajor=%d", (int)r, rows, K, ld, (int)kmajor);
+    return VLDD_ERR_CUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return VLDD_OK;
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+inline bool gemm_ok(const GemmOperands& g) {
+  if (!operand_ok(g.A0, g.M, g.K0, g.lda0, A_KMAJOR) || !operand_ok(g.B0, g.N, g.K0, g.ldb0, B_KMAJOR)) return false;
+  if (g.K1 > 0 && (!operand_ok(g.A1, g.M, g.K1, g.lda1, A_KMAJOR) || !operand_ok(g.B1, g.N, g.K1, g.ldb1, B_KMAJOR)))
+    return false;
+  return true;
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi>
+inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st) {
+  using C = Cfg<kSplit>;
+  auto kern = tc_gemm_kernel<A_KMAJOR, B_KMAJOR, kSplit, Epi>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", C::kSmemBytes, cudaGetErrorString(e)); return VLDD_ERR_CUDA; }
+    configured = true;
+  }
+  Maps maps;
+  int rc = get_map(g.A0, g.M, g.K0, g.lda0, A_KMAJOR, &maps.a0);
+  if (rc) return rc;
+  rc = get_map(g.B0, g.N, g.K0, g.ldb0, B_KMAJOR, &maps.b0);
+  if (rc) return rc;
+  if (g.K1 > 0) {
+    rc = get_map(g.A1, g.M, g.K1, g.lda1, A_KMAJOR, &maps.a1);
+    if (rc) return rc;
+    rc = get_map(g.B1, g.N, g.K1, g.ldb1, B_KMAJOR, &maps.b1);
+    if (rc) return rc;
+  } else {
+    maps.a1 = maps.a0;
+    maps.b1 = maps.b0;
+  }
+  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), splits);
+  kern<<<grid, NUM_THREADS, C::kSmemBytes, st>>>(maps, g.M, g.N, g.K0, g.K1, epi);
+  return VLDD_OK;
+}
+
+// number of K splits so that tiles x splits ~ one wave of 148 SMs, each split keeping >= 2 k-blocks
+inline int pick_splits(int M, int N, int Ktot) {
+  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int nkb = ceil_div(Ktot, BK);
+  int s = (kNumSMs + tiles - 1) / tiles;
+  const int max_s = nkb / 2 > 0 ? nkb / 2 : 1;
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
+}
+
+}  // namespace tc
+}  // namespace vldd
