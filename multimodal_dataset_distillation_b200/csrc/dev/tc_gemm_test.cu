@@ -30,7 +30,7 @@ static float* dev_rand(size_t n, unsigned seed, float scale = 1.0f) {
 
 struct Res { double maxerr, maxref; float ms; };
 
-template <bool AK, bool BKm, int kSplit>
+template <bool AK, bool BKm, int kSplit, int kStagesT = 0>
 static Res run_case(const char* name, int M, int N, int K0, int K1, int splits, bool axpy) {
   const size_t asz0 = (size_t)M * K0, bsz0 = (size_t)N * K0, asz1 = (size_t)M * (K1 ? K1 : 1), bsz1 = (size_t)N * (K1 ? K1 : 1);
   float *A0 = dev_rand(asz0, 1), *B0 = dev_rand(bsz0, 2), *A1 = dev_rand(asz1, 3), *B1 = dev_rand(bsz1, 4);
@@ -47,12 +47,12 @@ static Res run_case(const char* name, int M, int N, int K0, int K1, int splits, 
   if (!tc::gemm_ok<AK, BKm>(g)) { printf("%s: not eligible\n", name); exit(1); }
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   float ms = 0;
-  for (int rep = 0; rep < 3; ++rep) {
+  for (int rep = 0; rep < 5; ++rep) {
     CK(cudaEventRecord(e0));
     int rc;
-    if (axpy) rc = tc::launch<AK, BKm, kSplit>(g, 1, tc::EpiAxpyTC{src, Ctc, N, lr}, 0);
-    else if (splits > 1) rc = tc::launch<AK, BKm, kSplit>(g, splits, tc::EpiPartial{part, (long long)csz}, 0);
-    else rc = tc::launch<AK, BKm, kSplit>(g, 1, tc::EpiScale{Ctc, N, 1.0f}, 0);
+    if (axpy) rc = tc::launch<AK, BKm, kSplit, tc::EpiAxpyTC, kStagesT>(g, 1, tc::EpiAxpyTC{src, Ctc, N, lr}, 0);
+    else if (splits > 1) rc = tc::launch<AK, BKm, kSplit, tc::EpiPartial, kStagesT>(g, splits, tc::EpiPartial{part, (long long)csz}, 0);
+    else rc = tc::launch<AK, BKm, kSplit, tc::EpiScale, kStagesT>(g, 1, tc::EpiScale{Ctc, N, 1.0f}, 0);
     if (rc) { printf("%s: launch failed: %s\n", name, g_err); exit(1); }
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
@@ -99,6 +99,18 @@ int main(int argc, char** argv) {
   if (want(c++)) run_case<true, true, 3>("NT sims 1000x5000x768", 1000, 5000, 768, 0, 1, false);
   if (want(c++)) run_case<true, true, 1>("NT sims 1x 1000x5000x768", 1000, 5000, 768, 0, 1, false);
   if (want(c++)) run_case<true, false, 3>("NN dY dual", 100, 768, 2304, 2304, 6, false);
+  // stage-count / split-count experiments
+  if (want(c++)) run_case<false, false, 3, 1>("TN dW2 axpy stages=1", 2304, 2304, 100, 0, 1, true);
+  if (want(c++)) run_case<false, false, 3, 2>("TN dW2 axpy stages=2", 2304, 2304, 100, 0, 1, true);
+  if (want(c++)) run_case<false, false, 3, 1>("TN dW2t dual axpy stages=1", 2304, 2304, 100, 100, 1, true);
+  if (want(c++)) run_case<false, false, 3, 1>("TN dW1 axpy stages=1", 2304, 768, 100, 0, 1, true);
+  if (want(c++)) run_case<true, true, 3, 1>("NT F2 splits=16 stages=1", 100, 2304, 2304, 0, 16, false);
+  if (want(c++)) run_case<true, true, 3, 1>("NT F2 splits=24 stages=1", 100, 2304, 2304, 0, 24, false);
+  if (want(c++)) run_case<true, true, 3, 2>("NT F2 splits=8 stages=2", 100, 2304, 2304, 0, 8, false);
+  if (want(c++)) run_case<true, true, 3, 1>("NT F2 splits=8 stages=1", 100, 2304, 2304, 0, 8, false);
+  if (want(c++)) run_case<true, true, 3, 1>("NT sims stages=1", 1000, 5000, 768, 0, 1, false);
+  if (want(c++)) run_case<true, true, 1, 2>("NT F2 1xTF32 splits=8 stages=2", 100, 2304, 2304, 0, 8, false);
+  if (want(c++)) run_case<true, true, 1, 2>("NT F2 1xTF32 splits=16 stages=2", 100, 2304, 2304, 0, 16, false);
   printf("done\n");
   return 0;
 }

@@ -16,6 +16,9 @@
 #include "kernels.h"
 #include "engine.h"
 
+#include <mutex>
+#include <vector>
+
 namespace vldd {
 
 namespace {
@@ -56,8 +59,8 @@ struct Bump {
 
 struct Work {
   Saved sv[64];
-  float *traj, *adj0, *adj1, *Xn, *un, *dXn;
-  float *pa, *pb;                      // GEMM partial slabs / raw outputs
+  float *traj, *tgt, *adj0, *adj1, *Xn, *un, *dXn;
+  float *pa, *pb, *pc, *pe;            // GEMM partial slabs / raw outputs (pc, pe: side-stream branches)
   float *pd, *hd, *rhatd, *ynd, *dzd, *drd, *dfd, *dpd, *t, *nzd, *Sd, *Gd, *rho, *kap, *rowA, *rowB;
   float *neg_one;                      // device constant -1 (first-order API)
   void* ml_scratch;
@@ -80,6 +83,7 @@ void carve(Work& w, const Dims& m, void* base) {
   Bump b{reinterpret_cast<char*>(base), 0, 0};
   const size_t Bd = (size_t)m.B * m.d, BB = (size_t)m.B * m.B;
   w.traj = b.f((size_t)(m.K + 1) * m.P);
+  w.tgt = b.f(m.P);
   w.adj0 = b.f(m.P);
   w.adj1 = b.f(m.P);
   w.Xn = b.f((size_t)m.N * m.d);
@@ -96,6 +100,8 @@ void carve(Work& w, const Dims& m, void* base) {
   const size_t pf = partial_floats(m);
   w.pa = b.f(pf);
   w.pb = b.f(pf);
+  w.pc = b.f(Bd);
+  w.pe = b.f((size_t)max_splits(m.B, m.dt, 2 * m.d) * m.B * m.dt);
   w.pd = b.f(Bd); w.hd = b.f(Bd); w.rhatd = b.f(Bd); w.ynd = b.f(Bd); w.dzd = b.f(Bd); w.drd = b.f(Bd);
   w.dfd = b.f(Bd); w.dpd = b.f(Bd);
   w.t = b.f(m.B); w.nzd = b.f(m.B); w.rho = b.f(m.B); w.kap = b.f(m.B); w.rowA = b.f(m.B); w.rowB = b.f(m.B);
@@ -132,11 +138,51 @@ inline int ew_grid(size_t n) {
 
 #define CHECK_RC(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 
+// Independent branches of a step (weight-gradient GEMMs, the dXn / dY side products) run on two side streams that
+// fork from / join into the main stream with events; under graph capture this becomes parallel branches of the graph.
+struct Lanes {
+  cudaStream_t main, s1, s2;
+  bool s1_busy, s2_busy;
+};
+std::mutex g_lane_mu;
+cudaStream_t g_side1 = nullptr, g_side2 = nullptr;
+std::vector<cudaEvent_t> g_events;
+size_t g_event_next = 0;
+
+int lanes_init(Lanes& L, cudaStream_t main) {
+  std::lock_guard<std::mutex> lock(g_lane_mu);
+  if (g_side1 == nullptr) {
+    VLDD_CUDA(cudaStreamCreateWithFlags(&g_side1, cudaStreamNonBlocking));
+    VLDD_CUDA(cudaStreamCreateWithFlags(&g_side2, cudaStreamNonBlocking));
+  }
+  L.main = main; L.s1 = g_side1; L.s2 = g_side2; L.s1_busy = false; L.s2_busy = false;
+  g_event_next = 0;
+  return VLDD_OK;
+}
+int lane_edge(cudaStream_t from, cudaStream_t to) {   // everything enqueued on `from` so far happens-before later work on `to`
+  if (g_event_next == g_events.size()) {
+    cudaEvent_t e;
+    VLDD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g_events.push_back(e);
+  }
+  cudaEvent_t e = g_events[g_event_next++];
+  VLDD_CUDA(cudaEventRecord(e, from));
+  VLDD_CUDA(cudaStreamWaitEvent(to, e, 0));
+  return VLDD_OK;
+}
+int lanes_join(Lanes& L) {
+  if (L.s1_busy) { CHECK_RC(lane_edge(L.s1, L.main)); L.s1_busy = false; }
+  if (L.s2_busy) { CHECK_RC(lane_edge(L.s2, L.main)); L.s2_busy = false; }
+  return VLDD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One forward (first-order) step.  th_src/th_dst: theta_k -> theta_{k+1} (th_src == nullptr: dst = -lr*g).
 // ---------------------------------------------------------------------------------------------------
 int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float* upd_src, float* upd_dst,
-                 const float* lr, const float* scale, const float* mask, float* ce_out, cudaStream_t st) {
+                 const float* lr, const float* scale, const float* mask, float* ce_out, Lanes& L) {
+  cudaStream_t st = L.main;
+  CHECK_RC(lanes_join(L));          // theta_k must be complete (previous step's weight-gradient branches)
   const int B = m.B, d = m.d, dt = m.dt;
   const size_t Bd = (size_t)B * d;
   const float *W1 = th + m.oW1, *b1 = th + m.ob1, *W2 = th + m.oW2, *b2 = th + m.ob2, *gam = th + m.og, *bet = th + m.obt;
@@ -157,15 +203,20 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   CHECK_RC((gemm_store<false, false>(gemm_ops(s.G, B, s.Xb, d, B, d, B), w.pb, d, 1.0f, st)));
   norm_ln_bwd_kernel<<<B, 256, 0, st>>>(w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d, s.dyn, s.q, s.dz, s.dr,
                                         s.df);
+  // branch 1: theta_{k+1}[W2] = theta_k[W2] - lr df^T h   (needs only df, h)
+  CHECK_RC(lane_edge(st, L.s1));
+  L.s1_busy = true;
+  CHECK_RC((gemm_axpy<false, false>(gemm_ops(s.df, d, s.h, d, d, d, B), upd_src ? upd_src + m.oW2 : nullptr,
+                                    upd_dst + m.oW2, d, lr, L.s1)));
   // dh = df W2 ; dp = dh gelu'(p) + dr
   CHECK_RC((gemm_partial<true, false>(gemm_ops(s.df, d, W2, d, B, d, d), w.pa, &sp, st)));
   epi_dp_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, s.p, s.dr, Bd, s.dh, s.dp);
-  // theta_{k+1}[W2] = theta_k[W2] - lr df^T h ; [W1] = ... - lr dp^T Yb ; small params
-  CHECK_RC((gemm_axpy<false, false>(gemm_ops(s.df, d, s.h, d, d, d, B), upd_src ? upd_src + m.oW2 : nullptr,
-                                    upd_dst + m.oW2, d, lr, st)));
+  // branch 2: theta_{k+1}[W1] = theta_k[W1] - lr dp^T Yb ;  main: small params
+  CHECK_RC(lane_edge(st, L.s2));
+  L.s2_busy = true;
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(s.dp, d, s.Yb, dt, d, dt, B), upd_src ? upd_src + m.oW1 : nullptr,
-                                    upd_dst + m.oW1, dt, lr, st)));
-  colsum_update_kernel<<<ceil_div(d, 128), 128, 0, st>>>(
+                                    upd_dst + m.oW1, dt, lr, L.s2)));
+  colsum_update_kernel<<<ceil_div(d, 32), 256, 0, st>>>(
       s.dp, s.df, s.dz, s.rhat, B, d, lr, upd_src ? upd_src + m.ob1 : nullptr, upd_dst + m.ob1,
       upd_src ? upd_src + m.ob2 : nullptr, upd_dst + m.ob2, upd_src ? upd_src + m.og : nullptr, upd_dst + m.og,
       upd_src ? upd_src + m.obt : nullptr, upd_dst + m.obt);
@@ -178,7 +229,8 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
 // ---------------------------------------------------------------------------------------------------
 int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const float* v, float* a_out,
                  const float* lr, const float* scale, const float* mask, const int64_t* perm, float* dY, float* dlr,
-                 float* dscale, cudaStream_t st) {
+                 float* dscale, Lanes& L) {
+  cudaStream_t st = L.main;
   const int B = m.B, d = m.d, dt = m.dt;
   const size_t Bd = (size_t)B * d, BB = (size_t)B * B;
   const float *W1 = th + m.oW1, *W2 = th + m.oW2, *gam = th + m.og;
@@ -196,28 +248,36 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   nce_t_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, BB, scale, s.S, s.lse_r, s.G, B, w.Sd, w.rho, w.rowA);
   nce_t_cols_kernel<<<B, 128, 0, st>>>(s.S, s.lse_c, w.Sd, B, w.kap);
   nce_t_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, w.Sd, w.rho, w.kap, B, w.Gd, w.rowB);
+  // branch 1: dXn_dot = scale (Gd Yn + G Ynd)  ->  dXn[perm] -= lr * scale * raw
+  CHECK_RC(lane_edge(st, L.s1));
+  L.s1_busy = true;
+  CHECK_RC((gemm_store<true, false>(gemm_ops2(w.Gd, B, s.yn, d, B, s.G, B, w.ynd, d, B, B, d), w.pc, d, 1.0f, L.s1)));
+  scatter_add_rows_kernel<<<B, 256, 0, L.s1>>>(w.pc, 1, Bd, perm, d, lr, scale, w.dXn);
   nce_t_finish_kernel<<<1, 128, 0, st>>>(w.rowA, w.rowB, B, lr, scale, dlr, dscale);
-  // dXn_dot = scale (Gd Yn + G Ynd)  ->  dXn[perm] -= lr * scale * raw
-  CHECK_RC((gemm_store<true, false>(gemm_ops2(w.Gd, B, s.yn, d, B, s.G, B, w.ynd, d, B, B, d), w.pa, d, 1.0f, st)));
-  scatter_add_rows_kernel<<<B, 256, 0, st>>>(w.pa, 1, Bd, perm, d, lr, scale, w.dXn);
   // dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
   CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, B, s.Xb, d, B, d, B), w.pb, d, 1.0f, st)));
   norm_ln_bwd_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd,
                                                                 s.dz, s.rhat, w.rhatd, s.rstd, w.t, s.dr, gam, gamd,
                                                                 mask, d, w.dzd, w.drd, w.dfd);
+  // branch 2: a_k[W2] = a_{k+1}[W2] - lr (dfd^T h + df^T hd)   (fused into the GEMM epilogue)
+  CHECK_RC(lane_edge(st, L.s2));
+  L.s2_busy = true;
+  CHECK_RC((gemm_axpy<false, false>(gemm_ops2(w.dfd, d, s.h, d, B, s.df, d, w.hd, d, B, d, d), v + m.oW2, a_out + m.oW2, d,
+                                    lr, L.s2)));
   // dhd = dfd W2 + df V2 ; dpd
   CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), w.pa, &sp, st)));
   epi_dpd_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, s.p, w.pd, s.dh, w.drd, Bd, w.dpd);
-  // dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.)
-  CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dpd, d, W1, dt, d, s.dp, d, V1, dt, d, B, dt), w.pb, &sp, st)));
-  scatter_add_rows_kernel<<<B, 256, 0, st>>>(w.pb, sp, (size_t)B * dt, perm, dt, lr, nullptr, dY);
-  // a_k = a_{k+1} - lr * H v   (W2, W1 tiles fused into the GEMM epilogues; small params by column sums)
-  CHECK_RC((gemm_axpy<false, false>(gemm_ops2(w.dfd, d, s.h, d, B, s.df, d, w.hd, d, B, d, d), v + m.oW2, a_out + m.oW2, d,
-                                    lr, st)));
+  // branch 1 (after dXn): dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.)
+  CHECK_RC(lane_edge(st, L.s1));
+  int sp_y = 1;
+  CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dpd, d, W1, dt, d, s.dp, d, V1, dt, d, B, dt), w.pe, &sp_y, L.s1)));
+  scatter_add_rows_kernel<<<B, 256, 0, L.s1>>>(w.pe, sp_y, (size_t)B * dt, perm, dt, lr, nullptr, dY);
+  // main: a_k[W1] = a_{k+1}[W1] - lr dpd^T Yb ; small params by column sums
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), v + m.oW1, a_out + m.oW1, dt, lr, st)));
-  colsum_tangent_update_kernel<<<ceil_div(d, 128), 128, 0, st>>>(
+  colsum_tangent_update_kernel<<<ceil_div(d, 32), 256, 0, st>>>(
       w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
       v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
+  CHECK_RC(lanes_join(L));          // a_k, dXn, dY complete before the next reverse step reuses the scratch buffers
   return check_launch("tangent_step");
 }
 
@@ -238,6 +298,74 @@ size_t unrolled_match_workspace_bytes(int N, int B, int K, int dt, int d) {
   return w.bytes;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Body of one call, everything after theta_0 / theta_tgt have been staged into the workspace.  All addresses it
+// touches are workspace addresses or the caller's (Y, U, lr, scale, perms, masks, outputs), so the launch sequence
+// (~300 kernels) is captured ONCE per such address set into a CUDA graph and replayed afterwards.
+// ---------------------------------------------------------------------------------------------------
+static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const float* U, const float* lr,
+                               const float* scale, const int64_t* perms, const float* masks, float* out5, float* ce,
+                               float* dY, float* dU, float* theta_K, cudaStream_t st) {
+  const int N = m.N, B = m.B, K = m.K, dt = m.dt, d = m.d;
+  const size_t Bd = (size_t)B * d;
+  Lanes L;
+  CHECK_RC(lanes_init(L, st));
+  VLDD_CUDA(cudaMemsetAsync(w.ml_scratch, 0, 16, st));
+  VLDD_CUDA(cudaMemsetAsync(out5 + 3, 0, 2 * sizeof(float), st));
+  VLDD_CUDA(cudaMemsetAsync(dY, 0, (size_t)N * dt * sizeof(float), st));
+  VLDD_CUDA(cudaMemsetAsync(w.dXn, 0, (size_t)N * d * sizeof(float), st));
+  row_normalise_kernel<<<N, 256, 0, st>>>(U, d, w.Xn, w.un);
+  // forward unroll
+  for (int k = 0; k < K; ++k) {
+    Saved& s = w.sv[k];
+    const int64_t* perm = perms + (size_t)k * B;
+    gather_rows_kernel<<<B, 256, 0, st>>>(Y, perm, dt, s.Yb);
+    gather_rows_kernel<<<B, 256, 0, st>>>(w.Xn, perm, d, s.Xb);
+    const float* th = w.traj + (size_t)k * m.P;
+    CHECK_RC(forward_step(m, w, s, th, th, w.traj + (size_t)(k + 1) * m.P, lr, scale, masks ? masks + k * Bd : nullptr,
+                          ce ? ce + k : nullptr, L));
+  }
+  CHECK_RC(lanes_join(L));
+  const float* thK = w.traj + (size_t)K * m.P;
+  CHECK_RC(match_loss_fwd(thK, w.tgt, w.traj, m.P, out5, w.ml_scratch, st));
+  CHECK_RC(match_loss_bwd(thK, w.tgt, out5, nullptr, w.adj0, m.P, st));
+  if (theta_K) VLDD_CUDA(cudaMemcpyAsync(theta_K, thK, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // reverse sweep
+  float* a_cur = w.adj0;
+  float* a_nxt = w.adj1;
+  for (int k = K - 1; k >= 0; --k) {
+    const float* th = w.traj + (size_t)k * m.P;
+    CHECK_RC(tangent_step(m, w, w.sv[k], th, a_cur, a_nxt, lr, scale, masks ? masks + k * Bd : nullptr,
+                          perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L));
+    float* t = a_cur; a_cur = a_nxt; a_nxt = t;
+  }
+  row_normalise_bwd_kernel<<<N, 256, 0, st>>>(w.Xn, w.un, w.dXn, nullptr, d, dU);
+  return check_launch("unrolled_match");
+}
+
+namespace {
+struct GraphKey {
+  const void* p[12];
+  int dims[5];
+  bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t last_use; };
+std::mutex g_graph_mu;
+std::vector<GraphEntry> g_graphs;
+uint64_t g_graph_clock = 0;
+cudaStream_t g_capture_stream = nullptr;
+constexpr size_t kMaxGraphs = 32;
+
+bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLDD_GRAPH");
+    v = (e && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+}  // namespace
+
 int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, const float* U, const float* lr,
                    const float* scale, const int64_t* perms, const float* masks, int N, int B, int K, int dt, int d,
                    float* out5, float* ce, float* dY, float* dU, float* theta_K, void* workspace,
@@ -250,39 +378,49 @@ int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, 
     set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
     return VLDD_ERR_WORKSPACE;
   }
-  const size_t Bd = (size_t)B * d;
-  // one-time set-up of this call
-  VLDD_CUDA(cudaMemsetAsync(w.ml_scratch, 0, 16, st));
-  VLDD_CUDA(cudaMemsetAsync(out5 + 3, 0, 2 * sizeof(float), st));
-  VLDD_CUDA(cudaMemsetAsync(dY, 0, (size_t)N * dt * sizeof(float), st));
-  VLDD_CUDA(cudaMemsetAsync(w.dXn, 0, (size_t)N * d * sizeof(float), st));
+  // stage the segment into the workspace (outside the graph: these two source addresses change every iteration)
   VLDD_CUDA(cudaMemcpyAsync(w.traj, theta0, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  row_normalise_kernel<<<N, 256, 0, st>>>(U, d, w.Xn, w.un);
-  // forward unroll
-  for (int k = 0; k < K; ++k) {
-    Saved& s = w.sv[k];
-    const int64_t* perm = perms + (size_t)k * B;
-    gather_rows_kernel<<<B, 256, 0, st>>>(Y, perm, dt, s.Yb);
-    gather_rows_kernel<<<B, 256, 0, st>>>(w.Xn, perm, d, s.Xb);
-    const float* th = w.traj + (size_t)k * m.P;
-    CHECK_RC(forward_step(m, w, s, th, th, w.traj + (size_t)(k + 1) * m.P, lr, scale, masks ? masks + k * Bd : nullptr,
-                          ce ? ce + k : nullptr, st));
+  VLDD_CUDA(cudaMemcpyAsync(w.tgt, theta_tgt, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (!graphs_enabled()) {
+    std::lock_guard<std::mutex> lock(g_graph_mu);   // the side streams / event pool are process-wide
+    return unrolled_match_body(m, w, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K, st);
   }
-  const float* thK = w.traj + (size_t)K * m.P;
-  CHECK_RC(match_loss_fwd(thK, theta_tgt, theta0, m.P, out5, w.ml_scratch, st));
-  CHECK_RC(match_loss_bwd(thK, theta_tgt, out5, nullptr, w.adj0, m.P, st));
-  if (theta_K) VLDD_CUDA(cudaMemcpyAsync(theta_K, thK, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  // reverse sweep
-  float* a_cur = w.adj0;
-  float* a_nxt = w.adj1;
-  for (int k = K - 1; k >= 0; --k) {
-    const float* th = w.traj + (size_t)k * m.P;
-    CHECK_RC(tangent_step(m, w, w.sv[k], th, a_cur, a_nxt, lr, scale, masks ? masks + k * Bd : nullptr,
-                          perms + (size_t)k * B, dY, out5 + 3, out5 + 4, st));
-    float* t = a_cur; a_cur = a_nxt; a_nxt = t;
+
+  GraphKey key;
+  memset(&key, 0, sizeof(key));
+  const void* ptrs[12] = {workspace, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K};
+  memcpy(key.p, ptrs, sizeof(ptrs));
+  const int dims[5] = {N, B, K, dt, d};
+  memcpy(key.dims, dims, sizeof(dims));
+  std::lock_guard<std::mutex> lock(g_graph_mu);
+  cudaGraphExec_t exec = nullptr;
+  for (auto& e : g_graphs)
+    if (e.key == key) { exec = e.exec; e.last_use = ++g_graph_clock; break; }
+  if (exec == nullptr) {
+    if (g_capture_stream == nullptr) VLDD_CUDA(cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking));
+    VLDD_CUDA(cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = unrolled_match_body(m, w, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K, g_capture_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce_end = cudaStreamEndCapture(g_capture_stream, &graph);
+    if (rc != VLDD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce_end != cudaSuccess || graph == nullptr) {
+      set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce_end));
+      return VLDD_ERR_CUDA;
+    }
+    const cudaError_t ce_inst = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce_inst != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce_inst)); return VLDD_ERR_CUDA; }
+    if (g_graphs.size() >= kMaxGraphs) {
+      size_t victim = 0;
+      for (size_t i = 1; i < g_graphs.size(); ++i)
+        if (g_graphs[i].last_use < g_graphs[victim].last_use) victim = i;
+      cudaGraphExecDestroy(g_graphs[victim].exec);
+      g_graphs.erase(g_graphs.begin() + victim);
+    }
+    g_graphs.push_back(GraphEntry{key, exec, ++g_graph_clock});
   }
-  row_normalise_bwd_kernel<<<N, 256, 0, st>>>(w.Xn, w.un, w.dXn, nullptr, d, dU);
-  return check_launch("unrolled_match");
+  VLDD_CUDA(cudaGraphLaunch(exec, st));
+  return VLDD_OK;
 }
 
 // First-order contrastive step on the whole batch (config 2): loss, g_theta, dY, dU, dscale.
@@ -305,7 +443,11 @@ int contrastive_step(const float* theta, const float* Y, const float* U, const f
   row_normalise_kernel<<<B, 256, 0, st>>>(U, d, w.Xn, w.un);
   VLDD_CUDA(cudaMemcpyAsync(s.Yb, Y, (size_t)B * dt * sizeof(float), cudaMemcpyDeviceToDevice, st));
   VLDD_CUDA(cudaMemcpyAsync(s.Xb, w.Xn, Bd * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  CHECK_RC(forward_step(m, w, s, theta, nullptr, g_theta, w.neg_one, scale, mask, loss, st));
+  std::lock_guard<std::mutex> lock(g_graph_mu);
+  Lanes L;
+  CHECK_RC(lanes_init(L, st));
+  CHECK_RC(forward_step(m, w, s, theta, nullptr, g_theta, w.neg_one, scale, mask, loss, L));
+  CHECK_RC(lanes_join(L));
   // dY = dp W1
   if (dY) {
     int sp = 1;

@@ -243,29 +243,39 @@ __global__ void __launch_bounds__(256) epi_dp_kernel(const float* __restrict__ p
 
 // Column sums over the batch and the fused update of the small parameters:
 //   db1 = sum dp ; db2 = sum df ; dgamma = sum dz*rhat ; dbeta = sum dz ;  dst = src - lr * grad   (src nullable = 0)
-__global__ void __launch_bounds__(128) colsum_update_kernel(const float* __restrict__ dp, const float* __restrict__ df,
+// block = 32 columns x 8 row groups (each warp reads 128 contiguous bytes of one row); fixed-order smem reduction.
+__global__ void __launch_bounds__(256) colsum_update_kernel(const float* __restrict__ dp, const float* __restrict__ df,
                                                             const float* __restrict__ dz, const float* __restrict__ rhat,
                                                             int B, int d, const float* __restrict__ lr,
                                                             const float* __restrict__ src_b1, float* __restrict__ dst_b1,
                                                             const float* __restrict__ src_b2, float* __restrict__ dst_b2,
                                                             const float* __restrict__ src_g, float* __restrict__ dst_g,
                                                             const float* __restrict__ src_b, float* __restrict__ dst_b) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= d) return;
+  __shared__ float red[4][8][33];
+  const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + cx;
   float a1 = 0.f, a2 = 0.f, ag = 0.f, ab = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const size_t i = (size_t)b * d + n;
-    a1 += dp[i];
-    a2 += df[i];
-    const float z = dz[i];
-    ag = fmaf(z, rhat[i], ag);
-    ab += z;
+  if (n < d) {
+    for (int b = rg; b < B; b += 8) {
+      const size_t i = (size_t)b * d + n;
+      a1 += dp[i];
+      a2 += df[i];
+      const float z = dz[i];
+      ag = fmaf(z, rhat[i], ag);
+      ab += z;
+    }
   }
-  const float l = *lr;
-  dst_b1[n] = (src_b1 ? src_b1[n] : 0.f) - l * a1;
-  dst_b2[n] = (src_b2 ? src_b2[n] : 0.f) - l * a2;
-  dst_g[n] = (src_g ? src_g[n] : 0.f) - l * ag;
-  dst_b[n] = (src_b ? src_b[n] : 0.f) - l * ab;
+  red[0][rg][cx] = a1; red[1][rg][cx] = a2; red[2][rg][cx] = ag; red[3][rg][cx] = ab;
+  __syncthreads();
+  if (rg < 4 && n < d) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[rg][r][cx];
+    const float l = *lr;
+    const float* src = rg == 0 ? src_b1 : rg == 1 ? src_b2 : rg == 2 ? src_g : src_b;
+    float* dst = rg == 0 ? dst_b1 : rg == 1 ? dst_b2 : rg == 2 ? dst_g : dst_b;
+    dst[n] = (src ? src[n] : 0.f) - l * t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -463,29 +473,38 @@ __global__ void __launch_bounds__(256) epi_dpd_kernel(const float* __restrict__ 
 }
 
 // db1d = sum dpd ; db2d = sum dfd ; dgammad = sum (dzd rhat + dz rhatd) ; dbetad = sum dzd ;  dst = src - lr * (.)
-__global__ void __launch_bounds__(128) colsum_tangent_update_kernel(
+__global__ void __launch_bounds__(256) colsum_tangent_update_kernel(
     const float* __restrict__ dpd, const float* __restrict__ dfd, const float* __restrict__ dzd,
     const float* __restrict__ dz, const float* __restrict__ rhat, const float* __restrict__ rhatd, int B, int d,
     const float* __restrict__ lr, const float* __restrict__ src_b1, float* __restrict__ dst_b1,
     const float* __restrict__ src_b2, float* __restrict__ dst_b2, const float* __restrict__ src_g,
     float* __restrict__ dst_g, const float* __restrict__ src_b, float* __restrict__ dst_b) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= d) return;
+  __shared__ float red[4][8][33];
+  const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + cx;
   float a1 = 0.f, a2 = 0.f, ag = 0.f, ab = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const size_t i = (size_t)b * d + n;
-    a1 += dpd[i];
-    a2 += dfd[i];
-    const float zd = dzd[i];
-    ag = fmaf(zd, rhat[i], ag);
-    ag = fmaf(dz[i], rhatd[i], ag);
-    ab += zd;
+  if (n < d) {
+    for (int b = rg; b < B; b += 8) {
+      const size_t i = (size_t)b * d + n;
+      a1 += dpd[i];
+      a2 += dfd[i];
+      const float zd = dzd[i];
+      ag = fmaf(zd, rhat[i], ag);
+      ag = fmaf(dz[i], rhatd[i], ag);
+      ab += zd;
+    }
   }
-  const float l = *lr;
-  dst_b1[n] = src_b1[n] - l * a1;
-  dst_b2[n] = src_b2[n] - l * a2;
-  dst_g[n] = src_g[n] - l * ag;
-  dst_b[n] = src_b[n] - l * ab;
+  red[0][rg][cx] = a1; red[1][rg][cx] = a2; red[2][rg][cx] = ag; red[3][rg][cx] = ab;
+  __syncthreads();
+  if (rg < 4 && n < d) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[rg][r][cx];
+    const float l = *lr;
+    const float* src = rg == 0 ? src_b1 : rg == 1 ? src_b2 : rg == 2 ? src_g : src_b;
+    float* dst = rg == 0 ? dst_b1 : rg == 1 ? dst_b2 : rg == 2 ? dst_g : dst_b;
+    dst[n] = src[n] - l * t;
+  }
 }
 
 }  // namespace vldd

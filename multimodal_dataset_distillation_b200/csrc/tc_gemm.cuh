@@ -28,9 +28,9 @@ constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB per operand per sta
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 128;
 
-template <int kSplit>
+template <int kSplit, int kStagesT = 0>
 struct Cfg {
-  static constexpr int kStages = kSplit == 3 ? 3 : 6;
+  static constexpr int kStages = kStagesT > 0 ? kStagesT : (kSplit == 3 ? 3 : 6);
   static constexpr int kStageBytes = (kSplit == 3 ? 4 : 2) * TILE_BYTES;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -141,22 +141,23 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(bool a_mn_major, bool b_m
 struct EpiPartial {   // raw fp32 tile -> slab z of [splits][M*N]
   float* part; long long stride;
   __device__ __forceinline__ float* row_ptr(int m, int N, int z) const { return part + (size_t)z * stride + (size_t)m * N; }
-  __device__ __forceinline__ float apply(float acc, const float*, int) const { return acc; }
+  __device__ __forceinline__ float coef() const { return 1.0f; }
+  __device__ __forceinline__ float apply(float acc, float, float) const { return acc; }
   __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
 };
 struct EpiScale {     // C = alpha * acc
   float* C; int ldc; float alpha;
   __device__ __forceinline__ float* row_ptr(int m, int, int) const { return C + (size_t)m * ldc; }
-  __device__ __forceinline__ float apply(float acc, const float*, int) const { return alpha * acc; }
+  __device__ __forceinline__ float coef() const { return alpha; }
+  __device__ __forceinline__ float apply(float acc, float, float c) const { return c * acc; }
   __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
 };
 struct EpiAxpyTC {    // dst = src - (*lr) * acc   (src nullable = 0)
   const float* src; float* dst; int ld; const float* lr;
   __device__ __forceinline__ float* row_ptr(int m, int, int) const { return dst + (size_t)m * ld; }
   __device__ __forceinline__ const float* src_row(int m) const { return src ? src + (size_t)m * ld : nullptr; }
-  __device__ __forceinline__ float apply(float acc, const float* srow, int n) const {
-    return (srow ? srow[n] : 0.f) - (*lr) * acc;
-  }
+  __device__ __forceinline__ float coef() const { return *lr; }
+  __device__ __forceinline__ float apply(float acc, float srcv, float c) const { return srcv - c * acc; }
 };
 
 #ifdef VLDD_TC_DEBUG
@@ -168,10 +169,10 @@ struct Maps {
 };
 
 // ---- the kernel ----------------------------------------------------------------------------------------
-template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi>
+template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, Epi epi) {
-  using C = Cfg<kSplit>;
+  using C = Cfg<kSplit, kStagesT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -289,14 +290,40 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         mbar_arrive(&ready[s]);
       }
     }
-    // epilogue: TMEM lane quadrant is fixed by warp index % 4
+    // epilogue: TMEM lane quadrant is fixed by warp index % 4.  Each thread drains 32 columns of its own row
+    // (tcgen05.ld 32x32b.x32), the warp transposes the 32x32 block through shared memory (the pipeline stages are
+    // free once tmem_full has fired) and then touches global memory as 4 rows x 128 contiguous bytes per instruction.
+    const int quad = warp & 3;
+    constexpr int LDS = 36;                                    // padded row stride (floats): conflict-free float4 access
+    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * LDS;
+    const int rsub = lane >> 3, q4 = (lane & 7) * 4;
+    const int z = blockIdx.z;
+    const float coef = epi.coef();
+    // `src` operand of the axpy epilogue: 8 independent 128-bit loads per thread per 32-column chunk, issued one chunk
+    // ahead (the first chunk before the accumulator is even ready) so their latency hides behind the MMAs / TMEM drain
+    float4 sv[8];
+    auto load_src = [&](int c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + quad * 32 + i * 4 + rsub, nb = n0 + c + q4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* src = (m < M && nb < N) ? epi.src_row(m) : nullptr;
+        if (src != nullptr) {
+          if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(src + nb) & 15) == 0)) {
+            t = *reinterpret_cast<const float4*>(src + nb);
+          } else {
+            t.x = src[nb];
+            if (nb + 1 < N) t.y = src[nb + 1];
+            if (nb + 2 < N) t.z = src[nb + 2];
+            if (nb + 3 < N) t.w = src[nb + 3];
+          }
+        }
+        sv[i] = t;
+      }
+    };
+    load_src(0);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int m = m0 + row;
-    float* out_row = (m < M) ? epi.row_ptr(m, N, blockIdx.z) : nullptr;
-    const float* src_row = (m < M) ? epi.src_row(m) : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       float v[32];
@@ -307,22 +334,31 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      if (out_row != nullptr) {
-        const int nb = n0 + c;
-        if (nb + 31 < N && ((reinterpret_cast<uintptr_t>(out_row + nb) & 15) == 0)) {
+      __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = epi.apply(v[j + 0], src_row, nb + j + 0);
-            o.y = epi.apply(v[j + 1], src_row, nb + j + 1);
-            o.z = epi.apply(v[j + 2], src_row, nb + j + 2);
-            o.w = epi.apply(v[j + 3], src_row, nb + j + 3);
-            *reinterpret_cast<float4*>(out_row + nb + j) = o;
-          }
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stage + lane * LDS + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+      float4 cur[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = sv[i];
+      if (c + 32 < BN) load_src(c + 32);
+      const int nb = n0 + c + q4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + quad * 32 + i * 4 + rsub;
+        if (m >= M || nb >= N) continue;
+        const float4 a = *reinterpret_cast<const float4*>(stage + (i * 4 + rsub) * LDS + q4);
+        float* out = epi.row_ptr(m, N, z) + nb;
+        const float4 o = make_float4(epi.apply(a.x, cur[i].x, coef), epi.apply(a.y, cur[i].y, coef),
+                                     epi.apply(a.z, cur[i].z, coef), epi.apply(a.w, cur[i].w, coef));
+        if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+          *reinterpret_cast<float4*>(out) = o;
         } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < N) out_row[nb + j] = epi.apply(v[j], src_row, nb + j);
+          out[0] = o.x;
+          if (nb + 1 < N) out[1] = o.y;
+          if (nb + 2 < N) out[2] = o.z;
+          if (nb + 3 < N) out[3] = o.w;
         }
       }
     }

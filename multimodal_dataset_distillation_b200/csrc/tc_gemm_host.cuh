@@ -94,10 +94,10 @@ inline bool gemm_ok(const GemmOperands& g) {
   return true;
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi>
+template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0>
 inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st) {
-  using C = Cfg<kSplit>;
-  auto kern = tc_gemm_kernel<A_KMAJOR, B_KMAJOR, kSplit, Epi>;
+  using C = Cfg<kSplit, kStagesT>;
+  auto kern = tc_gemm_kernel<A_KMAJOR, B_KMAJOR, kSplit, Epi, kStagesT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);

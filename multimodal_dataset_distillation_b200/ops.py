@@ -242,7 +242,11 @@ def contrastive_step(theta: torch.Tensor, Y: torch.Tensor, U: torch.Tensor, scal
 
 
 class UnrollWorkspace:
-    """Caller-owned device workspace of the unroll engine, sized once per (N, B, K, dt, d)."""
+    """Caller-owned device state of the unroll engine, sized once per (N, B, K, dt, d).
+
+    Besides the engine's scratch it owns the persistent argument / result buffers (perms, masks, out5, ce, dY, dU):
+    the engine replays a CUDA graph keyed on the addresses it is given, so stable addresses mean one capture.
+    """
 
     def __init__(self, N: int, B: int, K: int, dt: int, d: int, device):
         self.key = (N, B, K, dt, d)
@@ -250,6 +254,15 @@ class UnrollWorkspace:
         if nbytes == 0:
             check(-1, "unrolled_match_workspace_bytes")
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.perms = torch.empty(max(K, 1), B, dtype=torch.int64, device=device)
+        self.masks = None
+        self.out5 = torch.empty(5, dtype=torch.float32, device=device)
+        self.ce = torch.empty(max(K, 1), dtype=torch.float32, device=device)
+        self.dY = torch.empty(N, dt, dtype=torch.float32, device=device)
+        self.dU = torch.empty(N, d, dtype=torch.float32, device=device)
+        self.theta_K = None
+        self.lr = torch.empty(1, dtype=torch.float32, device=device)
+        self.scale = torch.empty(1, dtype=torch.float32, device=device)
 
 
 def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, workspace: UnrollWorkspace | None = None,
@@ -266,21 +279,30 @@ def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, worksp
     if theta0.numel() != head_numel(dt, d) or theta_tgt.numel() != theta0.numel():
         raise ValueError(f"theta has {theta0.numel()} elements, expected {head_numel(dt, d)}")
     dev = Y.device
-    lr_t, sc_t = _scalar(lr, dev, "lr"), _scalar(scale, dev, "scale")
+    if workspace is None or workspace.key != (N, B, K, dt, d):
+        workspace = UnrollWorkspace(N, B, K, dt, d, dev)
+    ws = workspace
+    ws.lr.copy_(_scalar(lr, dev, "lr"))
+    ws.scale.copy_(_scalar(scale, dev, "scale"))
+    if K > 0:
+        ws.perms.copy_(perms)
+    m_ptr = None
     if masks is not None:
         masks = _req(masks, "masks")
         if tuple(masks.shape) != (K, B, d):
             raise ValueError(f"masks must be [{K},{B},{d}]")
-    if workspace is None or workspace.key != (N, B, K, dt, d):
-        workspace = UnrollWorkspace(N, B, K, dt, d, dev)
-    out5 = torch.empty(5, device=dev)
-    ce = torch.empty(max(K, 1), device=dev)
-    dY, dU = torch.empty_like(Y), torch.empty_like(U)
-    thK = torch.empty_like(theta0) if want_theta_K else None
-    check(lib().vldd_unrolled_match(_ptr(theta0), _ptr(theta_tgt), _ptr(Y), _ptr(U), _ptr(lr_t), _ptr(sc_t), _ptr(perms),
-                                    _ptr(masks), N, B, K, dt, d, _ptr(out5), _ptr(ce), _ptr(dY), _ptr(dU), _ptr(thK),
-                                    _ptr(workspace.buf), workspace.buf.numel(), _stream()), "unrolled_match")
-    res = dict(out5=out5, ce=ce[:K], dY=dY, dU=dU, workspace=workspace)
+        if ws.masks is None:
+            ws.masks = torch.empty(K, B, d, dtype=torch.float32, device=dev)
+        ws.masks.copy_(masks)
+        m_ptr = ws.masks
+    if want_theta_K and ws.theta_K is None:
+        ws.theta_K = torch.empty_like(theta0)
+    thK = ws.theta_K if want_theta_K else None
+    check(lib().vldd_unrolled_match(_ptr(theta0), _ptr(theta_tgt), _ptr(Y), _ptr(U), _ptr(ws.lr), _ptr(ws.scale),
+                                    _ptr(ws.perms), _ptr(m_ptr), N, B, K, dt, d, _ptr(ws.out5), _ptr(ws.ce), _ptr(ws.dY),
+                                    _ptr(ws.dU), _ptr(thK), _ptr(ws.buf), ws.buf.numel(), _stream()), "unrolled_match")
+    # results are copied out of the persistent buffers (1.2 MB at Flickr shape) so that they survive the next call
+    res = dict(out5=ws.out5.clone(), ce=ws.ce[:K].clone(), dY=ws.dY.clone(), dU=ws.dU.clone(), workspace=ws)
     if want_theta_K:
-        res["theta_K"] = thK
+        res["theta_K"] = thK.clone()
     return res
