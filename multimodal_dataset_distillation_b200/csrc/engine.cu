@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm_dispatch.cuh"
 #include "head_kernels.cuh"
+#include "row_kernels_v4.cuh"
 #include "kernels.h"
 #include "engine.h"
 
@@ -24,13 +25,13 @@ namespace vldd {
 namespace {
 
 struct Dims {
-  int N, B, K, dt, d;
+  int N, B, K, dt, d, Bp;   // Bp: leading dimension of the B x B matrices (multiple of 32 for the MN-major tensor maps)
   int64_t P, oW1, ob1, oW2, ob2, og, obt;
 };
 
 Dims make_dims(int N, int B, int K, int dt, int d) {
   Dims m;
-  m.N = N; m.B = B; m.K = K; m.dt = dt; m.d = d;
+  m.N = N; m.B = B; m.K = K; m.dt = dt; m.d = d; m.Bp = (B + 31) / 32 * 32;
   m.oW1 = 0;
   m.ob1 = (int64_t)d * dt;
   m.oW2 = m.ob1 + d;
@@ -81,7 +82,7 @@ size_t partial_floats(const Dims& m) {
 
 void carve(Work& w, const Dims& m, void* base) {
   Bump b{reinterpret_cast<char*>(base), 0, 0};
-  const size_t Bd = (size_t)m.B * m.d, BB = (size_t)m.B * m.B;
+  const size_t Bd = (size_t)m.B * m.d, BB = (size_t)m.B * m.Bp, Bpd = (size_t)m.Bp * m.d;
   w.traj = b.f((size_t)(m.K + 1) * m.P);
   w.tgt = b.f(m.P);
   w.adj0 = b.f(m.P);
@@ -98,8 +99,8 @@ void carve(Work& w, const Dims& m, void* base) {
     s.S = b.f(BB); s.G = b.f(BB);
   }
   const size_t pf = partial_floats(m);
-  w.pa = b.f(pf);
-  w.pb = b.f(pf);
+  w.pa = b.f(pf > Bpd ? pf : Bpd);
+  w.pb = b.f(pf > Bpd ? pf : Bpd);
   w.pc = b.f(Bd);
   w.pe = b.f((size_t)max_splits(m.B, m.dt, 2 * m.d) * m.B * m.dt);
   w.pd = b.f(Bd); w.hd = b.f(Bd); w.rhatd = b.f(Bd); w.ynd = b.f(Bd); w.dzd = b.f(Bd); w.drd = b.f(Bd);
@@ -130,6 +131,19 @@ __global__ void __launch_bounds__(256) dot_over_scale_kernel(const float* __rest
   if (threadIdx.x == 0) *out = acc / (*scale);
 }
 
+// the padding columns [B, Bp) of S, G, Sd, Gd must read as zeros (they feed GEMMs as extra, all-zero rows)
+int zero_square_matrices(const Dims& m, Work& w, cudaStream_t st) {
+  const size_t bytes = (size_t)m.B * m.Bp * sizeof(float);
+  if (m.Bp == m.B) return VLDD_OK;
+  for (int k = 0; k < m.K; ++k) {
+    VLDD_CUDA(cudaMemsetAsync(w.sv[k].G, 0, bytes, st));
+    VLDD_CUDA(cudaMemsetAsync(w.sv[k].S, 0, bytes, st));
+  }
+  VLDD_CUDA(cudaMemsetAsync(w.Gd, 0, bytes, st));
+  VLDD_CUDA(cudaMemsetAsync(w.Sd, 0, bytes, st));
+  return VLDD_OK;
+}
+
 inline int ew_grid(size_t n) {
   size_t g = (n + 255) / 256;
   const size_t cap = (size_t)kNumSMs * 8;
@@ -137,6 +151,43 @@ inline int ew_grid(size_t n) {
 }
 
 #define CHECK_RC(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+// VLDD_PROFILE=1: serialise everything on one stream and time every launch with events (developer aid; prints a
+// per-call-site table to stderr at the end of vldd_unrolled_match).
+struct ProfMark { const char* label; cudaEvent_t ev; };
+std::vector<ProfMark> g_prof;
+bool prof_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VLDD_PROFILE"); v = (e && strcmp(e, "1") == 0) ? 1 : 0; }
+  return v == 1;
+}
+void prof_mark(const char* label, cudaStream_t st) {
+  if (!prof_enabled()) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  g_prof.push_back(ProfMark{label, e});
+}
+void prof_report() {
+  if (!prof_enabled() || g_prof.size() < 2) return;
+  cudaDeviceSynchronize();
+  struct Acc { const char* label; double ms; int n; };
+  std::vector<Acc> acc;
+  double total = 0;
+  for (size_t i = 1; i < g_prof.size(); ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, g_prof[i - 1].ev, g_prof[i].ev);
+    total += ms;
+    bool found = false;
+    for (auto& a : acc) if (strcmp(a.label, g_prof[i].label) == 0) { a.ms += ms; a.n++; found = true; break; }
+    if (!found) acc.push_back(Acc{g_prof[i].label, ms, 1});
+  }
+  fprintf(stderr, "[vldd profile] one call, serialised on one stream: %.1f us\n", total * 1e3);
+  for (auto& a : acc) fprintf(stderr, "[vldd profile] %9.1f us %5.1f%% x%3d  %s\n", a.ms * 1e3, 100 * a.ms / total, a.n, a.label);
+  for (auto& m : g_prof) cudaEventDestroy(m.ev);
+  g_prof.clear();
+}
+#define MARK(label) prof_mark(label, st)
 
 // Independent branches of a step (weight-gradient GEMMs, the dXn / dY side products) run on two side streams that
 // fork from / join into the main stream with events; under graph capture this becomes parallel branches of the graph.
@@ -156,10 +207,12 @@ int lanes_init(Lanes& L, cudaStream_t main) {
     VLDD_CUDA(cudaStreamCreateWithFlags(&g_side2, cudaStreamNonBlocking));
   }
   L.main = main; L.s1 = g_side1; L.s2 = g_side2; L.s1_busy = false; L.s2_busy = false;
+  if (prof_enabled()) { L.s1 = main; L.s2 = main; }
   g_event_next = 0;
   return VLDD_OK;
 }
 int lane_edge(cudaStream_t from, cudaStream_t to) {   // everything enqueued on `from` so far happens-before later work on `to`
+  if (from == to) return VLDD_OK;
   if (g_event_next == g_events.size()) {
     cudaEvent_t e;
     VLDD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -183,43 +236,67 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
                  const float* lr, const float* scale, const float* mask, float* ce_out, Lanes& L) {
   cudaStream_t st = L.main;
   CHECK_RC(lanes_join(L));          // theta_k must be complete (previous step's weight-gradient branches)
-  const int B = m.B, d = m.d, dt = m.dt;
+  const int B = m.B, d = m.d, dt = m.dt, Bp = m.Bp;
   const size_t Bd = (size_t)B * d;
   const float *W1 = th + m.oW1, *b1 = th + m.ob1, *W2 = th + m.oW2, *b2 = th + m.ob2, *gam = th + m.og, *bet = th + m.obt;
   // p = Yb W1^T + b1 ; h = gelu(p)
   int sp = 1;
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, W1, dt, B, d, dt), w.pa, &sp, st)));
+  prof_mark("gemm_partial<true,true> A=s.Yb", st);
   epi_p_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, b1, B, d, s.p, s.h);
+  prof_mark("epi_p_kernel", st);
   // f = h W2^T + b2 ; r = mask f + p ; LN ; normalise
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.h, d, W2, d, B, d, d), w.pa, &sp, st)));
-  ln_fwd_kernel<<<B, 256, d * sizeof(float), st>>>(w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr, s.yn,
-                                                   s.rstd, s.nz);
+  prof_mark("gemm_partial<true,true> A=s.h", st);
+  if (row_v4_ok(d))
+    VLDD_ROW_V4_DISPATCH(d, ln_fwd_v4_kernel, <<<B, 256, 0, st>>>(w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr,
+                                                                   s.yn, s.rstd, s.nz));
+  else
+    ln_fwd_kernel<<<B, 256, d * sizeof(float), st>>>(w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr, s.yn,
+                                                     s.rstd, s.nz);
+  prof_mark("ln_fwd_kernel", st);
   // S = scale * Xb Yn^T ; lse ; G ; loss
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, s.yn, d, B, B, d), w.pa, &sp, st)));
-  nce_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, (size_t)B * B, scale, B, s.S, s.lse_r);
-  nce_cols_kernel<<<B, 128, 0, st>>>(s.S, B, s.lse_c);
-  nce_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, B, s.G, ce_out);
+  prof_mark("gemm_partial<true,true> A=s.Xb", st);
+  nce_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, (size_t)B * B, scale, B, Bp, s.S, s.lse_r);
+  prof_mark("nce_rows_kernel", st);
+  nce_cols_kernel<<<B, 128, 0, st>>>(s.S, B, Bp, s.lse_c);
+  prof_mark("nce_cols_kernel", st);
+  nce_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, B, Bp, s.G, ce_out);
+  prof_mark("nce_grad_kernel", st);
   // dyn_raw[j,:] = sum_i G[i,j] Xb[i,:]
-  CHECK_RC((gemm_store<false, false>(gemm_ops(s.G, B, s.Xb, d, B, d, B), w.pb, d, 1.0f, st)));
-  norm_ln_bwd_kernel<<<B, 256, 0, st>>>(w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d, s.dyn, s.q, s.dz, s.dr,
-                                        s.df);
+  // (G is stored with leading dimension Bp and zero padding columns: rows B..Bp-1 of the product are zeros)
+  CHECK_RC((gemm_store<false, false>(gemm_ops(s.G, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st)));
+  prof_mark("gemm_store<false,false> A=s.G", st);
+  if (row_v4_ok(d))
+    VLDD_ROW_V4_DISPATCH(d, norm_ln_bwd_v4_kernel, <<<B, 256, 0, st>>>(w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d,
+                                                                        s.dyn, s.q, s.dz, s.dr, s.df));
+  else
+    norm_ln_bwd_kernel<<<B, 256, 0, st>>>(w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d, s.dyn, s.q, s.dz, s.dr,
+                                          s.df);
+  prof_mark("norm_ln_bwd_kernel", st);
   // branch 1: theta_{k+1}[W2] = theta_k[W2] - lr df^T h   (needs only df, h)
   CHECK_RC(lane_edge(st, L.s1));
   L.s1_busy = true;
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(s.df, d, s.h, d, d, d, B), upd_src ? upd_src + m.oW2 : nullptr,
                                     upd_dst + m.oW2, d, lr, L.s1)));
+  prof_mark("gemm_axpy<false,false> A=s.df", L.s1);
   // dh = df W2 ; dp = dh gelu'(p) + dr
   CHECK_RC((gemm_partial<true, false>(gemm_ops(s.df, d, W2, d, B, d, d), w.pa, &sp, st)));
+  prof_mark("gemm_partial<true,false> A=s.df", st);
   epi_dp_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, s.p, s.dr, Bd, s.dh, s.dp);
+  prof_mark("epi_dp_kernel", st);
   // branch 2: theta_{k+1}[W1] = theta_k[W1] - lr dp^T Yb ;  main: small params
   CHECK_RC(lane_edge(st, L.s2));
   L.s2_busy = true;
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(s.dp, d, s.Yb, dt, d, dt, B), upd_src ? upd_src + m.oW1 : nullptr,
                                     upd_dst + m.oW1, dt, lr, L.s2)));
-  colsum_update_kernel<<<ceil_div(d, 32), 256, 0, st>>>(
+  prof_mark("gemm_axpy<false,false> A=s.dp", L.s2);
+  colsum_update_kernel<<<ceil_div(d, 16), 256, 0, st>>>(
       s.dp, s.df, s.dz, s.rhat, B, d, lr, upd_src ? upd_src + m.ob1 : nullptr, upd_dst + m.ob1,
       upd_src ? upd_src + m.ob2 : nullptr, upd_dst + m.ob2, upd_src ? upd_src + m.og : nullptr, upd_dst + m.og,
       upd_src ? upd_src + m.obt : nullptr, upd_dst + m.obt);
+  prof_mark("colsum_update_kernel", st);
   return check_launch("forward_step");
 }
 
@@ -231,52 +308,81 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
                  const float* lr, const float* scale, const float* mask, const int64_t* perm, float* dY, float* dlr,
                  float* dscale, Lanes& L) {
   cudaStream_t st = L.main;
-  const int B = m.B, d = m.d, dt = m.dt;
-  const size_t Bd = (size_t)B * d, BB = (size_t)B * B;
+  const int B = m.B, d = m.d, dt = m.dt, Bp = m.Bp;
+  const size_t Bd = (size_t)B * d;
   const float *W1 = th + m.oW1, *W2 = th + m.oW2, *gam = th + m.og;
   const float *V1 = v + m.oW1, *c1 = v + m.ob1, *V2 = v + m.oW2, *c2 = v + m.ob2, *gamd = v + m.og, *betd = v + m.obt;
   // pd = Yb V1^T + c1 ; hd = gelu'(p) pd
   int sp = 1;
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), w.pa, &sp, st)));
+  prof_mark("gemm_partial<true,true> A=s.Yb", st);
   epi_pd_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, c1, s.p, B, d, w.pd, w.hd);
+  prof_mark("epi_pd_kernel", st);
   // fd = hd W2^T + h V2^T + c2 ; LN / normalise tangents
   CHECK_RC((gemm_partial<true, true>(gemm_ops2(w.hd, d, W2, d, d, s.h, d, V2, d, d, B, d), w.pa, &sp, st)));
-  ln_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz, gam,
-                                                       gamd, betd, d, w.rhatd, w.ynd, w.t, w.nzd);
+  prof_mark("gemm_partial<true,true> A=w.hd", st);
+  if (row_v4_ok(d))
+    VLDD_ROW_V4_DISPATCH(d, ln_tangent_v4_kernel, <<<B, 256, 0, st>>>(w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz,
+                                                                       gam, gamd, betd, d, w.rhatd, w.ynd, w.t, w.nzd));
+  else
+    ln_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz, gam,
+                                                         gamd, betd, d, w.rhatd, w.ynd, w.t, w.nzd);
+  prof_mark("ln_tangent_kernel", st);
   // Sd = scale Xb Ynd^T ; rho, kappa, Gd ; L_dot ; dlr, dscale
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, w.ynd, d, B, B, d), w.pa, &sp, st)));
-  nce_t_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, BB, scale, s.S, s.lse_r, s.G, B, w.Sd, w.rho, w.rowA);
-  nce_t_cols_kernel<<<B, 128, 0, st>>>(s.S, s.lse_c, w.Sd, B, w.kap);
-  nce_t_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, w.Sd, w.rho, w.kap, B, w.Gd, w.rowB);
+  prof_mark("gemm_partial<true,true> A=s.Xb", st);
+  nce_t_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, (size_t)B * B, scale, s.S, s.lse_r, s.G, B, Bp, w.Sd, w.rho, w.rowA);
+  prof_mark("nce_t_rows_kernel", st);
+  nce_t_cols_kernel<<<B, 128, 0, st>>>(s.S, s.lse_c, w.Sd, B, Bp, w.kap);
+  prof_mark("nce_t_cols_kernel", st);
+  nce_t_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, w.Sd, w.rho, w.kap, B, Bp, w.Gd, w.rowB);
+  prof_mark("nce_t_grad_kernel", st);
   // branch 1: dXn_dot = scale (Gd Yn + G Ynd)  ->  dXn[perm] -= lr * scale * raw
   CHECK_RC(lane_edge(st, L.s1));
   L.s1_busy = true;
-  CHECK_RC((gemm_store<true, false>(gemm_ops2(w.Gd, B, s.yn, d, B, s.G, B, w.ynd, d, B, B, d), w.pc, d, 1.0f, L.s1)));
+  CHECK_RC((gemm_store<true, false>(gemm_ops2(w.Gd, Bp, s.yn, d, B, s.G, Bp, w.ynd, d, B, B, d), w.pc, d, 1.0f, L.s1)));
+  prof_mark("gemm_store<true,false> A=w.Gd", L.s1);
   scatter_add_rows_kernel<<<B, 256, 0, L.s1>>>(w.pc, 1, Bd, perm, d, lr, scale, w.dXn);
+  prof_mark("scatter_add_rows_kernel", L.s1);
   nce_t_finish_kernel<<<1, 128, 0, st>>>(w.rowA, w.rowB, B, lr, scale, dlr, dscale);
+  prof_mark("nce_t_finish_kernel", st);
   // dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
-  CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, B, s.Xb, d, B, d, B), w.pb, d, 1.0f, st)));
-  norm_ln_bwd_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd,
-                                                                s.dz, s.rhat, w.rhatd, s.rstd, w.t, s.dr, gam, gamd,
-                                                                mask, d, w.dzd, w.drd, w.dfd);
+  CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st)));
+  prof_mark("gemm_store<false,false> A=w.Gd", st);
+  if (row_v4_ok(d))
+    VLDD_ROW_V4_DISPATCH(d, norm_ln_bwd_tangent_v4_kernel,
+                         <<<B, 256, 0, st>>>(w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd, s.dz, s.rhat, w.rhatd, s.rstd,
+                                             w.t, s.dr, gam, gamd, mask, d, w.dzd, w.drd, w.dfd));
+  else
+    norm_ln_bwd_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd,
+                                                                  s.dz, s.rhat, w.rhatd, s.rstd, w.t, s.dr, gam, gamd,
+                                                                  mask, d, w.dzd, w.drd, w.dfd);
+  prof_mark("norm_ln_bwd_tangent_kernel", st);
   // branch 2: a_k[W2] = a_{k+1}[W2] - lr (dfd^T h + df^T hd)   (fused into the GEMM epilogue)
   CHECK_RC(lane_edge(st, L.s2));
   L.s2_busy = true;
   CHECK_RC((gemm_axpy<false, false>(gemm_ops2(w.dfd, d, s.h, d, B, s.df, d, w.hd, d, B, d, d), v + m.oW2, a_out + m.oW2, d,
                                     lr, L.s2)));
+  prof_mark("gemm_axpy<false,false> A=w.dfd", L.s2);
   // dhd = dfd W2 + df V2 ; dpd
   CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), w.pa, &sp, st)));
+  prof_mark("gemm_partial<true,false> A=w.dfd", st);
   epi_dpd_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, s.p, w.pd, s.dh, w.drd, Bd, w.dpd);
+  prof_mark("epi_dpd_kernel", st);
   // branch 1 (after dXn): dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.)
   CHECK_RC(lane_edge(st, L.s1));
   int sp_y = 1;
   CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dpd, d, W1, dt, d, s.dp, d, V1, dt, d, B, dt), w.pe, &sp_y, L.s1)));
+  prof_mark("gemm_partial<true,false> A=w.dpd", L.s1);
   scatter_add_rows_kernel<<<B, 256, 0, L.s1>>>(w.pe, sp_y, (size_t)B * dt, perm, dt, lr, nullptr, dY);
+  prof_mark("scatter_add_rows_kernel", L.s1);
   // main: a_k[W1] = a_{k+1}[W1] - lr dpd^T Yb ; small params by column sums
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), v + m.oW1, a_out + m.oW1, dt, lr, st)));
-  colsum_tangent_update_kernel<<<ceil_div(d, 32), 256, 0, st>>>(
+  prof_mark("gemm_axpy<false,false> A=w.dpd", st);
+  colsum_tangent_update_kernel<<<ceil_div(d, 16), 256, 0, st>>>(
       w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
       v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
+  prof_mark("colsum_tangent_update_kernel", st);
   CHECK_RC(lanes_join(L));          // a_k, dXn, dY complete before the next reverse step reuses the scratch buffers
   return check_launch("tangent_step");
 }
@@ -314,13 +420,17 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   VLDD_CUDA(cudaMemsetAsync(out5 + 3, 0, 2 * sizeof(float), st));
   VLDD_CUDA(cudaMemsetAsync(dY, 0, (size_t)N * dt * sizeof(float), st));
   VLDD_CUDA(cudaMemsetAsync(w.dXn, 0, (size_t)N * d * sizeof(float), st));
+  CHECK_RC(zero_square_matrices(m, w, st));
+  MARK("start");
   row_normalise_kernel<<<N, 256, 0, st>>>(U, d, w.Xn, w.un);
+  MARK("row_normalise");
   // forward unroll
   for (int k = 0; k < K; ++k) {
     Saved& s = w.sv[k];
     const int64_t* perm = perms + (size_t)k * B;
     gather_rows_kernel<<<B, 256, 0, st>>>(Y, perm, dt, s.Yb);
     gather_rows_kernel<<<B, 256, 0, st>>>(w.Xn, perm, d, s.Xb);
+    MARK("gather_rows x2");
     const float* th = w.traj + (size_t)k * m.P;
     CHECK_RC(forward_step(m, w, s, th, th, w.traj + (size_t)(k + 1) * m.P, lr, scale, masks ? masks + k * Bd : nullptr,
                           ce ? ce + k : nullptr, L));
@@ -329,6 +439,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   const float* thK = w.traj + (size_t)K * m.P;
   CHECK_RC(match_loss_fwd(thK, w.tgt, w.traj, m.P, out5, w.ml_scratch, st));
   CHECK_RC(match_loss_bwd(thK, w.tgt, out5, nullptr, w.adj0, m.P, st));
+  MARK("match_loss fwd+bwd");
   if (theta_K) VLDD_CUDA(cudaMemcpyAsync(theta_K, thK, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // reverse sweep
   float* a_cur = w.adj0;
@@ -340,6 +451,8 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
     float* t = a_cur; a_cur = a_nxt; a_nxt = t;
   }
   row_normalise_bwd_kernel<<<N, 256, 0, st>>>(w.Xn, w.un, w.dXn, nullptr, d, dU);
+  MARK("row_normalise_bwd");
+  prof_report();
   return check_launch("unrolled_match");
 }
 
@@ -381,7 +494,7 @@ int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, 
   // stage the segment into the workspace (outside the graph: these two source addresses change every iteration)
   VLDD_CUDA(cudaMemcpyAsync(w.traj, theta0, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
   VLDD_CUDA(cudaMemcpyAsync(w.tgt, theta_tgt, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (!graphs_enabled()) {
+  if (!graphs_enabled() || prof_enabled()) {
     std::lock_guard<std::mutex> lock(g_graph_mu);   // the side streams / event pool are process-wide
     return unrolled_match_body(m, w, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K, st);
   }
@@ -440,6 +553,7 @@ int contrastive_step(const float* theta, const float* Y, const float* U, const f
   Saved& s = w.sv[0];
   const size_t Bd = (size_t)B * d;
   fill_kernel<<<1, 32, 0, st>>>(w.neg_one, -1.0f, 4);
+  CHECK_RC(zero_square_matrices(m, w, st));
   row_normalise_kernel<<<B, 256, 0, st>>>(U, d, w.Xn, w.un);
   VLDD_CUDA(cudaMemcpyAsync(s.Yb, Y, (size_t)B * dt * sizeof(float), cudaMemcpyDeviceToDevice, st));
   VLDD_CUDA(cudaMemcpyAsync(s.Xb, w.Xn, Bd * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -456,11 +570,11 @@ int contrastive_step(const float* theta, const float* Y, const float* U, const f
   }
   // dU = normalise_bwd(scale * G Yn)
   if (dU) {
-    CHECK_RC((gemm_store<true, false>(gemm_ops(s.G, B, s.yn, d, B, d, B), w.pb, d, 1.0f, st)));
+    CHECK_RC((gemm_store<true, false>(gemm_ops(s.G, m.Bp, s.yn, d, B, d, B), w.pb, d, 1.0f, st)));
     row_normalise_bwd_kernel<<<B, 256, 0, st>>>(w.Xn, w.un, w.pb, scale, d, dU);
   }
   // dscale = sum(G * S) / scale
-  if (dscale) dot_over_scale_kernel<<<1, 256, 0, st>>>(s.G, s.S, (size_t)B * B, scale, dscale);
+  if (dscale) dot_over_scale_kernel<<<1, 256, 0, st>>>(s.G, s.S, (size_t)B * m.Bp, scale, dscale);
   return check_launch("contrastive_step");
 }
 
@@ -492,8 +606,12 @@ int proj_head_forward(const float* theta, const float* Y, const float* mask, int
   CHECK_RC((gemm_partial<true, true>(gemm_ops(Y, dt, theta + m.oW1, dt, rows, d, dt), part, &sp, st)));
   epi_p_kernel<<<ew_grid(Rd), 256, 0, st>>>(part, sp, Rd, theta + m.ob1, rows, d, p, h);
   CHECK_RC((gemm_partial<true, true>(gemm_ops(h, d, theta + m.oW2, d, rows, d, d), part, &sp, st)));
-  ln_fwd_kernel<<<rows, 256, d * sizeof(float), st>>>(part, sp, Rd, theta + m.ob2, mask, p, theta + m.og,
-                                                      theta + m.obt, d, nullptr, z, zn, nullptr, nullptr);
+  if (row_v4_ok(d))
+    VLDD_ROW_V4_DISPATCH(d, ln_fwd_v4_kernel, <<<rows, 256, 0, st>>>(part, sp, Rd, theta + m.ob2, mask, p, theta + m.og,
+                                                                      theta + m.obt, d, nullptr, z, zn, nullptr, nullptr));
+  else
+    ln_fwd_kernel<<<rows, 256, d * sizeof(float), st>>>(part, sp, Rd, theta + m.ob2, mask, p, theta + m.og,
+                                                        theta + m.obt, d, nullptr, z, zn, nullptr, nullptr);
   return check_launch("proj_head_forward");
 }
 

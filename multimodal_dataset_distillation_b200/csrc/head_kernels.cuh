@@ -117,7 +117,12 @@ __global__ void __launch_bounds__(256) row_normalise_bwd_kernel(const float* __r
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
                                                           int cols, float* __restrict__ dst) {
   const size_t s = (size_t)idx[blockIdx.x] * cols, t = (size_t)blockIdx.x * cols;
-  for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[t + j] = src[s + j];
+  if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    for (int j = threadIdx.x; j < (cols >> 2); j += blockDim.x)
+      reinterpret_cast<float4*>(dst + t)[j] = reinterpret_cast<const float4*>(src + s)[j];
+  } else {
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[t + j] = src[s + j];
+  }
 }
 
 // dst[idx[b],:] += coef * sum_slabs(part)[b,:]   with coef = -(*lr) * (scale ? *scale : 1)
@@ -137,51 +142,52 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
 // ------------------------------------------------------------------------------------------------
 // row i: S[i,:] = scale * sum_slabs ; lse_r[i]
 __global__ void __launch_bounds__(128) nce_rows_kernel(const float* __restrict__ part, int splits, size_t stride,
-                                                       const float* __restrict__ scale, int B, float* __restrict__ S,
-                                                       float* __restrict__ lse_r) {
+                                                       const float* __restrict__ scale, int B, int ld,
+                                                       float* __restrict__ S, float* __restrict__ lse_r) {
   __shared__ float scratch[34];
   const int i = blockIdx.x;
   const float sc = *scale;
   float mx = -INFINITY;
   for (int j = threadIdx.x; j < B; j += blockDim.x) {
     const float v = sc * sum_slabs(part, splits, stride, (size_t)i * B + j);
-    S[(size_t)i * B + j] = v;
+    S[(size_t)i * ld + j] = v;
     mx = fmaxf(mx, v);
   }
   mx = block_max(mx, scratch);
   float se = 0.f;
-  for (int j = threadIdx.x; j < B; j += blockDim.x) se += expf(S[(size_t)i * B + j] - mx);
+  for (int j = threadIdx.x; j < B; j += blockDim.x) se += expf(S[(size_t)i * ld + j] - mx);
   se = block_sum<float>(se, scratch);
   if (threadIdx.x == 0) lse_r[i] = mx + logf(se);
 }
 // column j: lse_c[j]
-__global__ void __launch_bounds__(128) nce_cols_kernel(const float* __restrict__ S, int B, float* __restrict__ lse_c) {
+__global__ void __launch_bounds__(128) nce_cols_kernel(const float* __restrict__ S, int B, int ld,
+                                                       float* __restrict__ lse_c) {
   __shared__ float scratch[34];
   const int j = blockIdx.x;
   float mx = -INFINITY;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) mx = fmaxf(mx, S[(size_t)i * B + j]);
+  for (int i = threadIdx.x; i < B; i += blockDim.x) mx = fmaxf(mx, S[(size_t)i * ld + j]);
   mx = block_max(mx, scratch);
   float se = 0.f;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) se += expf(S[(size_t)i * B + j] - mx);
+  for (int i = threadIdx.x; i < B; i += blockDim.x) se += expf(S[(size_t)i * ld + j] - mx);
   se = block_sum<float>(se, scratch);
   if (threadIdx.x == 0) lse_c[j] = mx + logf(se);
 }
 // G = (softmax_rows + softmax_cols - 2I) / (2B); block 0 also writes the loss
 __global__ void __launch_bounds__(128) nce_grad_kernel(const float* __restrict__ S, const float* __restrict__ lse_r,
-                                                       const float* __restrict__ lse_c, int B, float* __restrict__ G,
-                                                       float* __restrict__ loss_out) {
+                                                       const float* __restrict__ lse_c, int B, int ld,
+                                                       float* __restrict__ G, float* __restrict__ loss_out) {
   __shared__ float scratch[34];
   const int i = blockIdx.x;
   const float inv2B = 0.5f / B, lr_i = lse_r[i];
   for (int j = threadIdx.x; j < B; j += blockDim.x) {
-    const float s = S[(size_t)i * B + j];
+    const float s = S[(size_t)i * ld + j];
     float g = expf(s - lr_i) + expf(s - lse_c[j]);
     if (j == i) g -= 2.0f;
-    G[(size_t)i * B + j] = g * inv2B;
+    G[(size_t)i * ld + j] = g * inv2B;
   }
   if (blockIdx.x == 0) {
     float acc = 0.f;
-    for (int r = threadIdx.x; r < B; r += blockDim.x) acc += (lse_r[r] - S[(size_t)r * B + r]) + (lse_c[r] - S[(size_t)r * B + r]);
+    for (int r = threadIdx.x; r < B; r += blockDim.x) acc += (lse_r[r] - S[(size_t)r * ld + r]) + (lse_c[r] - S[(size_t)r * ld + r]);
     acc = block_sum<float>(acc, scratch);
     if (threadIdx.x == 0 && loss_out) *loss_out = acc * inv2B;
   }
@@ -251,12 +257,12 @@ __global__ void __launch_bounds__(256) colsum_update_kernel(const float* __restr
                                                             const float* __restrict__ src_b2, float* __restrict__ dst_b2,
                                                             const float* __restrict__ src_g, float* __restrict__ dst_g,
                                                             const float* __restrict__ src_b, float* __restrict__ dst_b) {
-  __shared__ float red[4][8][33];
-  const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + cx;
+  __shared__ float red[4][16][17];
+  const int cx = threadIdx.x & 15, rg = threadIdx.x >> 4;
+  const int n = blockIdx.x * 16 + cx;
   float a1 = 0.f, a2 = 0.f, ag = 0.f, ab = 0.f;
   if (n < d) {
-    for (int b = rg; b < B; b += 8) {
+    for (int b = rg; b < B; b += 16) {
       const size_t i = (size_t)b * d + n;
       a1 += dp[i];
       a2 += df[i];
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(256) colsum_update_kernel(const float* __restr
   if (rg < 4 && n < d) {
     float t = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += red[rg][r][cx];
+    for (int r = 0; r < 16; ++r) t += red[rg][r][cx];
     const float l = *lr;
     const float* src = rg == 0 ? src_b1 : rg == 1 ? src_b2 : rg == 2 ? src_g : src_b;
     float* dst = rg == 0 ? dst_b1 : rg == 1 ? dst_b2 : rg == 2 ? dst_g : dst_b;
@@ -343,15 +349,15 @@ __global__ void __launch_bounds__(256) ln_tangent_kernel(const float* __restrict
 __global__ void __launch_bounds__(128) nce_t_rows_kernel(const float* __restrict__ part, int splits, size_t stride,
                                                          const float* __restrict__ scale, const float* __restrict__ S,
                                                          const float* __restrict__ lse_r, const float* __restrict__ G,
-                                                         int B, float* __restrict__ Sd, float* __restrict__ rho,
+                                                         int B, int ld, float* __restrict__ Sd, float* __restrict__ rho,
                                                          float* __restrict__ rowLd) {
   __shared__ float scratch[34];
   const int i = blockIdx.x;
   const float sc = *scale, l = lse_r[i];
   float a = 0.f, b = 0.f;
   for (int j = threadIdx.x; j < B; j += blockDim.x) {
-    const size_t ij = (size_t)i * B + j;
-    const float v = sc * sum_slabs(part, splits, stride, ij);
+    const size_t ij = (size_t)i * ld + j;
+    const float v = sc * sum_slabs(part, splits, stride, (size_t)i * B + j);
     Sd[ij] = v;
     a = fmaf(expf(S[ij] - l), v, a);
     b = fmaf(G[ij], v, b);
@@ -362,13 +368,14 @@ __global__ void __launch_bounds__(128) nce_t_rows_kernel(const float* __restrict
 }
 // column j: kap_j = sum_i Pc_ij Sd_ij
 __global__ void __launch_bounds__(128) nce_t_cols_kernel(const float* __restrict__ S, const float* __restrict__ lse_c,
-                                                         const float* __restrict__ Sd, int B, float* __restrict__ kap) {
+                                                         const float* __restrict__ Sd, int B, int ld,
+                                                         float* __restrict__ kap) {
   __shared__ float scratch[34];
   const int j = blockIdx.x;
   const float l = lse_c[j];
   float a = 0.f;
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
-    const size_t ij = (size_t)i * B + j;
+    const size_t ij = (size_t)i * ld + j;
     a = fmaf(expf(S[ij] - l), Sd[ij], a);
   }
   a = block_sum<float>(a, scratch);
@@ -378,13 +385,14 @@ __global__ void __launch_bounds__(128) nce_t_cols_kernel(const float* __restrict
 __global__ void __launch_bounds__(128) nce_t_grad_kernel(const float* __restrict__ S, const float* __restrict__ lse_r,
                                                          const float* __restrict__ lse_c, const float* __restrict__ Sd,
                                                          const float* __restrict__ rho, const float* __restrict__ kap,
-                                                         int B, float* __restrict__ Gd, float* __restrict__ rowGdS) {
+                                                         int B, int ld, float* __restrict__ Gd,
+                                                         float* __restrict__ rowGdS) {
   __shared__ float scratch[34];
   const int i = blockIdx.x;
   const float inv2B = 0.5f / B, l = lse_r[i], rh = rho[i];
   float a = 0.f;
   for (int j = threadIdx.x; j < B; j += blockDim.x) {
-    const size_t ij = (size_t)i * B + j;
+    const size_t ij = (size_t)i * ld + j;
     const float s = S[ij], sd = Sd[ij];
     const float g = (expf(s - l) * (sd - rh) + expf(s - lse_c[j]) * (sd - kap[j])) * inv2B;
     Gd[ij] = g;
@@ -479,12 +487,12 @@ __global__ void __launch_bounds__(256) colsum_tangent_update_kernel(
     const float* __restrict__ lr, const float* __restrict__ src_b1, float* __restrict__ dst_b1,
     const float* __restrict__ src_b2, float* __restrict__ dst_b2, const float* __restrict__ src_g,
     float* __restrict__ dst_g, const float* __restrict__ src_b, float* __restrict__ dst_b) {
-  __shared__ float red[4][8][33];
-  const int cx = threadIdx.x & 31, rg = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + cx;
+  __shared__ float red[4][16][17];
+  const int cx = threadIdx.x & 15, rg = threadIdx.x >> 4;
+  const int n = blockIdx.x * 16 + cx;
   float a1 = 0.f, a2 = 0.f, ag = 0.f, ab = 0.f;
   if (n < d) {
-    for (int b = rg; b < B; b += 8) {
+    for (int b = rg; b < B; b += 16) {
       const size_t i = (size_t)b * d + n;
       a1 += dpd[i];
       a2 += dfd[i];
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(256) colsum_tangent_update_kernel(
   if (rg < 4 && n < d) {
     float t = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += red[rg][r][cx];
+    for (int r = 0; r < 16; ++r) t += red[rg][r][cx];
     const float l = *lr;
     const float* src = rg == 0 ? src_b1 : rg == 1 ? src_b2 : rg == 2 ? src_g : src_b;
     float* dst = rg == 0 ? dst_b1 : rg == 1 ? dst_b2 : rg == 2 ? dst_g : dst_b;
