@@ -62,6 +62,14 @@ int vldd_momentum_sgd(float* p, const float* g, float* buf, float lr, float mome
 int vldd_ranks_from_scores(const float* scores_i2t, const float* scores_t2i, int n_img, int n_txt,
                            const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx,
                            int32_t* ranks_i2t, int32_t* ranks_t2i, void* stream);
+/* Caption-sharded ranking (multi-GPU; `scores` holds columns [col_offset, col_offset+cols) of the full matrix, ground
+ * truth indices are GLOBAL).  best_gt: per row the best local ground-truth (score, global index; -inf / -1 if none).
+ * count: per row #{local j : s_j > thr_score or (s_j == thr_score and global j < thr_idx)}.  Summed over shards this is
+ * the rank of epoch.py:219-244 with the tie rule above. */
+int vldd_rank_best_gt(const float* scores, int rows, int cols, int col_offset, const int32_t* gt_ptr,
+                      const int32_t* gt_idx, float* best_score, int32_t* best_idx, void* stream);
+int vldd_rank_count(const float* scores, int rows, int cols, int col_offset, const float* thr_score,
+                    const int32_t* thr_idx, int32_t* counts, void* stream);
 /* counts3 = {#ranks<1, #ranks<5, #ranks<10}.   epoch.py:227-229,236-238. */
 int vldd_recall_counts(const int32_t* ranks, int n, int32_t* counts3, void* stream);
 /* S_i2t[I,T] = scale * img @ txt^T and/or S_t2i[T,I] (either may be NULL).   epoch_original.py:94,101. */

@@ -104,6 +104,20 @@ int vldd_ranks_from_scores(const float* scores_i2t, const float* scores_t2i, int
   return VLDD_OK;
 }
 
+int vldd_rank_best_gt(const float* scores, int rows, int cols, int col_offset, const int32_t* gt_ptr,
+                      const int32_t* gt_idx, float* best_score, int32_t* best_idx, void* stream) {
+  VLDD_REQUIRE(rows >= 0 && cols >= 0 && (rows == 0 || (scores && gt_ptr && gt_idx && best_score && best_idx)),
+               "rank_best_gt: bad arguments");
+  return best_gt_rows(scores, cols, rows, cols, col_offset, gt_ptr, gt_idx, best_score, best_idx, S(stream));
+}
+
+int vldd_rank_count(const float* scores, int rows, int cols, int col_offset, const float* thr_score,
+                    const int32_t* thr_idx, int32_t* counts, void* stream) {
+  VLDD_REQUIRE(rows >= 0 && cols >= 0 && (rows == 0 || (scores && thr_score && thr_idx && counts)),
+               "rank_count: bad arguments");
+  return count_rows(scores, cols, rows, cols, col_offset, thr_score, thr_idx, counts, S(stream));
+}
+
 int vldd_recall_counts(const int32_t* ranks, int n, int32_t* counts3, void* stream) {
   VLDD_REQUIRE(n >= 0 && counts3 && (n == 0 || ranks), "recall_counts: null pointer");
   return recall_counts(ranks, n, counts3, S(stream));

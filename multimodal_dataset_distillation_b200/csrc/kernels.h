@@ -18,6 +18,10 @@ int momentum_sgd(float* p, const float* g, float* buf, float lr, float momentum,
 // retrieval.cu
 int ranks_rows(const float* S, int64_t ld, int nrows, int ncols, const int32_t* gt_ptr, const int32_t* gt_idx,
                int32_t* ranks, cudaStream_t st);
+int best_gt_rows(const float* S, int64_t ld, int nrows, int ncols, int col_offset, const int32_t* gt_ptr,
+                 const int32_t* gt_idx, float* best_score, int32_t* best_idx, cudaStream_t st);
+int count_rows(const float* S, int64_t ld, int nrows, int ncols, int col_offset, const float* thr_score,
+               const int32_t* thr_idx, int32_t* counts, cudaStream_t st);
 int recall_counts(const int32_t* ranks, int n, int32_t* counts3, cudaStream_t st);
 int sim_scores(const float* img, const float* txt, int I, int T, int D, float scale, float* S_i2t, float* S_t2i,
                cudaStream_t st);

@@ -88,6 +88,70 @@ int ranks_rows(const float* S, int64_t ld, int nrows, int ncols, const int32_t* 
   return check_launch("ranks_rows");
 }
 
+// ---- caption-sharded form (multi-GPU): the score matrix holds columns [col_offset, col_offset + ncols) of the full
+// one.  Step 1: best ground-truth candidate per row among the LOCAL columns; step 2 (after the candidates of all
+// shards are merged on the host side of the collective): count local columns that beat the global threshold.
+__global__ void __launch_bounds__(32) best_gt_rows_kernel(const float* __restrict__ S, int64_t ld, int ncols, int col_offset,
+                                                          const int32_t* __restrict__ gt_ptr,
+                                                          const int32_t* __restrict__ gt_idx, float* __restrict__ best_score,
+                                                          int32_t* __restrict__ best_idx) {
+  const int r = blockIdx.x, lane = threadIdx.x;
+  const float* __restrict__ row = S + (size_t)r * ld;
+  float bs = -INFINITY;
+  int bc = INT_MAX;
+  bool any = false;
+  for (int e = gt_ptr[r] + lane; e < gt_ptr[r + 1]; e += 32) {
+    const int c = gt_idx[e] - col_offset;            // global -> local column
+    if (c < 0 || c >= ncols) continue;
+    const float s = row[c];
+    const int cg = c + col_offset;
+    if (!any || s > bs || (s == bs && cg < bc)) { bs = s; bc = cg; any = true; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+    const bool oa = __shfl_xor_sync(0xffffffffu, (int)any, o);
+    if (oa && (!any || os > bs || (os == bs && oc < bc))) { bs = os; bc = oc; any = true; }
+  }
+  if (lane == 0) { best_score[r] = any ? bs : -INFINITY; best_idx[r] = any ? bc : -1; }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) count_rows_kernel(const float* __restrict__ S, int64_t ld, int ncols,
+                                                             int col_offset, const float* __restrict__ thr_score,
+                                                             const int32_t* __restrict__ thr_idx,
+                                                             int32_t* __restrict__ counts) {
+  __shared__ int scratch[34];
+  const int r = blockIdx.x;
+  const float* __restrict__ row = S + (size_t)r * ld;
+  const float sg = thr_score[r];
+  const int cg = thr_idx[r] - col_offset;              // may lie outside [0, ncols): then only the sign of (j < cg) matters
+  int cnt = 0;
+  if (thr_idx[r] >= 0) {
+    for (int j = threadIdx.x; j < ncols; j += THREADS) {
+      const float v = row[j];
+      cnt += (v > sg) + (v == sg && j < cg);
+    }
+  }
+  const int total = block_sum<int>(cnt, scratch);
+  if (threadIdx.x == 0) counts[r] = total;
+}
+
+int best_gt_rows(const float* S, int64_t ld, int nrows, int ncols, int col_offset, const int32_t* gt_ptr,
+                 const int32_t* gt_idx, float* best_score, int32_t* best_idx, cudaStream_t st) {
+  if (nrows <= 0) return VLDD_OK;
+  best_gt_rows_kernel<<<nrows, 32, 0, st>>>(S, ld, ncols, col_offset, gt_ptr, gt_idx, best_score, best_idx);
+  return check_launch("best_gt_rows");
+}
+
+int count_rows(const float* S, int64_t ld, int nrows, int ncols, int col_offset, const float* thr_score,
+               const int32_t* thr_idx, int32_t* counts, cudaStream_t st) {
+  if (nrows <= 0) return VLDD_OK;
+  count_rows_kernel<256><<<nrows, 256, 0, st>>>(S, ld, ncols, col_offset, thr_score, thr_idx, counts);
+  return check_launch("count_rows");
+}
+
 // counts3 += (#ranks<1, #ranks<5, #ranks<10)     (epoch.py:227-229,236-238)
 __global__ void __launch_bounds__(256) recall_counts_kernel(const int32_t* __restrict__ ranks, int n,
                                                             int32_t* __restrict__ counts3) {

@@ -139,6 +139,27 @@ def ranks_from_scores(scores_i2t, scores_t2i, txt2img: torch.Tensor, img2txt_ptr
     return (r1 if s1 is not None else None), (r2 if s2 is not None else None)
 
 
+def rank_best_gt(scores: torch.Tensor, col_offset: int, gt_ptr: torch.Tensor, gt_idx: torch.Tensor):
+    """Best local ground-truth candidate per row of a column shard: (score[rows] f32, global index[rows] i32)."""
+    s = _req(scores, "scores")
+    rows, cols = s.shape
+    bs = torch.empty(rows, dtype=torch.float32, device=s.device)
+    bi = torch.empty(rows, dtype=torch.int32, device=s.device)
+    check(lib().vldd_rank_best_gt(_ptr(s), rows, cols, int(col_offset), _ptr(_req(gt_ptr, "gt_ptr", torch.int32)),
+                                  _ptr(_req(gt_idx, "gt_idx", torch.int32)), _ptr(bs), _ptr(bi), _stream()), "rank_best_gt")
+    return bs, bi
+
+
+def rank_count(scores: torch.Tensor, col_offset: int, thr_score: torch.Tensor, thr_idx: torch.Tensor) -> torch.Tensor:
+    """Per row: number of local columns ranked ahead of the (global) threshold candidate."""
+    s = _req(scores, "scores")
+    rows, cols = s.shape
+    out = torch.empty(rows, dtype=torch.int32, device=s.device)
+    check(lib().vldd_rank_count(_ptr(s), rows, cols, int(col_offset), _ptr(_req(thr_score, "thr_score")),
+                                _ptr(_req(thr_idx, "thr_idx", torch.int32)), _ptr(out), _stream()), "rank_count")
+    return out
+
+
 def recall_counts(ranks: torch.Tensor) -> torch.Tensor:
     r = _req(ranks, "ranks", torch.int32)
     out = torch.empty(3, dtype=torch.int32, device=r.device)

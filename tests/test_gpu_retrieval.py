@@ -138,3 +138,33 @@ def test_sim_rank_flickr_shape():
     res_ref = RR.recall_dict(ref1, RR.ranks_vectorised(np.ascontiguousarray(S.T), np.arange(5001, dtype=np.int32), t2i))
     for k in res_ref:
         assert abs(res_gpu[k] - res_ref[k]) <= 0.2, k
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_caption_sharded_ranks_match_single_gpu(world):
+    """The per-shard kernels + the product merge rule reproduce the unsharded ranks bit for bit (shards emulated
+    sequentially on one GPU; the collectives themselves are tested under gloo in tests/test_dist_gloo.py)."""
+    from multimodal_dataset_distillation_b200 import dist as D, ops
+    rng = np.random.default_rng(world)
+    I, C, Dm = 37, 5, 32
+    img, txt = RR.synthetic_retrieval(I, C, Dm, seed=world)
+    img, txt = (np.round(img * 4) / 4).astype(np.float32), (np.round(txt * 4) / 4).astype(np.float32)     # ties
+    T = I * C
+    txt2img, img2txt = RR.flickr_maps(I, C)
+    t2i, ptr, idx = ops.maps_to_arrays(txt2img, img2txt, I, T)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    s_full, st_full = ops.sim_scores(dev(img), dev(txt), 14.285714)
+    ref_i, ref_t = ops.ranks_from_scores(s_full, st_full, dev(t2i), dev(ptr), dev(idx))
+    be = D.CudaBackend()
+    cands, shards = [], []
+    for r in range(world):
+        lo, hi = D.shard_bounds(T, world, r)
+        s1, s2 = be.scores(dev(img), dev(txt[lo:hi].copy()), 14.285714)
+        assert torch.equal(s1, s_full[:, lo:hi])                        # same arithmetic per element regardless of tiling
+        shards.append((lo, hi, s1, s2))
+        cands.append(be.best_gt(s1, lo, dev(ptr), dev(idx)))
+    thr_s, thr_i = D.merge_candidates(torch.stack([c[0] for c in cands]), torch.stack([c[1] for c in cands]))
+    counts = sum(be.count(s1, lo, thr_s, thr_i) for lo, hi, s1, s2 in shards)
+    assert torch.equal(counts, ref_i)
+    got_t = torch.cat([be.ranks_t2i(s2, dev(t2i[lo:hi].copy())) for lo, hi, s1, s2 in shards])
+    assert torch.equal(got_t, ref_t)
