@@ -2,6 +2,7 @@
 // C++ launchers.  No torch types cross this boundary.
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/vldd_b200.h"
@@ -18,6 +19,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLDD_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int check_launch(const char* what) {

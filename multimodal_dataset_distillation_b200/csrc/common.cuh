@@ -35,6 +35,32 @@ int check_launch(const char* what);
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Every kernel of the library starts with pdl_wait(): it blocks until the preceding kernel in the stream has
+// completed and its writes are visible (a no-op when the launch carries no programmatic dependency), then
+// pdl_launch_dependents() lets the NEXT kernel be scheduled early so that its launch latency and prologue
+// (barrier init, TMEM allocation, descriptor prefetch) overlap this kernel's execution.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_launch_dependents(); }
+
+bool pdl_enabled();   // VLDD_PDL=0 disables the launch attribute (capi.cu)
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors surface through cudaGetLastError (check_launch)
+}
+
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

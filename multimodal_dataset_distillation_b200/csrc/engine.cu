@@ -113,17 +113,20 @@ void carve(Work& w, const Dims& m, void* base) {
 }
 
 __global__ void fill_kernel(float* p, float v, int n) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 __global__ void reduce_slabs_kernel(const float* __restrict__ part, int splits, size_t stride, size_t n,
                                     float* __restrict__ out) {
+  pdl_enter();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = sum_slabs(part, splits, stride, i);
 }
 __global__ void __launch_bounds__(256) dot_over_scale_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                              size_t n, const float* __restrict__ scale,
                                                              float* __restrict__ out) {
+  pdl_enter();
   __shared__ float scratch[34];
   float acc = 0.f;
   for (size_t i = threadIdx.x; i < n; i += blockDim.x) acc = fmaf(a[i], b[i], acc);
@@ -243,36 +246,36 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   int sp = 1;
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, W1, dt, B, d, dt), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,true> A=s.Yb", st);
-  epi_p_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, b1, B, d, s.p, s.h);
+  launch_k(epi_p_kernel, ew_grid(Bd), 256, 0, st, w.pa, sp, Bd, b1, B, d, s.p, s.h);
   prof_mark("epi_p_kernel", st);
   // f = h W2^T + b2 ; r = mask f + p ; LN ; normalise
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.h, d, W2, d, B, d, d), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,true> A=s.h", st);
   if (row_v4_ok(d))
-    VLDD_ROW_V4_DISPATCH(d, ln_fwd_v4_kernel, <<<B, 256, 0, st>>>(w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr,
+    VLDD_ROW_V4_DISPATCH(d, ln_fwd_v4_kernel, (B, 256, 0, st), (w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr,
                                                                    s.yn, s.rstd, s.nz));
   else
-    ln_fwd_kernel<<<B, 256, d * sizeof(float), st>>>(w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr, s.yn,
+    launch_k(ln_fwd_kernel, B, 256, d * sizeof(float), st, w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr, s.yn,
                                                      s.rstd, s.nz);
   prof_mark("ln_fwd_kernel", st);
   // S = scale * Xb Yn^T ; lse ; G ; loss
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, s.yn, d, B, B, d), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,true> A=s.Xb", st);
-  nce_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, (size_t)B * B, scale, B, Bp, s.S, s.lse_r);
+  launch_k(nce_rows_kernel, B, 128, 0, st, w.pa, sp, (size_t)B * B, scale, B, Bp, s.S, s.lse_r);
   prof_mark("nce_rows_kernel", st);
-  nce_cols_kernel<<<B, 128, 0, st>>>(s.S, B, Bp, s.lse_c);
+  launch_k(nce_cols_kernel, B, 128, 0, st, s.S, B, Bp, s.lse_c);
   prof_mark("nce_cols_kernel", st);
-  nce_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, B, Bp, s.G, ce_out);
+  launch_k(nce_grad_kernel, B, 128, 0, st, s.S, s.lse_r, s.lse_c, B, Bp, s.G, ce_out);
   prof_mark("nce_grad_kernel", st);
   // dyn_raw[j,:] = sum_i G[i,j] Xb[i,:]
   // (G is stored with leading dimension Bp and zero padding columns: rows B..Bp-1 of the product are zeros)
   CHECK_RC((gemm_store<false, false>(gemm_ops(s.G, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st)));
   prof_mark("gemm_store<false,false> A=s.G", st);
   if (row_v4_ok(d))
-    VLDD_ROW_V4_DISPATCH(d, norm_ln_bwd_v4_kernel, <<<B, 256, 0, st>>>(w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d,
+    VLDD_ROW_V4_DISPATCH(d, norm_ln_bwd_v4_kernel, (B, 256, 0, st), (w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d,
                                                                         s.dyn, s.q, s.dz, s.dr, s.df));
   else
-    norm_ln_bwd_kernel<<<B, 256, 0, st>>>(w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d, s.dyn, s.q, s.dz, s.dr,
+    launch_k(norm_ln_bwd_kernel, B, 256, 0, st, w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d, s.dyn, s.q, s.dz, s.dr,
                                           s.df);
   prof_mark("norm_ln_bwd_kernel", st);
   // branch 1: theta_{k+1}[W2] = theta_k[W2] - lr df^T h   (needs only df, h)
@@ -284,7 +287,7 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   // dh = df W2 ; dp = dh gelu'(p) + dr
   CHECK_RC((gemm_partial<true, false>(gemm_ops(s.df, d, W2, d, B, d, d), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,false> A=s.df", st);
-  epi_dp_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, s.p, s.dr, Bd, s.dh, s.dp);
+  launch_k(epi_dp_kernel, ew_grid(Bd), 256, 0, st, w.pa, sp, Bd, s.p, s.dr, Bd, s.dh, s.dp);
   prof_mark("epi_dp_kernel", st);
   // branch 2: theta_{k+1}[W1] = theta_k[W1] - lr dp^T Yb ;  main: small params
   CHECK_RC(lane_edge(st, L.s2));
@@ -292,7 +295,7 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(s.dp, d, s.Yb, dt, d, dt, B), upd_src ? upd_src + m.oW1 : nullptr,
                                     upd_dst + m.oW1, dt, lr, L.s2)));
   prof_mark("gemm_axpy<false,false> A=s.dp", L.s2);
-  colsum_update_kernel<<<ceil_div(d, 16), 256, 0, st>>>(
+  launch_k(colsum_update_kernel, ceil_div(d, 16), 256, 0, st, 
       s.dp, s.df, s.dz, s.rhat, B, d, lr, upd_src ? upd_src + m.ob1 : nullptr, upd_dst + m.ob1,
       upd_src ? upd_src + m.ob2 : nullptr, upd_dst + m.ob2, upd_src ? upd_src + m.og : nullptr, upd_dst + m.og,
       upd_src ? upd_src + m.obt : nullptr, upd_dst + m.obt);
@@ -316,45 +319,44 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   int sp = 1;
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,true> A=s.Yb", st);
-  epi_pd_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, c1, s.p, B, d, w.pd, w.hd);
+  launch_k(epi_pd_kernel, ew_grid(Bd), 256, 0, st, w.pa, sp, Bd, c1, s.p, B, d, w.pd, w.hd);
   prof_mark("epi_pd_kernel", st);
   // fd = hd W2^T + h V2^T + c2 ; LN / normalise tangents
   CHECK_RC((gemm_partial<true, true>(gemm_ops2(w.hd, d, W2, d, d, s.h, d, V2, d, d, B, d), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,true> A=w.hd", st);
   if (row_v4_ok(d))
-    VLDD_ROW_V4_DISPATCH(d, ln_tangent_v4_kernel, <<<B, 256, 0, st>>>(w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz,
+    VLDD_ROW_V4_DISPATCH(d, ln_tangent_v4_kernel, (B, 256, 0, st), (w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz,
                                                                        gam, gamd, betd, d, w.rhatd, w.ynd, w.t, w.nzd));
   else
-    ln_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz, gam,
+    launch_k(ln_tangent_kernel, B, 256, d * sizeof(float), st, w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz, gam,
                                                          gamd, betd, d, w.rhatd, w.ynd, w.t, w.nzd);
   prof_mark("ln_tangent_kernel", st);
   // Sd = scale Xb Ynd^T ; rho, kappa, Gd ; L_dot ; dlr, dscale
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, w.ynd, d, B, B, d), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,true> A=s.Xb", st);
-  nce_t_rows_kernel<<<B, 128, 0, st>>>(w.pa, sp, (size_t)B * B, scale, s.S, s.lse_r, s.G, B, Bp, w.Sd, w.rho, w.rowA);
+  launch_k(nce_t_rows_kernel, B, 128, 0, st, w.pa, sp, (size_t)B * B, scale, s.S, s.lse_r, s.G, B, Bp, w.Sd, w.rho, w.rowA);
   prof_mark("nce_t_rows_kernel", st);
-  nce_t_cols_kernel<<<B, 128, 0, st>>>(s.S, s.lse_c, w.Sd, B, Bp, w.kap);
+  launch_k(nce_t_cols_kernel, B, 128, 0, st, s.S, s.lse_c, w.Sd, B, Bp, w.kap);
   prof_mark("nce_t_cols_kernel", st);
-  nce_t_grad_kernel<<<B, 128, 0, st>>>(s.S, s.lse_r, s.lse_c, w.Sd, w.rho, w.kap, B, Bp, w.Gd, w.rowB);
+  launch_k(nce_t_grad_kernel, B, 128, 0, st, s.S, s.lse_r, s.lse_c, w.Sd, w.rho, w.kap, B, Bp, w.Gd, w.rowB);
   prof_mark("nce_t_grad_kernel", st);
   // branch 1: dXn_dot = scale (Gd Yn + G Ynd)  ->  dXn[perm] -= lr * scale * raw
   CHECK_RC(lane_edge(st, L.s1));
   L.s1_busy = true;
   CHECK_RC((gemm_store<true, false>(gemm_ops2(w.Gd, Bp, s.yn, d, B, s.G, Bp, w.ynd, d, B, B, d), w.pc, d, 1.0f, L.s1)));
   prof_mark("gemm_store<true,false> A=w.Gd", L.s1);
-  scatter_add_rows_kernel<<<B, 256, 0, L.s1>>>(w.pc, 1, Bd, perm, d, lr, scale, w.dXn);
+  launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pc, 1, Bd, perm, d, lr, scale, w.dXn);
   prof_mark("scatter_add_rows_kernel", L.s1);
-  nce_t_finish_kernel<<<1, 128, 0, st>>>(w.rowA, w.rowB, B, lr, scale, dlr, dscale);
+  launch_k(nce_t_finish_kernel, 1, 128, 0, st, w.rowA, w.rowB, B, lr, scale, dlr, dscale);
   prof_mark("nce_t_finish_kernel", st);
   // dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
   CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st)));
   prof_mark("gemm_store<false,false> A=w.Gd", st);
   if (row_v4_ok(d))
-    VLDD_ROW_V4_DISPATCH(d, norm_ln_bwd_tangent_v4_kernel,
-                         <<<B, 256, 0, st>>>(w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd, s.dz, s.rhat, w.rhatd, s.rstd,
+    VLDD_ROW_V4_DISPATCH(d, norm_ln_bwd_tangent_v4_kernel, (B, 256, 0, st), (w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd, s.dz, s.rhat, w.rhatd, s.rstd,
                                              w.t, s.dr, gam, gamd, mask, d, w.dzd, w.drd, w.dfd));
   else
-    norm_ln_bwd_tangent_kernel<<<B, 256, d * sizeof(float), st>>>(w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd,
+    launch_k(norm_ln_bwd_tangent_kernel, B, 256, d * sizeof(float), st, w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd,
                                                                   s.dz, s.rhat, w.rhatd, s.rstd, w.t, s.dr, gam, gamd,
                                                                   mask, d, w.dzd, w.drd, w.dfd);
   prof_mark("norm_ln_bwd_tangent_kernel", st);
@@ -367,19 +369,19 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   // dhd = dfd W2 + df V2 ; dpd
   CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,false> A=w.dfd", st);
-  epi_dpd_kernel<<<ew_grid(Bd), 256, 0, st>>>(w.pa, sp, Bd, s.p, w.pd, s.dh, w.drd, Bd, w.dpd);
+  launch_k(epi_dpd_kernel, ew_grid(Bd), 256, 0, st, w.pa, sp, Bd, s.p, w.pd, s.dh, w.drd, Bd, w.dpd);
   prof_mark("epi_dpd_kernel", st);
   // branch 1 (after dXn): dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.)
   CHECK_RC(lane_edge(st, L.s1));
   int sp_y = 1;
   CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dpd, d, W1, dt, d, s.dp, d, V1, dt, d, B, dt), w.pe, &sp_y, L.s1)));
   prof_mark("gemm_partial<true,false> A=w.dpd", L.s1);
-  scatter_add_rows_kernel<<<B, 256, 0, L.s1>>>(w.pe, sp_y, (size_t)B * dt, perm, dt, lr, nullptr, dY);
+  launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pe, sp_y, (size_t)B * dt, perm, dt, lr, nullptr, dY);
   prof_mark("scatter_add_rows_kernel", L.s1);
   // main: a_k[W1] = a_{k+1}[W1] - lr dpd^T Yb ; small params by column sums
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), v + m.oW1, a_out + m.oW1, dt, lr, st)));
   prof_mark("gemm_axpy<false,false> A=w.dpd", st);
-  colsum_tangent_update_kernel<<<ceil_div(d, 16), 256, 0, st>>>(
+  launch_k(colsum_tangent_update_kernel, ceil_div(d, 16), 256, 0, st, 
       w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
       v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
   prof_mark("colsum_tangent_update_kernel", st);
@@ -422,14 +424,14 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   VLDD_CUDA(cudaMemsetAsync(w.dXn, 0, (size_t)N * d * sizeof(float), st));
   CHECK_RC(zero_square_matrices(m, w, st));
   MARK("start");
-  row_normalise_kernel<<<N, 256, 0, st>>>(U, d, w.Xn, w.un);
+  launch_k(row_normalise_kernel, N, 256, 0, st, U, d, w.Xn, w.un);
   MARK("row_normalise");
   // forward unroll
   for (int k = 0; k < K; ++k) {
     Saved& s = w.sv[k];
     const int64_t* perm = perms + (size_t)k * B;
-    gather_rows_kernel<<<B, 256, 0, st>>>(Y, perm, dt, s.Yb);
-    gather_rows_kernel<<<B, 256, 0, st>>>(w.Xn, perm, d, s.Xb);
+    launch_k(gather_rows_kernel, B, 256, 0, st, Y, perm, dt, s.Yb);
+    launch_k(gather_rows_kernel, B, 256, 0, st, w.Xn, perm, d, s.Xb);
     MARK("gather_rows x2");
     const float* th = w.traj + (size_t)k * m.P;
     CHECK_RC(forward_step(m, w, s, th, th, w.traj + (size_t)(k + 1) * m.P, lr, scale, masks ? masks + k * Bd : nullptr,
@@ -450,7 +452,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
                           perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L));
     float* t = a_cur; a_cur = a_nxt; a_nxt = t;
   }
-  row_normalise_bwd_kernel<<<N, 256, 0, st>>>(w.Xn, w.un, w.dXn, nullptr, d, dU);
+  launch_k(row_normalise_bwd_kernel, N, 256, 0, st, w.Xn, w.un, w.dXn, nullptr, d, dU);
   MARK("row_normalise_bwd");
   prof_report();
   return check_launch("unrolled_match");
@@ -552,9 +554,9 @@ int contrastive_step(const float* theta, const float* Y, const float* U, const f
   }
   Saved& s = w.sv[0];
   const size_t Bd = (size_t)B * d;
-  fill_kernel<<<1, 32, 0, st>>>(w.neg_one, -1.0f, 4);
+  launch_k(fill_kernel, 1, 32, 0, st, w.neg_one, -1.0f, 4);
   CHECK_RC(zero_square_matrices(m, w, st));
-  row_normalise_kernel<<<B, 256, 0, st>>>(U, d, w.Xn, w.un);
+  launch_k(row_normalise_kernel, B, 256, 0, st, U, d, w.Xn, w.un);
   VLDD_CUDA(cudaMemcpyAsync(s.Yb, Y, (size_t)B * dt * sizeof(float), cudaMemcpyDeviceToDevice, st));
   VLDD_CUDA(cudaMemcpyAsync(s.Xb, w.Xn, Bd * sizeof(float), cudaMemcpyDeviceToDevice, st));
   std::lock_guard<std::mutex> lock(g_graph_mu);
@@ -566,15 +568,15 @@ int contrastive_step(const float* theta, const float* Y, const float* U, const f
   if (dY) {
     int sp = 1;
     CHECK_RC((gemm_partial<true, false>(gemm_ops(s.dp, d, theta + m.oW1, dt, B, dt, d), w.pa, &sp, st)));
-    reduce_slabs_kernel<<<ew_grid((size_t)B * dt), 256, 0, st>>>(w.pa, sp, (size_t)B * dt, (size_t)B * dt, dY);
+    launch_k(reduce_slabs_kernel, ew_grid((size_t)B * dt), 256, 0, st, w.pa, sp, (size_t)B * dt, (size_t)B * dt, dY);
   }
   // dU = normalise_bwd(scale * G Yn)
   if (dU) {
     CHECK_RC((gemm_store<true, false>(gemm_ops(s.G, m.Bp, s.yn, d, B, d, B), w.pb, d, 1.0f, st)));
-    row_normalise_bwd_kernel<<<B, 256, 0, st>>>(w.Xn, w.un, w.pb, scale, d, dU);
+    launch_k(row_normalise_bwd_kernel, B, 256, 0, st, w.Xn, w.un, w.pb, scale, d, dU);
   }
   // dscale = sum(G * S) / scale
-  if (dscale) dot_over_scale_kernel<<<1, 256, 0, st>>>(s.G, s.S, (size_t)B * m.Bp, scale, dscale);
+  if (dscale) launch_k(dot_over_scale_kernel, 1, 256, 0, st, s.G, s.S, (size_t)B * m.Bp, scale, dscale);
   return check_launch("contrastive_step");
 }
 
@@ -604,13 +606,13 @@ int proj_head_forward(const float* theta, const float* Y, const float* mask, int
   float* part = h + Rd;
   int sp = 1;
   CHECK_RC((gemm_partial<true, true>(gemm_ops(Y, dt, theta + m.oW1, dt, rows, d, dt), part, &sp, st)));
-  epi_p_kernel<<<ew_grid(Rd), 256, 0, st>>>(part, sp, Rd, theta + m.ob1, rows, d, p, h);
+  launch_k(epi_p_kernel, ew_grid(Rd), 256, 0, st, part, sp, Rd, theta + m.ob1, rows, d, p, h);
   CHECK_RC((gemm_partial<true, true>(gemm_ops(h, d, theta + m.oW2, d, rows, d, d), part, &sp, st)));
   if (row_v4_ok(d))
-    VLDD_ROW_V4_DISPATCH(d, ln_fwd_v4_kernel, <<<rows, 256, 0, st>>>(part, sp, Rd, theta + m.ob2, mask, p, theta + m.og,
+    VLDD_ROW_V4_DISPATCH(d, ln_fwd_v4_kernel, (rows, 256, 0, st), (part, sp, Rd, theta + m.ob2, mask, p, theta + m.og,
                                                                       theta + m.obt, d, nullptr, z, zn, nullptr, nullptr));
   else
-    ln_fwd_kernel<<<rows, 256, d * sizeof(float), st>>>(part, sp, Rd, theta + m.ob2, mask, p, theta + m.og,
+    launch_k(ln_fwd_kernel, rows, 256, d * sizeof(float), st, part, sp, Rd, theta + m.ob2, mask, p, theta + m.og,
                                                         theta + m.obt, d, nullptr, z, zn, nullptr, nullptr);
   return check_launch("proj_head_forward");
 }

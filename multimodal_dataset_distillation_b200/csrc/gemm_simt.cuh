@@ -97,6 +97,7 @@ template <bool A_KMAJOR, bool B_KMAJOR, class Epi>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmOperands g, float* __restrict__ partials,
                                                         long long part_stride, Epi epi, int vecA0, int vecB0,
                                                         int vecA1, int vecB1) {
+  pdl_enter();
   __shared__ __align__(16) float As[2][GBK][GBM + GPAD];
   __shared__ __align__(16) float Bs[2][GBK][GBN + GPAD];
   const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
@@ -173,7 +174,7 @@ inline int vec_ok(const float* p, int ld) { return p != nullptr && aligned16(p) 
 template <bool A_KMAJOR, bool B_KMAJOR, class Epi>
 inline void launch_gemm(const GemmOperands& g, int splits, float* partials, Epi epi, cudaStream_t st) {
   dim3 grid(ceil_div(g.N, GBN), ceil_div(g.M, GBM), splits);
-  gemm_simt_kernel<A_KMAJOR, B_KMAJOR, Epi><<<grid, 256, 0, st>>>(
+  launch_k(gemm_simt_kernel<A_KMAJOR, B_KMAJOR, Epi>, grid, 256, 0, st, 
       g, partials, (long long)g.M * g.N, epi, vec_ok(g.A0, g.lda0), vec_ok(g.B0, g.ldb0),
       g.K1 ? vec_ok(g.A1, g.lda1) : 0, g.K1 ? vec_ok(g.B1, g.ldb1) : 0);
 }

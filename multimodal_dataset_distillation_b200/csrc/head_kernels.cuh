@@ -27,6 +27,7 @@ __device__ __forceinline__ float sum_slabs(const float* __restrict__ part, int s
 __global__ void __launch_bounds__(256) epi_p_kernel(const float* __restrict__ part, int splits, size_t stride,
                                                     const float* __restrict__ b1, int rows, int d,
                                                     float* __restrict__ p, float* __restrict__ h) {
+  pdl_enter();
   const size_t n = (size_t)rows * d;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % d);
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ p
                                                      float* __restrict__ rhat, float* __restrict__ z_out,
                                                      float* __restrict__ yn, float* __restrict__ rstd_out,
                                                      float* __restrict__ nz_out) {
+  pdl_enter();
   extern __shared__ float rbuf[];  // d floats
   __shared__ float scratch[34];
   const int row = blockIdx.x;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ p
 // x / |x| per row (distill.py:533 on the image-encoder output); also stores |x|
 __global__ void __launch_bounds__(256) row_normalise_kernel(const float* __restrict__ x, int d, float* __restrict__ xn,
                                                             float* __restrict__ norm_out) {
+  pdl_enter();
   __shared__ float scratch[34];
   const size_t base = (size_t)blockIdx.x * d;
   float s = 0.f;
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(256) row_normalise_bwd_kernel(const float* __r
                                                                 const float* __restrict__ dxn,
                                                                 const float* __restrict__ scale, int d,
                                                                 float* __restrict__ dx) {
+  pdl_enter();
   __shared__ float scratch[34];
   const size_t base = (size_t)blockIdx.x * d;
   float s = 0.f;
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(256) row_normalise_bwd_kernel(const float* __r
 // dst[b,:] = src[idx[b],:]
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
                                                           int cols, float* __restrict__ dst) {
+  pdl_enter();
   const size_t s = (size_t)idx[blockIdx.x] * cols, t = (size_t)blockIdx.x * cols;
   if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
     for (int j = threadIdx.x; j < (cols >> 2); j += blockDim.x)
@@ -132,6 +137,7 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
                                                                const float* __restrict__ lr,
                                                                const float* __restrict__ scale,
                                                                float* __restrict__ dst) {
+  pdl_enter();
   const float coef = -(*lr) * (scale ? *scale : 1.0f);
   const size_t s = (size_t)blockIdx.x * cols, t = (size_t)idx[blockIdx.x] * cols;
   for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[t + j] += coef * sum_slabs(part, splits, stride, s + j);
@@ -144,6 +150,7 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
 __global__ void __launch_bounds__(128) nce_rows_kernel(const float* __restrict__ part, int splits, size_t stride,
                                                        const float* __restrict__ scale, int B, int ld,
                                                        float* __restrict__ S, float* __restrict__ lse_r) {
+  pdl_enter();
   __shared__ float scratch[34];
   const int i = blockIdx.x;
   const float sc = *scale;
@@ -162,6 +169,7 @@ __global__ void __launch_bounds__(128) nce_rows_kernel(const float* __restrict__
 // column j: lse_c[j]
 __global__ void __launch_bounds__(128) nce_cols_kernel(const float* __restrict__ S, int B, int ld,
                                                        float* __restrict__ lse_c) {
+  pdl_enter();
   __shared__ float scratch[34];
   const int j = blockIdx.x;
   float mx = -INFINITY;
@@ -176,6 +184,7 @@ __global__ void __launch_bounds__(128) nce_cols_kernel(const float* __restrict__
 __global__ void __launch_bounds__(128) nce_grad_kernel(const float* __restrict__ S, const float* __restrict__ lse_r,
                                                        const float* __restrict__ lse_c, int B, int ld,
                                                        float* __restrict__ G, float* __restrict__ loss_out) {
+  pdl_enter();
   __shared__ float scratch[34];
   const int i = blockIdx.x;
   const float inv2B = 0.5f / B, lr_i = lse_r[i];
@@ -204,6 +213,7 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_kernel(const float* __restric
                                                           int d, float* __restrict__ dyn, float* __restrict__ q_out,
                                                           float* __restrict__ dz, float* __restrict__ dr,
                                                           float* __restrict__ df) {
+  pdl_enter();
   __shared__ float scratch[34];
   const int row = blockIdx.x;
   const size_t base = (size_t)row * d;
@@ -238,6 +248,7 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_kernel(const float* __restric
 __global__ void __launch_bounds__(256) epi_dp_kernel(const float* __restrict__ part, int splits, size_t stride,
                                                      const float* __restrict__ p, const float* __restrict__ dr,
                                                      size_t n, float* __restrict__ dh, float* __restrict__ dp) {
+  pdl_enter();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = sum_slabs(part, splits, stride, i);
     float phi, d1, d2;
@@ -257,6 +268,7 @@ __global__ void __launch_bounds__(256) colsum_update_kernel(const float* __restr
                                                             const float* __restrict__ src_b2, float* __restrict__ dst_b2,
                                                             const float* __restrict__ src_g, float* __restrict__ dst_g,
                                                             const float* __restrict__ src_b, float* __restrict__ dst_b) {
+  pdl_enter();
   __shared__ float red[4][16][17];
   const int cx = threadIdx.x & 15, rg = threadIdx.x >> 4;
   const int n = blockIdx.x * 16 + cx;
@@ -291,6 +303,7 @@ __global__ void __launch_bounds__(256) colsum_update_kernel(const float* __restr
 __global__ void __launch_bounds__(256) epi_pd_kernel(const float* __restrict__ part, int splits, size_t stride,
                                                      const float* __restrict__ c1, const float* __restrict__ p, int rows,
                                                      int d, float* __restrict__ pd, float* __restrict__ hd) {
+  pdl_enter();
   const size_t n = (size_t)rows * d;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % d);
@@ -312,6 +325,7 @@ __global__ void __launch_bounds__(256) ln_tangent_kernel(const float* __restrict
                                                          const float* __restrict__ gammad, const float* __restrict__ betad,
                                                          int d, float* __restrict__ rhatd, float* __restrict__ ynd,
                                                          float* __restrict__ t_out, float* __restrict__ nzd_out) {
+  pdl_enter();
   extern __shared__ float buf[];  // d floats
   __shared__ float scratch[34];
   const int row = blockIdx.x;
@@ -351,6 +365,7 @@ __global__ void __launch_bounds__(128) nce_t_rows_kernel(const float* __restrict
                                                          const float* __restrict__ lse_r, const float* __restrict__ G,
                                                          int B, int ld, float* __restrict__ Sd, float* __restrict__ rho,
                                                          float* __restrict__ rowLd) {
+  pdl_enter();
   __shared__ float scratch[34];
   const int i = blockIdx.x;
   const float sc = *scale, l = lse_r[i];
@@ -370,6 +385,7 @@ __global__ void __launch_bounds__(128) nce_t_rows_kernel(const float* __restrict
 __global__ void __launch_bounds__(128) nce_t_cols_kernel(const float* __restrict__ S, const float* __restrict__ lse_c,
                                                          const float* __restrict__ Sd, int B, int ld,
                                                          float* __restrict__ kap) {
+  pdl_enter();
   __shared__ float scratch[34];
   const int j = blockIdx.x;
   const float l = lse_c[j];
@@ -387,6 +403,7 @@ __global__ void __launch_bounds__(128) nce_t_grad_kernel(const float* __restrict
                                                          const float* __restrict__ rho, const float* __restrict__ kap,
                                                          int B, int ld, float* __restrict__ Gd,
                                                          float* __restrict__ rowGdS) {
+  pdl_enter();
   __shared__ float scratch[34];
   const int i = blockIdx.x;
   const float inv2B = 0.5f / B, l = lse_r[i], rh = rho[i];
@@ -406,6 +423,7 @@ __global__ void __launch_bounds__(128) nce_t_finish_kernel(const float* __restri
                                                            const float* __restrict__ rowGdS, int B,
                                                            const float* __restrict__ lr, const float* __restrict__ scale,
                                                            float* __restrict__ dlr, float* __restrict__ dscale) {
+  pdl_enter();
   __shared__ float scratch[34];
   float a = 0.f, b = 0.f;
   for (int i = threadIdx.x; i < B; i += blockDim.x) { a += rowLd[i]; b += rowGdS[i]; }
@@ -430,6 +448,7 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_tangent_kernel(
     const float* __restrict__ t_p, const float* __restrict__ dr, const float* __restrict__ gamma,
     const float* __restrict__ gammad, const float* __restrict__ mask, int d, float* __restrict__ dzd,
     float* __restrict__ drd, float* __restrict__ dfd) {
+  pdl_enter();
   extern __shared__ float buf[];  // d floats (dynd, then drhatd)
   __shared__ float scratch[34];
   const int row = blockIdx.x;
@@ -472,6 +491,7 @@ __global__ void __launch_bounds__(256) epi_dpd_kernel(const float* __restrict__ 
                                                       const float* __restrict__ p, const float* __restrict__ pd,
                                                       const float* __restrict__ dh, const float* __restrict__ drd,
                                                       size_t n, float* __restrict__ dpd) {
+  pdl_enter();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = sum_slabs(part, splits, stride, i);
     float phi, d1, d2;
@@ -487,6 +507,7 @@ __global__ void __launch_bounds__(256) colsum_tangent_update_kernel(
     const float* __restrict__ lr, const float* __restrict__ src_b1, float* __restrict__ dst_b1,
     const float* __restrict__ src_b2, float* __restrict__ dst_b2, const float* __restrict__ src_g,
     float* __restrict__ dst_g, const float* __restrict__ src_b, float* __restrict__ dst_b) {
+  pdl_enter();
   __shared__ float red[4][16][17];
   const int cx = threadIdx.x & 15, rg = threadIdx.x >> 4;
   const int n = blockIdx.x * 16 + cx;

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(THREADS) ranks_rows_kernel(const float* __rest
                                                              const int32_t* __restrict__ gt_ptr,
                                                              const int32_t* __restrict__ gt_idx,
                                                              int32_t* __restrict__ ranks, int vec) {
+  pdl_enter();
   __shared__ int scratch[34];
   __shared__ float s_best;
   __shared__ int c_best;
@@ -82,9 +83,9 @@ int ranks_rows(const float* S, int64_t ld, int nrows, int ncols, const int32_t* 
   if (nrows <= 0) return VLDD_OK;
   const int vec = aligned16(S) && (ld % 4 == 0);
   if (ncols > 4096)
-    ranks_rows_kernel<256><<<nrows, 256, 0, st>>>(S, ld, ncols, gt_ptr, gt_idx, ranks, vec);
+    launch_k(ranks_rows_kernel<256>, nrows, 256, 0, st, S, ld, ncols, gt_ptr, gt_idx, ranks, vec);
   else
-    ranks_rows_kernel<128><<<nrows, 128, 0, st>>>(S, ld, ncols, gt_ptr, gt_idx, ranks, vec);
+    launch_k(ranks_rows_kernel<128>, nrows, 128, 0, st, S, ld, ncols, gt_ptr, gt_idx, ranks, vec);
   return check_launch("ranks_rows");
 }
 
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(32) best_gt_rows_kernel(const float* __restric
                                                           const int32_t* __restrict__ gt_ptr,
                                                           const int32_t* __restrict__ gt_idx, float* __restrict__ best_score,
                                                           int32_t* __restrict__ best_idx) {
+  pdl_enter();
   const int r = blockIdx.x, lane = threadIdx.x;
   const float* __restrict__ row = S + (size_t)r * ld;
   float bs = -INFINITY;
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(THREADS) count_rows_kernel(const float* __rest
                                                              int col_offset, const float* __restrict__ thr_score,
                                                              const int32_t* __restrict__ thr_idx,
                                                              int32_t* __restrict__ counts) {
+  pdl_enter();
   __shared__ int scratch[34];
   const int r = blockIdx.x;
   const float* __restrict__ row = S + (size_t)r * ld;
@@ -141,20 +144,21 @@ __global__ void __launch_bounds__(THREADS) count_rows_kernel(const float* __rest
 int best_gt_rows(const float* S, int64_t ld, int nrows, int ncols, int col_offset, const int32_t* gt_ptr,
                  const int32_t* gt_idx, float* best_score, int32_t* best_idx, cudaStream_t st) {
   if (nrows <= 0) return VLDD_OK;
-  best_gt_rows_kernel<<<nrows, 32, 0, st>>>(S, ld, ncols, col_offset, gt_ptr, gt_idx, best_score, best_idx);
+  launch_k(best_gt_rows_kernel, nrows, 32, 0, st, S, ld, ncols, col_offset, gt_ptr, gt_idx, best_score, best_idx);
   return check_launch("best_gt_rows");
 }
 
 int count_rows(const float* S, int64_t ld, int nrows, int ncols, int col_offset, const float* thr_score,
                const int32_t* thr_idx, int32_t* counts, cudaStream_t st) {
   if (nrows <= 0) return VLDD_OK;
-  count_rows_kernel<256><<<nrows, 256, 0, st>>>(S, ld, ncols, col_offset, thr_score, thr_idx, counts);
+  launch_k(count_rows_kernel<256>, nrows, 256, 0, st, S, ld, ncols, col_offset, thr_score, thr_idx, counts);
   return check_launch("count_rows");
 }
 
 // counts3 += (#ranks<1, #ranks<5, #ranks<10)     (epoch.py:227-229,236-238)
 __global__ void __launch_bounds__(256) recall_counts_kernel(const int32_t* __restrict__ ranks, int n,
                                                             int32_t* __restrict__ counts3) {
+  pdl_enter();
   __shared__ int scratch[34];
   int c1 = 0, c5 = 0, c10 = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -177,7 +181,7 @@ int recall_counts(const int32_t* ranks, int n, int32_t* counts3, cudaStream_t st
   if (n <= 0) return VLDD_OK;
   int grid = ceil_div(n, 256);
   if (grid > kNumSMs * 4) grid = kNumSMs * 4;
-  recall_counts_kernel<<<grid, 256, 0, st>>>(ranks, n, counts3);
+  launch_k(recall_counts_kernel, grid, 256, 0, st, ranks, n, counts3);
   return check_launch("recall_counts");
 }
 
@@ -212,6 +216,7 @@ __device__ __forceinline__ unsigned int float_key(float f) {
 
 __global__ void __launch_bounds__(256) topk_fill_rows_kernel(const float* __restrict__ S, float* __restrict__ out,
                                                              int ncols, int k, float fill) {
+  pdl_enter();
   __shared__ int hist[256];
   __shared__ unsigned int sel_prefix;
   __shared__ int sel_remaining;
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(256) topk_fill_rows_kernel(const float* __rest
 
 int topk_fill_rows(const float* S, float* out, int nrows, int ncols, int k, float fill, cudaStream_t st) {
   if (nrows <= 0 || ncols <= 0) return VLDD_OK;
-  topk_fill_rows_kernel<<<nrows, 256, 0, st>>>(S, out, ncols, k, fill);
+  launch_k(topk_fill_rows_kernel, nrows, 256, 0, st, S, out, ncols, k, fill);
   return check_launch("topk_fill_rows");
 }
 

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256) ln_fwd_v4_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, int d, float* __restrict__ rhat,
                                                         float* __restrict__ z_out, float* __restrict__ yn,
                                                         float* __restrict__ rstd_out, float* __restrict__ nz_out) {
+  pdl_enter();
   __shared__ float2 scratch[32];
   const int row = blockIdx.x, d4 = d >> 2;
   const size_t base = (size_t)row * d;
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_v4_kernel(const float* __rest
                                                              int d, float* __restrict__ dyn, float* __restrict__ q_out,
                                                              float* __restrict__ dz, float* __restrict__ dr,
                                                              float* __restrict__ df) {
+  pdl_enter();
   __shared__ float2 scratch[32];
   const int row = blockIdx.x, d4 = d >> 2;
   const size_t base = (size_t)row * d;
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(256) ln_tangent_v4_kernel(const float* __restr
                                                             const float* __restrict__ gammad, const float* __restrict__ betad,
                                                             int d, float* __restrict__ rhatd, float* __restrict__ ynd,
                                                             float* __restrict__ t_out, float* __restrict__ nzd_out) {
+  pdl_enter();
   __shared__ float2 scratch[32];
   const int row = blockIdx.x, d4 = d >> 2;
   const size_t base = (size_t)row * d;
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_tangent_v4_kernel(
     const float* __restrict__ t_p, const float* __restrict__ dr, const float* __restrict__ gamma,
     const float* __restrict__ gammad, const float* __restrict__ mask, int d, float* __restrict__ dzd,
     float* __restrict__ drd, float* __restrict__ dfd) {
+  pdl_enter();
   __shared__ float2 scratch[32];
   const int row = blockIdx.x, d4 = d >> 2;
   const size_t base = (size_t)row * d;
@@ -260,11 +264,12 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_tangent_v4_kernel(
 }
 
 inline bool row_v4_ok(int d) { return d % 4 == 0 && d <= 3072; }
-#define VLDD_ROW_V4_DISPATCH(d, KERNEL, ...)                           \
-  do {                                                                 \
-    if ((d) <= 1024) KERNEL<1> __VA_ARGS__;                            \
-    else if ((d) <= 2048) KERNEL<2> __VA_ARGS__;                       \
-    else KERNEL<3> __VA_ARGS__;                                        \
+#define VLDD_UNPACK(...) __VA_ARGS__
+#define VLDD_ROW_V4_DISPATCH(d, KERNEL, CFG, ARGS)                                         \
+  do {                                                                                     \
+    if ((d) <= 1024) launch_k(KERNEL<1>, VLDD_UNPACK CFG, VLDD_UNPACK ARGS);               \
+    else if ((d) <= 2048) launch_k(KERNEL<2>, VLDD_UNPACK CFG, VLDD_UNPACK ARGS);          \
+    else launch_k(KERNEL<3>, VLDD_UNPACK CFG, VLDD_UNPACK ARGS);                           \
   } while (0)
 
 }  // namespace vldd

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(kStreamThreads) flat_sgd_step_kernel(const flo
                                                                        const float* __restrict__ grad,
                                                                        const float* __restrict__ lr_p,
                                                                        float* __restrict__ out, int64_t n, int vec) {
+  pdl_enter();
   const float lr = *lr_p;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   if (vec) {
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(kStreamThreads) match_loss_fwd_kernel(const fl
                                                                         int vec, double* __restrict__ block_partials,
                                                                         unsigned int* __restrict__ ticket,
                                                                         float* __restrict__ out3) {
+  pdl_enter();
   __shared__ double scratch[34];
   __shared__ bool is_last;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(kStreamThreads) match_loss_bwd_kernel(const fl
                                                                         const float* __restrict__ num_den,
                                                                         const float* __restrict__ gout,
                                                                         float* __restrict__ a, int64_t n, int vec) {
+  pdl_enter();
   const float c = (gout ? *gout : 1.0f) * 2.0f / num_den[1];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   if (vec) {
@@ -122,6 +125,7 @@ __global__ void __launch_bounds__(kStreamThreads) momentum_sgd_kernel(float* __r
                                                                       const float* __restrict__ g,
                                                                       float* __restrict__ buf, float lr, float momentum,
                                                                       int first, int64_t n, int vec) {
+  pdl_enter();
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   if (vec) {
     const int64_t n4 = n >> 2;
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(kStreamThreads) momentum_sgd_kernel(float* __r
 int flat_sgd_step(const float* theta, const float* grad, const float* lr, float* out, int64_t n, cudaStream_t st) {
   if (n <= 0) return VLDD_OK;
   const int vec = aligned16(theta) && aligned16(grad) && aligned16(out);
-  flat_sgd_step_kernel<<<stream_grid(n / 4 + 1), kStreamThreads, 0, st>>>(theta, grad, lr, out, n, vec);
+  launch_k(flat_sgd_step_kernel, stream_grid(n / 4 + 1), kStreamThreads, 0, st, theta, grad, lr, out, n, vec);
   return check_launch("flat_sgd_step");
 }
 
@@ -169,7 +173,7 @@ int match_loss_fwd(const float* thK, const float* tgt, const float* th0, int64_t
   double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 16);
   const int vec = aligned16(thK) && aligned16(tgt) && aligned16(th0);
   const int grid = stream_grid(n / 4 + 1);
-  match_loss_fwd_kernel<<<grid, kStreamThreads, 0, st>>>(thK, tgt, th0, n, vec, parts, ticket, out3);
+  launch_k(match_loss_fwd_kernel, grid, kStreamThreads, 0, st, thK, tgt, th0, n, vec, parts, ticket, out3);
   return check_launch("match_loss_fwd");
 }
 
@@ -177,7 +181,7 @@ int match_loss_bwd(const float* thK, const float* tgt, const float* num_den, con
                    cudaStream_t st) {
   if (n <= 0) return VLDD_OK;
   const int vec = aligned16(thK) && aligned16(tgt) && aligned16(a);
-  match_loss_bwd_kernel<<<stream_grid(n / 4 + 1), kStreamThreads, 0, st>>>(thK, tgt, num_den, gout, a, n, vec);
+  launch_k(match_loss_bwd_kernel, stream_grid(n / 4 + 1), kStreamThreads, 0, st, thK, tgt, num_den, gout, a, n, vec);
   return check_launch("match_loss_bwd");
 }
 
@@ -185,7 +189,7 @@ int momentum_sgd(float* p, const float* g, float* buf, float lr, float momentum,
                  cudaStream_t st) {
   if (n <= 0) return VLDD_OK;
   const int vec = aligned16(p) && aligned16(g) && aligned16(buf);
-  momentum_sgd_kernel<<<stream_grid(n / 4 + 1), kStreamThreads, 0, st>>>(p, g, buf, lr, momentum, first, n, vec);
+  launch_k(momentum_sgd_kernel, stream_grid(n / 4 + 1), kStreamThreads, 0, st, p, g, buf, lr, momentum, first, n, vec);
   return check_launch("momentum_sgd");
 }
 

@@ -207,6 +207,9 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is independent of the preceding kernel: under programmatic dependent launch it overlaps that
+  // kernel's tail; from here on global memory written by predecessors is read
+  pdl_enter();
 
   if (warp == 0) {
     // ===== TMA producer =====

@@ -119,7 +119,7 @@ inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st) {
     maps.b1 = maps.b0;
   }
   dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), splits);
-  kern<<<grid, NUM_THREADS, C::kSmemBytes, st>>>(maps, g.M, g.N, g.K0, g.K1, epi);
+  launch_k(kern, grid, NUM_THREADS, C::kSmemBytes, st, maps, g.M, g.N, g.K0, g.K1, epi);
   return VLDD_OK;
 }
 
