@@ -21,6 +21,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_defs() -> list[str]:
+    """VLDD_NVCC_DEFS="-DVLDD_STAGES_PARTIAL=2 -DVLDD_STAGES_AXPY=1": tuning overrides for experiments."""
+    return os.environ.get("VLDD_NVCC_DEFS", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -36,7 +41,7 @@ def _digest() -> str:
                 with open(os.path.join(root, name), "rb") as f:
                     h.update(name.encode())
                     h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_defs()).encode())
     return h.hexdigest()
 
 
@@ -50,7 +55,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *_extra_defs(), "-I", INCLUDE, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

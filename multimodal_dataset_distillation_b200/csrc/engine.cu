@@ -426,13 +426,16 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   MARK("start");
   launch_k(row_normalise_kernel, N, 256, 0, st, U, d, w.Xn, w.un);
   MARK("row_normalise");
+  // minibatches of all K steps in one launch (distill.py:510-513)
+  if (K > 0) {
+    const size_t step_stride = K > 1 ? (size_t)(w.sv[1].Yb - w.sv[0].Yb) : 0;
+    launch_k(gather_all_kernel, dim3(B, K, 2), 256, 0, st, Y, (const float*)w.Xn, perms, B, dt, d, w.sv[0].Yb, w.sv[0].Xb,
+             step_stride);
+    MARK("gather_all");
+  }
   // forward unroll
   for (int k = 0; k < K; ++k) {
     Saved& s = w.sv[k];
-    const int64_t* perm = perms + (size_t)k * B;
-    launch_k(gather_rows_kernel, B, 256, 0, st, Y, perm, dt, s.Yb);
-    launch_k(gather_rows_kernel, B, 256, 0, st, w.Xn, perm, d, s.Xb);
-    MARK("gather_rows x2");
     const float* th = w.traj + (size_t)k * m.P;
     CHECK_RC(forward_step(m, w, s, th, th, w.traj + (size_t)(k + 1) * m.P, lr, scale, masks ? masks + k * Bd : nullptr,
                           ce ? ce + k : nullptr, L));

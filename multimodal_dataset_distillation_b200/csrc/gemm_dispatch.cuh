@@ -8,6 +8,16 @@
 #include "gemm_simt.cuh"
 #include "tc_gemm_host.cuh"
 
+// pipeline depth per GEMM class (64 KB of shared memory per stage; 0 = the kernel's default of 3).  Measured on B200 at the
+// Flickr shape (ms / iteration): partial/axpy = 3/3: 2.53, 3/1: 2.54, 2/1: 2.74, 2/2: 2.81 -- depth matters for the skinny
+// split-K GEMMs, and shrinking the weight-gradient CTAs to co-reside with them buys nothing.
+#ifndef VLDD_STAGES_PARTIAL
+#define VLDD_STAGES_PARTIAL 0
+#endif
+#ifndef VLDD_STAGES_AXPY
+#define VLDD_STAGES_AXPY 0
+#endif
+
 namespace vldd {
 
 inline bool tc_enabled() {
@@ -39,7 +49,7 @@ inline int gemm_partial(const GemmOperands& g, float* part, int* splits, cudaStr
   const int Kt = g.K0 + g.K1;
   if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) {
     *splits = tc::pick_splits(g.M, g.N, Kt);
-    return tc::launch<AK, BKm, 3>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st);
+    return tc::launch<AK, BKm, 3, tc::EpiPartial, VLDD_STAGES_PARTIAL>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st);
   }
   *splits = simt_pick_splits(g.M, g.N, Kt);
   launch_gemm<AK, BKm>(g, *splits, part, EpiStore{}, st);
@@ -55,7 +65,7 @@ inline int gemm_store(const GemmOperands& g, float* C, int ldc, float alpha, cud
 // dst = src - (*lr) * A B      (src nullable)
 template <bool AK, bool BKm>
 inline int gemm_axpy(const GemmOperands& g, const float* src, float* dst, int ld, const float* lr, cudaStream_t st) {
-  if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) return tc::launch<AK, BKm, 3>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st);
+  if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) return tc::launch<AK, BKm, 3, tc::EpiAxpyTC, VLDD_STAGES_AXPY>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st);
   launch_gemm<AK, BKm>(g, 1, nullptr, EpiAxpy{src, dst, ld, lr}, st);
   return VLDD_OK;
 }

@@ -130,6 +130,26 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
   }
 }
 
+// All K steps at once: Yb[k][b,:] = Y[perms[k][b],:] and Xb[k][b,:] = Xn[perms[k][b],:]   (grid = (B, K, 2))
+__global__ void __launch_bounds__(256) gather_all_kernel(const float* __restrict__ Y, const float* __restrict__ Xn,
+                                                         const int64_t* __restrict__ perms, int B, int dt, int d,
+                                                         float* __restrict__ Yb0, float* __restrict__ Xb0,
+                                                         size_t step_stride) {
+  pdl_enter();
+  const int b = blockIdx.x, k = blockIdx.y;
+  const bool isx = blockIdx.z == 1;
+  const int cols = isx ? d : dt;
+  const size_t row = (size_t)perms[(size_t)k * B + b];
+  const float* src = (isx ? Xn : Y) + row * cols;
+  float* dst = (isx ? Xb0 : Yb0) + (size_t)k * step_stride + (size_t)b * cols;
+  if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    for (int j = threadIdx.x; j < (cols >> 2); j += blockDim.x)
+      reinterpret_cast<float4*>(dst)[j] = reinterpret_cast<const float4*>(src)[j];
+  } else {
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[j] = src[j];
+  }
+}
+
 // dst[idx[b],:] += coef * sum_slabs(part)[b,:]   with coef = -(*lr) * (scale ? *scale : 1)
 // (indices inside one step are unique -- randperm -- so no atomics are needed)
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ part, int splits, size_t stride,
