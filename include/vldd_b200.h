@@ -123,6 +123,14 @@ int vldd_unrolled_match(const float* theta0, const float* theta_tgt, const float
                         float* out5, float* ce, float* dY, float* dU, float* theta_K, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* ---- measurement hook ------------------------------------------------------------------------------ */
+/* One launch of the weight-streaming GEMM the engine issues for networks.py:642 (`fc`: f = h W2^T) inside the unroll:
+ * partial[z][M*N] (z < *splits_out) are split-K slabs of A[M,K] @ W[N,K]^T computed by the tcgen05 3xTF32 kernel.
+ * Used by bench.py to time the dominant kernel in isolation for the roofline figure. */
+size_t vldd_bench_skinny_gemm_workspace_bytes(int M, int N, int K);
+int vldd_bench_skinny_gemm(const float* A, const float* W, int M, int N, int K, float* partial, size_t partial_bytes,
+                           int* splits_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

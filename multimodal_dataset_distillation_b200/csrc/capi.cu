@@ -241,6 +241,13 @@ int vldd_contrastive_step(const float* theta, const float* Y, const float* U, co
                           S(stream));
 }
 
+size_t vldd_bench_skinny_gemm_workspace_bytes(int M, int N, int K) { return skinny_gemm_workspace_bytes(M, N, K); }
+
+int vldd_bench_skinny_gemm(const float* A, const float* W, int M, int N, int K, float* partial, size_t partial_bytes,
+                           int* splits_out, void* stream) {
+  return skinny_gemm_partial(A, W, M, N, K, partial, partial_bytes, splits_out, S(stream));
+}
+
 size_t vldd_unrolled_match_workspace_bytes(int N, int B, int K, int dt, int d) {
   return unrolled_match_workspace_bytes(N, B, K, dt, d);
 }

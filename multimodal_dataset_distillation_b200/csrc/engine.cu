@@ -620,4 +620,19 @@ int proj_head_forward(const float* theta, const float* Y, const float* mask, int
   return check_launch("proj_head_forward");
 }
 
+// Measurement hook (bench.py roofline): exactly the weight-streaming GEMM launch the engine issues for f = h W2^T
+// (split-K partial slabs, 3xTF32 tcgen05 kernel), on caller-provided operands.
+size_t skinny_gemm_workspace_bytes(int M, int N, int K) { return (size_t)max_splits(M, N, K) * M * N * sizeof(float); }
+
+int skinny_gemm_partial(const float* A, const float* W, int M, int N, int K, float* partial, size_t partial_bytes,
+                        int* splits, cudaStream_t st) {
+  VLDD_REQUIRE(A && W && partial && splits && M > 0 && N > 0 && K > 0, "skinny_gemm_partial: bad arguments");
+  if (partial_bytes < skinny_gemm_workspace_bytes(M, N, K)) {
+    set_error("skinny_gemm_partial: workspace too small");
+    return VLDD_ERR_WORKSPACE;
+  }
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(A, K, W, K, M, N, K), partial, splits, st)));
+  return check_launch("skinny_gemm_partial");
+}
+
 }  // namespace vldd

@@ -19,4 +19,8 @@ size_t proj_head_workspace_bytes(int rows, int dt, int d);
 int proj_head_forward(const float* theta, const float* Y, const float* mask, int rows, int dt, int d, float* z,
                       float* zn, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+size_t skinny_gemm_workspace_bytes(int M, int N, int K);
+int skinny_gemm_partial(const float* A, const float* W, int M, int N, int K, float* partial, size_t partial_bytes,
+                        int* splits, cudaStream_t st);
+
 }  // namespace vldd

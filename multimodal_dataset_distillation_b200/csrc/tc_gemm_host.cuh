@@ -123,11 +123,12 @@ inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st) {
   return VLDD_OK;
 }
 
-// number of K splits so that tiles x splits ~ one wave of 148 SMs, each split keeping >= 2 k-blocks
+// number of K splits so that tiles x splits fills ONE wave of the 148 SMs without spilling into a second one (the
+// kernel runs one CTA per SM: 18 tiles x 9 splits = 162 CTAs would cost two waves), each split keeping >= 2 k-blocks
 inline int pick_splits(int M, int N, int Ktot) {
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int nkb = ceil_div(Ktot, BK);
-  int s = (kNumSMs + tiles - 1) / tiles;
+  int s = kNumSMs / tiles;
   const int max_s = nkb / 2 > 0 ? nkb / 2 : 1;
   if (s > max_s) s = max_s;
   return s < 1 ? 1 : s;

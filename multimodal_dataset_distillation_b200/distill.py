@@ -223,6 +223,46 @@ class DistillEngine:
         return loss
 
 
+class SegmentPrefetcher:
+    """Host-resident expert trajectories (the reference keeps them as CPU tensors and uploads theta_start / theta_target
+    every iteration, distill.py:466-476) streamed to the device one iteration ahead.
+
+    Two device slots; the copy of the NEXT segment runs on its own stream from pinned memory while the engine works
+    on the current one, so the 2 x 28 MB upload is hidden behind compute instead of sitting in front of it.
+    """
+
+    def __init__(self, experts_host: torch.Tensor, device="cuda"):
+        self.host = experts_host if experts_host.is_pinned() else experts_host.pin_memory()
+        self.dev = torch.device(device)
+        P = self.host.shape[-1]
+        self.slots = [dict(th0=torch.empty(P, device=self.dev), tgt=torch.empty(P, device=self.dev),
+                           ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.n = 0
+        self.pending = None
+        for sl in self.slots:
+            sl["free"].record(torch.cuda.current_stream(self.dev))
+
+    def prefetch(self, expert: int, start_epoch: int, expert_epochs: int):
+        sl = self.slots[self.n % 2]
+        self.n += 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(sl["free"])                  # the engine has staged the slot's previous content
+            sl["th0"].copy_(self.host[expert, start_epoch], non_blocking=True)
+            sl["tgt"].copy_(self.host[expert, start_epoch + expert_epochs], non_blocking=True)
+            sl["ready"].record(self.copy_stream)
+        self.pending = sl
+
+    def get(self):
+        """Buffers of the prefetched segment, valid on the current stream; call release() after the engine call."""
+        sl = self.pending
+        torch.cuda.current_stream(self.dev).wait_event(sl["ready"])
+        return sl
+
+    def release(self, sl):
+        sl["free"].record(torch.cuda.current_stream(self.dev))
+
+
 def synthetic_experts(n_experts: int, n_snapshots: int, dt: int, d: int, seed: int = 0, step: float = 0.01) -> torch.Tensor:
     """Random-walk expert trajectories of ProjectionHead shape (no checkpoints are available offline)."""
     g = torch.Generator().manual_seed(seed)
