@@ -147,7 +147,7 @@ int vldd_topk_fill(const float* scores, float* out, int rows, int cols, int k, f
 size_t vldd_sim_rank_workspace_bytes(int n_img, int n_txt, int dim) {
   (void)dim;
   if (n_img <= 0 || n_txt <= 0) return 256;
-  return 2 * (size_t)n_img * (size_t)n_txt * sizeof(float) + 256;
+  return (size_t)n_img * (size_t)n_txt * sizeof(float) + 256;     // one [I,T] score matrix; the transpose is never built
 }
 
 int vldd_sim_rank(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale,
@@ -161,12 +161,11 @@ int vldd_sim_rank(const float* img, const float* txt, int n_img, int n_txt, int 
   }
   if (n_img == 0 || n_txt == 0) return VLDD_OK;
   float* s_i2t = reinterpret_cast<float*>(workspace);
-  float* s_t2i = s_i2t + (size_t)n_img * n_txt;
-  int rc = sim_scores(img, txt, n_img, n_txt, dim, scale, s_i2t, s_t2i, S(stream));
+  int rc = sim_scores(img, txt, n_img, n_txt, dim, scale, s_i2t, nullptr, S(stream));
   if (rc) return rc;
-  rc = ranks_rows(s_i2t, n_txt, n_img, n_txt, img2txt_ptr, img2txt_idx, ranks_i2t, S(stream));
+  rc = ranks_rows(s_i2t, n_txt, n_img, n_txt, img2txt_ptr, img2txt_idx, ranks_i2t, S(stream));   // image -> text: rows
   if (rc) return rc;
-  return ranks_rows(s_t2i, n_img, n_txt, n_img, nullptr, txt2img, ranks_t2i, S(stream));
+  return ranks_cols(s_i2t, n_txt, n_img, n_txt, txt2img, ranks_t2i, S(stream));                   // text -> image: columns
 }
 
 int vldd_itm_eval_host(const float* scores_i2t_host, const float* scores_t2i_host, int n_img, int n_txt,

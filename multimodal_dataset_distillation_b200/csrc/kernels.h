@@ -18,6 +18,7 @@ int momentum_sgd(float* p, const float* g, float* buf, float lr, float momentum,
 // retrieval.cu
 int ranks_rows(const float* S, int64_t ld, int nrows, int ncols, const int32_t* gt_ptr, const int32_t* gt_idx,
                int32_t* ranks, cudaStream_t st);
+int ranks_cols(const float* S, int64_t ld, int nrows, int ncols, const int32_t* gt_row, int32_t* ranks, cudaStream_t st);
 int best_gt_rows(const float* S, int64_t ld, int nrows, int ncols, int col_offset, const int32_t* gt_ptr,
                  const int32_t* gt_idx, float* best_score, int32_t* best_idx, cudaStream_t st);
 int count_rows(const float* S, int64_t ld, int nrows, int ncols, int col_offset, const float* thr_score,

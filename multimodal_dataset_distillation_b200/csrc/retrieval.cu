@@ -89,6 +89,59 @@ int ranks_rows(const float* S, int64_t ld, int nrows, int ncols, const int32_t* 
   return check_launch("ranks_rows");
 }
 
+// Column-wise ranking on the SAME matrix: rank of row gt_row[c] inside column c (text->image retrieval on S_i2t without
+// materialising the transpose).  Block = 32 columns x 8 row lanes; each warp reads 128 contiguous bytes of a row.
+// counts must be zero on entry; integer atomics => order-independent, bit-exact.
+constexpr int kColRowsPerBlock = 256;
+__global__ void __launch_bounds__(256) ranks_cols_kernel(const float* __restrict__ S, int64_t ld, int nrows, int ncols,
+                                                         const int32_t* __restrict__ gt_row, int32_t* __restrict__ counts) {
+  pdl_enter();
+  __shared__ int red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int r0 = blockIdx.y * kColRowsPerBlock, r1 = min(nrows, r0 + kColRowsPerBlock);
+  int cnt = 0;
+  if (c < ncols) {
+    const int g = gt_row[c];
+    if (g >= 0 && g < nrows) {
+      const float thr = S[(size_t)g * ld + c];
+      int r = r0 + w;
+      for (; r + 24 < r1; r += 32) {            // 4 independent row loads in flight per thread
+        const float v0 = S[(size_t)r * ld + c], v1 = S[(size_t)(r + 8) * ld + c], v2 = S[(size_t)(r + 16) * ld + c],
+                    v3 = S[(size_t)(r + 24) * ld + c];
+        cnt += (v0 > thr) + (v0 == thr && r < g);
+        cnt += (v1 > thr) + (v1 == thr && r + 8 < g);
+        cnt += (v2 > thr) + (v2 == thr && r + 16 < g);
+        cnt += (v3 > thr) + (v3 == thr && r + 24 < g);
+      }
+      for (; r < r1; r += 8) {
+        const float v = S[(size_t)r * ld + c];
+        cnt += (v > thr) + (v == thr && r < g);
+      }
+    } else if (blockIdx.y == 0 && w == 0) {
+      cnt = nrows;                                // no valid ground truth: never retrieved
+    }
+  }
+  red[w][lane] = cnt;
+  __syncthreads();
+  if (w == 0 && c < ncols) {
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    if (t) atomicAdd(counts + c, t);
+  }
+}
+
+int ranks_cols(const float* S, int64_t ld, int nrows, int ncols, const int32_t* gt_row, int32_t* ranks, cudaStream_t st) {
+  if (ncols <= 0) return VLDD_OK;
+  cudaError_t e = cudaMemsetAsync(ranks, 0, (size_t)ncols * sizeof(int32_t), st);
+  if (e != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); return VLDD_ERR_CUDA; }
+  if (nrows <= 0) return VLDD_OK;
+  dim3 grid(ceil_div(ncols, 32), ceil_div(nrows, kColRowsPerBlock));
+  launch_k(ranks_cols_kernel, grid, 256, 0, st, S, ld, nrows, ncols, gt_row, ranks);
+  return check_launch("ranks_cols");
+}
+
 // ---- caption-sharded form (multi-GPU): the score matrix holds columns [col_offset, col_offset + ncols) of the full
 // one.  Step 1: best ground-truth candidate per row among the LOCAL columns; step 2 (after the candidates of all
 // shards are merged on the host side of the collective): count local columns that beat the global threshold.

@@ -129,7 +129,10 @@ def test_sim_rank_flickr_shape():
     # GPU's own score matrix (bit-exact) and against numpy scores up to near-tie flips
     s1, s2 = ops.sim_scores(dev(img), dev(txt), 14.285714)
     assert np.array_equal(r1.cpu().numpy(), RR.ranks_vectorised(s1.cpu().numpy(), ptr, idx))
-    assert np.array_equal(r2.cpu().numpy(), RR.ranks_vectorised(s2.cpu().numpy(), np.arange(5001, dtype=np.int32), t2i))
+    # text->image ranks are taken column-wise from the SAME matrix (no transpose is built)
+    assert np.array_equal(r2.cpu().numpy(), RR.ranks_vectorised(np.ascontiguousarray(s1.cpu().numpy().T),
+                                                                np.arange(5001, dtype=np.int32), t2i))
+    np.testing.assert_allclose(s2.cpu().numpy(), s1.cpu().numpy().T, rtol=1e-5, atol=1e-5)
     S = (np.float32(14.285714) * img) @ txt.T
     np.testing.assert_allclose(s1.cpu().numpy(), S, rtol=1e-4, atol=1e-4)
     ref1 = RR.ranks_vectorised(S, ptr, idx)
@@ -168,3 +171,22 @@ def test_caption_sharded_ranks_match_single_gpu(world):
     assert torch.equal(counts, ref_i)
     got_t = torch.cat([be.ranks_t2i(s2, dev(t2i[lo:hi].copy())) for lo, hi, s1, s2 in shards])
     assert torch.equal(got_t, ref_t)
+
+
+@pytest.mark.parametrize("I,T,D", [(1, 1, 4), (3, 7, 8), (37, 300, 20), (300, 37, 12), (513, 1030, 64)])
+def test_sim_rank_random_maps_and_ties(I, T, D):
+    """Arbitrary (inconsistent) ground-truth maps, heavy ties, shapes that are not multiples of any tile."""
+    from multimodal_dataset_distillation_b200 import ops
+    rng = np.random.default_rng(I * 7 + T)
+    img = (rng.integers(-2, 3, size=(I, D)) / 2).astype(np.float32)
+    txt = (rng.integers(-2, 3, size=(T, D)) / 2).astype(np.float32)
+    img2txt = {i: sorted(rng.choice(T, size=rng.integers(1, min(T, 4) + 1), replace=False).tolist()) for i in range(I)}
+    txt2img = {t: int(rng.integers(0, I)) for t in range(T)}
+    t2i, ptr, idx = ops.maps_to_arrays(txt2img, img2txt, I, T)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    r1, r2 = ops.sim_rank(dev(img), dev(txt), dev(t2i), dev(ptr), dev(idx), 2.0)
+    s1, _ = ops.sim_scores(dev(img), dev(txt), 2.0, want_t2i=False)
+    S = s1.cpu().numpy()
+    assert np.array_equal(S, (2.0 * img @ txt.T).astype(np.float32))            # small half-integers: exact in any order
+    assert np.array_equal(r1.cpu().numpy(), RR.ranks_i2t(S, img2txt))
+    assert np.array_equal(r2.cpu().numpy(), RR.ranks_t2i(np.ascontiguousarray(S.T), txt2img))
