@@ -101,7 +101,8 @@ def bench_args():
     from multimodal_dataset_distillation_b200 import distill
     return distill.parse_args(["--syn_steps", str(CFG["K"]), "--expert_epochs", "1", "--max_start_epoch", "2",
                                "--num_queries", str(CFG["N"]), "--mini_batch_size", str(CFG["B"]), "--lr_img", "1000",
-                               "--lr_txt", "1000", "--lr_lr", "0.01", "--logit_scale_mode", "upstream"])
+                               "--lr_txt", "1000", "--lr_lr", "0.01", "--logit_scale_mode", "upstream",
+                               "--student_dropout", "0.1"])
 
 
 def kernel_launches_per_iteration(K):
@@ -221,7 +222,8 @@ def run_ours(opt):
     def e2e_step(i):
         sl = pre.get()
         perms = perms_host[i % 8].to(dev, non_blocking=True)
-        loss = distill.UnrolledMatch.apply(eng.Y, eng.U, eng.syn_lr_txt, eng.fixed_scale, sl["th0"], sl["tgt"], perms, None, eng.ws)
+        masks = ops.fill_dropout_masks(eng.ws, 0.1, eng.gen_dev)
+        loss = distill.UnrolledMatch.apply(eng.Y, eng.U, eng.syn_lr_txt, eng.fixed_scale, sl["th0"], sl["tgt"], perms, masks, eng.ws)
         pre.release(sl)
         pre.prefetch(*seg(i + 1), 1)                                     # next segment's H2D overlaps this iteration
         eng.outer_step(loss)
@@ -256,8 +258,8 @@ def run_ours(opt):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "configs[2]: full distill inner loop, Flickr30K-shaped (N=B=100 pairs, syn_steps=8, "
-                                   "expert_epochs=1, max_start_epoch=2, text_projection 768->2304, image side = frozen "
-                                   "2304-d embeddings)",
+                                   "expert_epochs=1, max_start_epoch=2, text_projection 768->2304 in train mode (fresh "
+                                   "dropout-0.1 masks every iteration), image side = frozen 2304-d embeddings)",
                        "unit_of_work": "one expert segment: 8-step unroll + matching loss + reverse sweep + outer SGD; "
                                        "one segment per rank per step, grads all-reduced (NCCL) when n_gpus > 1",
                        "l2_policy": "inputs larger than L2: steps rotate over 4 experts x 2 start epochs (340 MB of "
@@ -342,7 +344,7 @@ def bench_retrieval(dev, opt):
 def cpu_baseline_distill(max_seconds=20.0, max_iters=8):
     """Oracle (torch CPU restatement of distill.py:509-606, autograd double backward) on the host cores."""
     from oracle import distill_ref as R
-    pr = R.make_problem(N=CFG["N"], B=CFG["B"], K=CFG["K"], dt=CFG["dt"], d=CFG["d"], seed=0)
+    pr = R.make_problem(N=CFG["N"], B=CFG["B"], K=CFG["K"], dt=CFG["dt"], d=CFG["d"], seed=0, dropout=True)
     R.unrolled_match_autograd(**pr)                       # warm-up (thread pools, allocator)
     n, t0 = 0, time.perf_counter()
     while n < max_iters and (time.perf_counter() - t0) < max_seconds:
@@ -359,7 +361,7 @@ def run_reference(opt):
     if rank != 0:
         return None
     from oracle import distill_ref as R
-    pr = R.make_problem(N=CFG["N"], B=CFG["B"], K=CFG["K"], dt=CFG["dt"], d=CFG["d"], seed=0)
+    pr = R.make_problem(N=CFG["N"], B=CFG["B"], K=CFG["K"], dt=CFG["dt"], d=CFG["d"], seed=0, dropout=True)
     steps = min(opt.steps, 10)
     warm = min(opt.warmup, 2)
     for _ in range(max(warm, 1)):

@@ -97,6 +97,9 @@ def build_parser() -> argparse.ArgumentParser:
     A("--embed_path", type=str, default=None, help=".npz with image_embed [M,d] and text_embed [M,dt] (frozen encoders)")
     A("--synthetic", action="store_true", help="run on synthetic Flickr-shaped embeddings and experts")
     A("--seed", type=int, default=0)
+    A("--student_dropout", type=float, default=0.1,
+      help="dropout of the student text_projection during the unroll (networks.py:629,636; students are in train mode, "
+           "distill.py:446-447); 0 gives the deterministic parity mode")
     return p
 
 
@@ -173,6 +176,7 @@ class DistillEngine:
         self.first = True
         self.pg = process_group
         self.gen = torch.Generator().manual_seed(int(getattr(args, "seed", 0)))
+        self.gen_dev = torch.Generator(device=self.dev).manual_seed(int(getattr(args, "seed", 0)) + 1)
         self.expert_idx = 0
         self.fixed_scale = torch.tensor(ops.LOGIT_SCALE_UPSTREAM, device=self.dev)
 
@@ -186,6 +190,9 @@ class DistillEngine:
         perms = perms.to(self.dev)
         fork = getattr(a, "logit_scale_mode", "fork") == "fork"
         scale = self.syn_lr_img if fork else self.fixed_scale
+        p_drop = float(getattr(a, "student_dropout", 0.0))
+        if masks is None and p_drop > 0.0 and self.K > 0:
+            masks = ops.fill_dropout_masks(self.ws, p_drop, self.gen_dev)      # fresh masks per call, as nn.Dropout does
         return UnrolledMatch.apply(self.Y, self.U, self.syn_lr_txt, scale, theta0, theta_tgt, perms, masks, self.ws)
 
     def sample_segment(self):

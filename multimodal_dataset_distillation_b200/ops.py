@@ -286,6 +286,19 @@ class UnrollWorkspace:
         self.scale = torch.empty(1, dtype=torch.float32, device=device)
 
 
+def fill_dropout_masks(workspace: "UnrollWorkspace", p: float, generator: torch.Generator | None = None) -> torch.Tensor:
+    """Fresh pre-scaled dropout masks (0 or 1/(1-p)) for the K student steps, drawn in place in the workspace.
+
+    The reference's students run in train mode (distill.py:446-447), so every forward of text_projection draws a new
+    nn.Dropout(0.1) mask (networks.py:636,643); the engine replays the SAME masks in its reverse sweep.
+    """
+    N, B, K, dt, d = workspace.key
+    if workspace.masks is None:
+        workspace.masks = torch.empty(max(K, 1), B, d, dtype=torch.float32, device=workspace.buf.device)
+    workspace.masks.bernoulli_(1.0 - p, generator=generator).mul_(1.0 / (1.0 - p))
+    return workspace.masks
+
+
 def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, workspace: UnrollWorkspace | None = None,
                    want_theta_K: bool = False):
     """distill.py:509-606 for one expert segment.  Returns dict(out5=[num,den,loss,dlr,dscale], ce, dY, dU[, theta_K])."""
@@ -314,7 +327,8 @@ def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, worksp
             raise ValueError(f"masks must be [{K},{B},{d}]")
         if ws.masks is None:
             ws.masks = torch.empty(K, B, d, dtype=torch.float32, device=dev)
-        ws.masks.copy_(masks)
+        if masks.data_ptr() != ws.masks.data_ptr():
+            ws.masks.copy_(masks)
         m_ptr = ws.masks
     if want_theta_K and ws.theta_K is None:
         ws.theta_K = torch.empty_like(theta0)

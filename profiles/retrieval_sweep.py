@@ -1,0 +1,44 @@
+"""Retrieval throughput sweep (BASELINE.json configs[3]/[4] shapes) on one GPU: python profiles/retrieval_sweep.py"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from multimodal_dataset_distillation_b200 import ops
+
+def run(I, C, D, reps=5):
+    T = I * C
+    g = torch.Generator(device="cuda").manual_seed(0)
+    img = torch.randn(I, D, device="cuda", generator=g)
+    txt = torch.randn(T, D, device="cuda", generator=g) + 0.15 * img.repeat_interleave(C, 0)
+    img = img / img.norm(dim=1, keepdim=True)
+    txt = txt / txt.norm(dim=1, keepdim=True)
+    t2i = (torch.arange(T, device="cuda") // C).int()
+    ptr = (torch.arange(I + 1, device="cuda") * C).int()
+    idx = torch.arange(T, device="cuda").int()
+    ws = torch.empty(ops.lib().vldd_sim_rank_workspace_bytes(I, T, D), dtype=torch.uint8, device="cuda")
+    r1, r2 = ops.sim_rank(img, txt, t2i, ptr, idx, 14.285714, ws)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r1, r2 = ops.sim_rank(img, txt, t2i, ptr, idx, 14.285714, ws)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    # spot check a few rows against numpy on the same embeddings
+    rows = [0, I // 2, I - 1]
+    S = (14.285714 * img[rows] @ txt.T).cpu().numpy()
+    ok = True
+    for k, i in enumerate(rows):
+        best = max(range(C * i, C * i + C), key=lambda c: (S[k, c], -c))
+        ref = int((S[k] > S[k, best]).sum())
+        ok &= abs(int(r1[i]) - ref) <= 2          # fp32 summation-order near-ties only
+    rec = [(r1 < k).float().mean().item() * 100 for k in (1, 5, 10)]
+    print(f"I={I:6d} T={T:7d} D={D}: {ms:9.3f} ms  {I * T / ms / 1e6:9.2f} G pairs/s  GEMM {2 * I * T * D / ms / 1e9:7.1f} TFLOP/s(fp32-equiv) "
+          f"workspace {ws.numel() / 2**30:.2f} GiB  i2t R@1/5/10 = {rec[0]:.1f}/{rec[1]:.1f}/{rec[2]:.1f}  spot-check {'ok' if ok else 'MISMATCH'}")
+
+if __name__ == "__main__":
+    for I, D in ((1000, 768), (1000, 2304), (5000, 768), (10000, 768), (25000, 768)):
+        run(I, 5, D)

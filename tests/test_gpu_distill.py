@@ -158,7 +158,7 @@ def test_autograd_function_and_outer_step():
     from multimodal_dataset_distillation_b200 import distill
     args = distill.parse_args(["--syn_steps", "2", "--expert_epochs", "1", "--max_start_epoch", "2", "--num_queries", "16",
                                "--mini_batch_size", "16", "--lr_img", "10", "--lr_txt", "10", "--lr_lr", "0.01",
-                               "--logit_scale_mode", "fork"])
+                               "--logit_scale_mode", "fork", "--student_dropout", "0"])
     dt, d = 24, 40
     experts = distill.synthetic_experts(1, 3, dt, d, seed=1, step=0.05).cuda()
     g = torch.Generator().manual_seed(0)
@@ -179,3 +179,44 @@ def test_autograd_function_and_outer_step():
     torch.testing.assert_close(eng.Y.detach(), Y0 - 10 * eng.Y.grad, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(eng.U.detach(), U0 - 10 * eng.U.grad, rtol=1e-5, atol=1e-6)
     assert abs(float(eng.syn_lr_txt) - (0.1 - 0.01 * float(ref.dlr))) < 1e-6
+
+
+def test_train_mode_dropout_masks_are_fresh_scaled_and_replayed():
+    """Students run in train mode (distill.py:446-447): a new dropout-0.1 mask per call, same mask in the reverse sweep."""
+    from multimodal_dataset_distillation_b200 import distill, ops
+    args = distill.parse_args(["--syn_steps", "2", "--expert_epochs", "1", "--max_start_epoch", "2", "--num_queries", "32",
+                               "--mini_batch_size", "32", "--logit_scale_mode", "upstream", "--student_dropout", "0.1"])
+    dt, d = 64, 128
+    experts = distill.synthetic_experts(1, 3, dt, d, seed=1, step=0.05).cuda()
+    g = torch.Generator().manual_seed(0)
+    img, txt = torch.randn(32, d, generator=g), torch.randn(32, dt, generator=g)
+    eng = distill.DistillEngine(img, txt, experts, args)
+    perms = torch.stack([torch.randperm(32, generator=g) for _ in range(2)])
+    l1 = eng.segment_loss(0, 0, perms)
+    m1 = eng.ws.masks.clone()
+    vals = torch.unique(m1).cpu().tolist()
+    assert len(vals) == 2 and vals[0] == 0.0 and abs(vals[1] - 1 / 0.9) < 1e-6
+    assert 0.05 < float((m1 == 0).float().mean()) < 0.15
+    l2 = eng.segment_loss(0, 0, perms)
+    assert not torch.equal(m1, eng.ws.masks) and float(l1) != float(l2)             # fresh draw per call
+    # the oracle with the SAME masks reproduces loss and gradients (mask replayed in the reverse sweep)
+    m2 = eng.ws.masks.clone()
+    eng.outer_step(l2)
+    ref = R.unrolled_match_autograd(experts[0, 0].double().cpu(), experts[0, 1].double().cpu(), txt.double(), img.double(),
+                                    torch.tensor(0.1, dtype=torch.float64), torch.tensor(ops.LOGIT_SCALE_UPSTREAM, dtype=torch.float64),
+                                    perms, m2.double().cpu(), dt, d)
+    assert abs(float(l2) - float(ref.loss)) <= RTOL * float(ref.loss)
+    assert rel_err(eng.Y.grad, ref.dY) < RTOL and rel_err(eng.U.grad, ref.dU) < RTOL
+
+
+def test_segment_prefetcher_streams_host_experts():
+    from multimodal_dataset_distillation_b200 import distill
+    host = torch.randn(3, 4, 1000)
+    pre = distill.SegmentPrefetcher(host, "cuda")
+    pre.prefetch(0, 1, 2)
+    for i in range(6):
+        sl = pre.get()
+        e, s = i % 3, (i + 1) % 2
+        assert torch.equal(sl["th0"].cpu(), host[e, s]) and torch.equal(sl["tgt"].cpu(), host[e, s + 2])
+        pre.release(sl)
+        pre.prefetch((i + 1) % 3, (i + 2) % 2, 2)
