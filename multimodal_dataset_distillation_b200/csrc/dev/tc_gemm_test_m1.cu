@@ -1,5 +1,6 @@
 // Developer harness (not part of the library): tcgen05 GEMM vs the fp32 CUDA-core GEMM on random data.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I.. -I../../../include dev/tc_gemm_test.cu -o tc_gemm_test
+#define VLDD_TC_SPLIT_MODE 1
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>

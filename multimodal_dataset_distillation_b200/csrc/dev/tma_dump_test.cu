@@ -7,6 +7,7 @@
 namespace vldd {
 static char g_err[512];
 void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
+bool pdl_enabled() { return false; }
 int check_launch(const char*) { return 0; }
 }
 using namespace vldd;

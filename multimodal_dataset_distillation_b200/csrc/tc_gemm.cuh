@@ -6,9 +6,11 @@
 // Warp roles (192 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor loads of the fp32 A/B k-blocks (128 x 32 floats each, SWIZZLE_128B)
 //   warp 1      TMEM allocator + MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8, accumulator in TMEM
-//   warps 2..5  operand splitter, then epilogue.  tf32 keeps 10 mantissa bits, so every fp32 operand x is split in
-//               shared memory into hi = rna_tf32(x) (written in place) and lo = x - hi (second buffer, same swizzled
-//               offsets); the MMA warp issues hi*hi + lo*hi + hi*lo -> error ~2^-21 per product instead of 2^-11.
+//   warps 2..5  operand splitter, then epilogue.  tf32 keeps 10 mantissa bits and the tensor core TRUNCATES fp32 operands,
+//               so the landed fp32 tile is the hi operand as is and only lo = x - trunc_tf32(x) is produced (second
+//               buffer at the same swizzled offsets); the MMA warp issues lo*hi + hi*lo + hi*hi -> error ~2^-21 per
+//               product instead of 2^-11.  For K-major A the hi / lo rows go straight into TENSOR MEMORY
+//               (tcgen05.st, one TMEM lane per row) and the MMAs take A from TMEM: no A traffic on the shared-memory port.
 //               Afterwards the same warps drain TMEM with tcgen05.ld (32 lanes x 32 columns per instruction) and run
 //               the epilogue (partial-slab store / alpha store / theta - lr*acc).
 // Operand layouts: K-major  = row-major [rows, K]  (2-D tensor map, box 32 x 128);
@@ -26,13 +28,18 @@ constexpr int BM = 128, BN = 128, BK = 32;          // BK floats = 128 bytes = o
 constexpr int UMMA_K = 8;                           // tf32
 constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB per operand per stage
 constexpr int NUM_THREADS = 192;
-constexpr int TMEM_COLS = 128;
 
-template <int kSplit, int kStagesT = 0>
+// Stage layout (kSplit == 3):  K-major A  -> [A | B | B_lo]            48 KB x 4 stages; A_hi / A_lo live in TMEM
+//                              MN-major A -> [A | B | A_lo | B_lo]     64 KB x 3 stages
+//               (kSplit == 1):              [A | B]                    32 KB x 6 stages
+template <int kSplit, bool A_TMEM, int kStagesT = 0>
 struct Cfg {
-  static constexpr int kStages = kStagesT > 0 ? kStagesT : (kSplit == 3 ? 3 : 6);
-  static constexpr int kStageBytes = (kSplit == 3 ? 4 : 2) * TILE_BYTES;
+  static constexpr int kTiles = kSplit == 3 ? (A_TMEM ? 3 : 4) : 2;
+  static constexpr int kStages = kStagesT > 0 ? kStagesT : (kSplit == 3 ? (A_TMEM ? 4 : 3) : 6);
+  static constexpr int kStageBytes = kTiles * TILE_BYTES;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = (kSplit == 3 && A_TMEM) ? 512 : 128;   // accumulator 128 + kStages x (32 hi + 32 lo)
+  static constexpr uint32_t kTmemA = 128;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -98,6 +105,33 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = row, 8 consecutive 32-bit columns = the K=8 tf32 values of that row)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// fp32 -> the tf32 value the tensor core actually uses: kind::tf32 TRUNCATES the 13 low mantissa bits (measured with
+// csrc/dev/tc_gemm_test: lo = x - trunc(x) gives 1e-6 relative error, lo = x - rna(x) gives 7e-4)
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -160,6 +194,14 @@ struct EpiAxpyTC {    // dst = src - (*lr) * acc   (src nullable = 0)
   __device__ __forceinline__ float apply(float acc, float srcv, float c) const { return srcv - c * acc; }
 };
 
+#ifdef VLDD_TC_TIMELINE
+__device__ long long g_timeline[148 * 8 * 16];   // [cta][slot]: globaltimer at phase boundaries (developer harness only)
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TL(slot) do { if (lane == 0) g_timeline[((blockIdx.z * gridDim.x + blockIdx.x) * 8 + warp) * 16 + (slot)] = gtime(); } while (0)
+#else
+#define TL(slot) do {} while (0)
+#endif
+
 #ifdef VLDD_TC_DEBUG
 __constant__ uint32_t g_dbg[4];   // {lbo, sbo, step, unused} overrides for MN-major operands (developer harness only)
 #endif
@@ -172,7 +214,8 @@ struct Maps {
 template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, Epi epi) {
-  using C = Cfg<kSplit, kStagesT>;
+  constexpr bool A_TMEM = A_KMAJOR && kSplit == 3;     // K-major A: hi/lo of the A tile are staged in tensor memory
+  using C = Cfg<kSplit, A_TMEM, kStagesT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -183,6 +226,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TL(0);
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb0 = (K0 + BK - 1) / BK, nkb1 = (K1 + BK - 1) / BK, nkb = nkb0 + nkb1;
   const int splits = gridDim.z;
@@ -202,14 +246,21 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above is independent of the preceding kernel: under programmatic dependent launch it overlaps that
   // kernel's tail; from here on global memory written by predecessors is read
+  TL(1);
   pdl_enter();
+  TL(2);
+
+  // byte offsets of the tiles inside a stage
+  constexpr int OFF_A = 0, OFF_B = TILE_BYTES;
+  constexpr int OFF_ALO = 2 * TILE_BYTES;                           // only when A is fed from shared memory
+  constexpr int OFF_BLO = (A_TMEM ? 2 : 3) * TILE_BYTES;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -222,12 +273,14 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         const int k = (seg1 ? kb - nkb0 : kb) * BK;
         const CUtensorMap* ma = seg1 ? &maps.a1 : &maps.a0;
         const CUtensorMap* mb = seg1 ? &maps.b1 : &maps.b0;
-        uint8_t* sa = smem + s * C::kStageBytes;
-        uint8_t* sb = sa + TILE_BYTES;
+        uint8_t* sa = smem + s * C::kStageBytes + OFF_A;
+        uint8_t* sb = smem + s * C::kStageBytes + OFF_B;
         mbar_expect_tx(&full[s], 2 * TILE_BYTES);
         if (A_KMAJOR) tma_load_2d(sa, ma, &full[s], k, m0); else tma_load_3d(sa, ma, &full[s], 0, k, m0 / 32);
         if (B_KMAJOR) tma_load_2d(sb, mb, &full[s], k, n0); else tma_load_3d(sb, mb, &full[s], 0, k, n0 / 32);
+        if (i == 0) TL(3);
       }
+      TL(4);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -248,18 +301,29 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
       for (int i = 0; i < my_kb; ++i) {
         const int s = i % C::kStages, round = i / C::kStages;
         mbar_wait(kSplit == 3 ? &ready[s] : &full[s], round & 1);
+        if (i == 0) TL(3);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * C::kStageBytes), sb = sa + TILE_BYTES;
-        const uint32_t sal = sb + TILE_BYTES, sbl = sal + TILE_BYTES;
+        const uint32_t st = smem_u32(smem + s * C::kStageBytes);
+        const uint32_t sa = st + OFF_A, sb = st + OFF_B, sal = st + OFF_ALO, sbl = st + OFF_BLO;
+        const uint32_t ta_hi = tmem_base + C::kTmemA + s * 64, ta_lo = ta_hi + 32;     // TMEM columns of this stage's A
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt), db = smem_desc(sb + k * b_step, b_lbo, b_sbo, b_lt);
+          const uint64_t db = smem_desc(sb + k * b_step, b_lbo, b_sbo, b_lt);
           if (kSplit == 3) {
-            const uint64_t dal = smem_desc(sal + k * a_step, a_lbo, a_sbo, a_lt), dbl = smem_desc(sbl + k * b_step, b_lbo, b_sbo, b_lt);
-            umma_tf32(tmem_base, dal, db, idesc, accumulate);
-            umma_tf32(tmem_base, da, dbl, idesc, 1);
-            umma_tf32(tmem_base, da, db, idesc, 1);
+            const uint64_t dbl = smem_desc(sbl + k * b_step, b_lbo, b_sbo, b_lt);
+            if (A_TMEM) {
+              umma_tf32_ts(tmem_base, ta_lo + k * UMMA_K, db, idesc, accumulate);
+              umma_tf32_ts(tmem_base, ta_hi + k * UMMA_K, dbl, idesc, 1);
+              umma_tf32_ts(tmem_base, ta_hi + k * UMMA_K, db, idesc, 1);
+            } else {
+              const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt);
+              const uint64_t dal = smem_desc(sal + k * a_step, a_lbo, a_sbo, a_lt);
+              umma_tf32(tmem_base, dal, db, idesc, accumulate);
+              umma_tf32(tmem_base, da, dbl, idesc, 1);
+              umma_tf32(tmem_base, da, db, idesc, 1);
+            }
           } else {
+            const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt);
             umma_tf32(tmem_base, da, db, idesc, accumulate);
           }
           accumulate = 1;
@@ -267,31 +331,58 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
+      TL(4);
     }
   } else {
     // ===== operand splitter (kSplit == 3), then epilogue =====
+    // The tensor core truncates fp32 operands to tf32, so the landed fp32 tile IS the hi operand; only lo = x - trunc(x)
+    // has to be produced (same swizzled offsets as the source tile, so no layout knowledge is needed for B / MN-major A).
     const int t = threadIdx.x - 64;   // 0..127
     if (kSplit == 3) {
+      const int row = (warp & 3) * 32 + lane;                       // TMEM lane owned by this thread
       for (int i = 0; i < my_kb; ++i) {
         const int s = i % C::kStages, round = i / C::kStages;
         mbar_wait(&full[s], round & 1);
-        float4* hi = reinterpret_cast<float4*>(smem + s * C::kStageBytes);           // A then B, 2 x 16 KB contiguous
-        float4* lo = reinterpret_cast<float4*>(smem + s * C::kStageBytes + 2 * TILE_BYTES);
+        if (i == 0) TL(3);
+        uint8_t* stg = smem + s * C::kStageBytes;
+        if (A_TMEM) {
+          // row `row` of the K-major A tile: 8 x 16-byte chunks, chunk c stored at c ^ (row & 7) (SWIZZLE_128B)
+          const uint8_t* arow = stg + OFF_A + row * 128;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+            hi[4 * c + 0] = __float_as_uint(v.x); lo[4 * c + 0] = __float_as_uint(tf32_lo(v.x));
+            hi[4 * c + 1] = __float_as_uint(v.y); lo[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
+            hi[4 * c + 2] = __float_as_uint(v.z); lo[4 * c + 2] = __float_as_uint(tf32_lo(v.z));
+            hi[4 * c + 3] = __float_as_uint(v.w); lo[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::kTmemA + s * 64;
+          tmem_st_32x32(ta, hi);
+          tmem_st_32x32(ta + 32, lo);
+          const float4* bsrc = reinterpret_cast<const float4*>(stg + OFF_B);
+          float4* blo = reinterpret_cast<float4*>(stg + OFF_BLO);
+#pragma unroll
+          for (int j = t; j < TILE_BYTES / 16; j += 128) {
+            const float4 v = bsrc[j];
+            blo[j] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          const float4* src = reinterpret_cast<const float4*>(stg + OFF_A);          // A then B, 2 x 16 KB contiguous
+          float4* lo = reinterpret_cast<float4*>(stg + OFF_ALO);                     // A_lo then B_lo
 #pragma unroll 4
-        for (int j = t; j < 2 * TILE_BYTES / 16; j += 128) {
-          const float4 v = hi[j];
-          float4 h, l;
-          uint32_t u;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
-          hi[j] = h;
-          lo[j] = l;
+          for (int j = t; j < 2 * TILE_BYTES / 16; j += 128) {
+            const float4 v = src[j];
+            lo[j] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+          }
         }
         fence_proxy_async();
         mbar_arrive(&ready[s]);
+        if (i == 0) TL(4);
       }
+      TL(5);
     }
     // epilogue: TMEM lane quadrant is fixed by warp index % 4.  Each thread drains 32 columns of its own row
     // (tcgen05.ld 32x32b.x32), the warp transposes the 32x32 block through shared memory (the pipeline stages are
@@ -326,6 +417,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     };
     load_src(0);
     mbar_wait(tmem_full, 0);
+    TL(6);
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
@@ -366,9 +458,11 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
       }
     }
   }
+  TL(7);
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+  TL(8);
 }
 
 }  // namespace tc

@@ -96,7 +96,7 @@ inline bool gemm_ok(const GemmOperands& g) {
 
 template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0>
 inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st) {
-  using C = Cfg<kSplit, kStagesT>;
+  using C = Cfg<kSplit, A_KMAJOR && kSplit == 3, kStagesT>;
   auto kern = tc_gemm_kernel<A_KMAJOR, B_KMAJOR, kSplit, Epi, kStagesT>;
   static bool configured = false;
   if (!configured) {
