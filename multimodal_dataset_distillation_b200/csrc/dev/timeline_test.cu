@@ -16,7 +16,7 @@ using namespace vldd;
 static float* dev_rand(size_t n) { std::vector<float> h(n); for (size_t i = 0; i < n; ++i) h[i] = (float)((i * 2654435761u) % 1000) / 1000.f - 0.5f; float* d; CK(cudaMalloc(&d, n * 4)); CK(cudaMemcpy(d, h.data(), n * 4, cudaMemcpyHostToDevice)); return d; }
 
 static void report(const char* name, int nctas) {
-  std::vector<long long> tl(148 * 8 * 16);
+  std::vector<long long> tl(148 * 10 * 16);
   CK(cudaMemcpyFromSymbol(tl.data(), tc::g_timeline, tl.size() * 8));
   long long t0 = (1ll << 62);
   for (int c = 0; c < nctas; ++c) if (tl[(c * 8 + 0) * 16 + 0] && tl[(c * 8 + 0) * 16 + 0] < t0) t0 = tl[(c * 8 + 0) * 16 + 0];
@@ -24,7 +24,7 @@ static void report(const char* name, int nctas) {
   for (int c : {0, 1, nctas / 2, nctas - 1}) {
     auto T = [&](int w, int s) { long long v = tl[(c * 8 + w) * 16 + s]; return v ? (long long)(v - t0) : -1ll; };
     printf("  cta %3d: %6lld %6lld | %6lld %6lld | %6lld %6lld | %6lld %6lld %6lld | %6lld %6lld | %6lld\n", c, T(0, 0), T(0, 2), T(0, 3), T(0, 4),
-           T(1, 3), T(1, 4), T(2, 3), T(2, 4), T(2, 5), T(2, 6), T(2, 7), T(0, 8));
+           T(1, 3), T(1, 4), T(2, 3), T(2, 4), T(2, 5), T(6, 6), T(6, 7), T(0, 8));
   }
 }
 
@@ -48,6 +48,6 @@ int main() {
     if (tc::launch<false, false, 3>(g2, 1, tc::EpiAxpyTC{src, dst, Nd, lr}, 0)) { printf("fail %s\n", g_err); return 1; }
     CK(cudaDeviceSynchronize());
   }
-  report("dW2 axpy (324 CTAs; timeline slots hold the first 148*... CTAs by blockIdx.x only)", 18);
+  report("dW2 axpy (324 tiles on 148 persistent CTAs; epilogue columns = first tile tmem_full / all tiles done)", 148);
   return 0;
 }

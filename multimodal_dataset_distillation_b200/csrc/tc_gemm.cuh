@@ -2,17 +2,18 @@
 //
 //   C[m,n] = sum_k opA(A)[m,k] * opB(B)[k,n]      (+ optional second K segment A1/B1, same shapes)
 //
-// One 128x128 output tile per CTA, K range split across blockIdx.z (partial slabs) or fused epilogue.
-// Warp roles (192 threads):
+// Persistent: CTA b handles work items b, b + grid, ... (one item = one 128x128 output tile x one K split); the
+// accumulator is double-buffered in TMEM so the epilogue of item i overlaps the main loop of item i+1.
+// Warp roles (320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor loads of the fp32 A/B k-blocks (128 x 32 floats each, SWIZZLE_128B)
 //   warp 1      TMEM allocator + MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8, accumulator in TMEM
-//   warps 2..5  operand splitter, then epilogue.  tf32 keeps 10 mantissa bits and the tensor core TRUNCATES fp32 operands,
+//   warps 6..9  epilogue: tcgen05.ld (32 lanes x 32 columns per instruction), 32x32 transpose through shared memory,
+//               fused epilogue (partial-slab store / alpha store / theta - lr*acc) with coalesced 128-byte rows
+//   warps 2..5  operand splitter.  tf32 keeps 10 mantissa bits and the tensor core TRUNCATES fp32 operands,
 //               so the landed fp32 tile is the hi operand as is and only lo = x - trunc_tf32(x) is produced (second
 //               buffer at the same swizzled offsets); the MMA warp issues lo*hi + hi*lo + hi*hi -> error ~2^-21 per
 //               product instead of 2^-11.  For K-major A the hi / lo rows go straight into TENSOR MEMORY
 //               (tcgen05.st, one TMEM lane per row) and the MMAs take A from TMEM: no A traffic on the shared-memory port.
-//               Afterwards the same warps drain TMEM with tcgen05.ld (32 lanes x 32 columns per instruction) and run
-//               the epilogue (partial-slab store / alpha store / theta - lr*acc).
 // Operand layouts: K-major  = row-major [rows, K]  (2-D tensor map, box 32 x 128);
 //                  MN-major = row-major [K, rows]  (3-D tensor map {32, K, rows/32}, box 32 x 32 x 4), used for
 //                  dH = dF W2 and the weight-gradient GEMMs dW = dF^T H, whose operands are contiguous along M/N.
@@ -27,7 +28,7 @@ namespace tc {
 constexpr int BM = 128, BN = 128, BK = 32;          // BK floats = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;                           // tf32
 constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB per operand per stage
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                    // producer, MMA, 4 splitter warps, 4 epilogue warps
 
 // Stage layout (kSplit == 3):  K-major A  -> [A | B | B_lo]            48 KB x 4 stages; A_hi / A_lo live in TMEM
 //                              MN-major A -> [A | B | A_lo | B_lo]     64 KB x 3 stages
@@ -37,9 +38,10 @@ struct Cfg {
   static constexpr int kTiles = kSplit == 3 ? (A_TMEM ? 3 : 4) : 2;
   static constexpr int kStages = kStagesT > 0 ? kStagesT : (kSplit == 3 ? (A_TMEM ? 4 : 3) : 6);
   static constexpr int kStageBytes = kTiles * TILE_BYTES;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = (kSplit == 3 && A_TMEM) ? 512 : 128;   // accumulator 128 + kStages x (32 hi + 32 lo)
-  static constexpr uint32_t kTmemA = 128;
+  static constexpr int kEpiBytes = 4 * 32 * 36 * 4;                       // private transpose patches of the epilogue warps
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = (kSplit == 3 && A_TMEM) ? 512 : 256;   // 2 accumulators x 128 + kStages x (32 hi + 32 lo)
+  static constexpr uint32_t kTmemA = 256;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -195,9 +197,9 @@ struct EpiAxpyTC {    // dst = src - (*lr) * acc   (src nullable = 0)
 };
 
 #ifdef VLDD_TC_TIMELINE
-__device__ long long g_timeline[148 * 8 * 16];   // [cta][slot]: globaltimer at phase boundaries (developer harness only)
+__device__ long long g_timeline[148 * 10 * 16];   // [cta][slot]: globaltimer at phase boundaries (developer harness only)
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define TL(slot) do { if (lane == 0) g_timeline[((blockIdx.z * gridDim.x + blockIdx.x) * 8 + warp) * 16 + (slot)] = gtime(); } while (0)
+#define TL(slot) do { if (lane == 0) g_timeline[(blockIdx.x * 10 + warp) * 16 + (slot)] = gtime(); } while (0)
 #else
 #define TL(slot) do {} while (0)
 #endif
@@ -211,28 +213,41 @@ struct Maps {
 };
 
 // ---- the kernel ----------------------------------------------------------------------------------------
+// Work item w (one per (m-tile, n-tile, k-split)) -> CTA blockIdx.x, blockIdx.x + gridDim.x, ... (persistent loop).
+struct WorkItem { int m0, n0, z, kb_begin, n_kb; };
+
 template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, Epi epi) {
+tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, int splits, Epi epi) {
   constexpr bool A_TMEM = A_KMAJOR && kSplit == 3;     // K-major A: hi/lo of the A tile are staged in tensor memory
   using C = Cfg<kSplit, A_TMEM, kStagesT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  float* epi_stage = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);        // 4 warps x 32 x 36 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kEpiBytes);
   uint64_t* full = bars;                       // TMA landed
   uint64_t* ready = bars + C::kStages;         // split done (kSplit == 3 only)
   uint64_t* empty = bars + 2 * C::kStages;     // MMAs reading the stage have completed
-  uint64_t* tmem_full = bars + 3 * C::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 1);
+  uint64_t* tmem_full = bars + 3 * C::kStages;       // [2] accumulator complete
+  uint64_t* tmem_empty = bars + 3 * C::kStages + 2;  // [2] accumulator drained by the epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TL(0);
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   const int nkb0 = (K0 + BK - 1) / BK, nkb1 = (K1 + BK - 1) / BK, nkb = nkb0 + nkb1;
-  const int splits = gridDim.z;
   const int per = (nkb + splits - 1) / splits;
-  const int kb_begin = blockIdx.z * per, kb_end = min(nkb, kb_begin + per);
-  const int my_kb = max(kb_end - kb_begin, 0);
+  const int total_work = tiles_m * tiles_n * splits;
+  auto decode = [&](int w) {
+    WorkItem it;
+    const int tile = w % (tiles_m * tiles_n);
+    it.z = w / (tiles_m * tiles_n);
+    it.n0 = (tile % tiles_n) * BN;            // consecutive CTAs take consecutive n-tiles of one m-tile (A reuse in L2)
+    it.m0 = (tile / tiles_n) * BM;
+    it.kb_begin = it.z * per;
+    it.n_kb = max(min(nkb, it.kb_begin + per) - it.kb_begin, 0);
+    return it;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a0);
@@ -243,7 +258,10 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
       mbar_init(&ready[s], 128);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -265,20 +283,24 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int i = 0; i < my_kb; ++i) {
-        const int s = i % C::kStages, round = i / C::kStages;
-        if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
-        const int kb = kb_begin + i;
-        const bool seg1 = kb >= nkb0;
-        const int k = (seg1 ? kb - nkb0 : kb) * BK;
-        const CUtensorMap* ma = seg1 ? &maps.a1 : &maps.a0;
-        const CUtensorMap* mb = seg1 ? &maps.b1 : &maps.b0;
-        uint8_t* sa = smem + s * C::kStageBytes + OFF_A;
-        uint8_t* sb = smem + s * C::kStageBytes + OFF_B;
-        mbar_expect_tx(&full[s], 2 * TILE_BYTES);
-        if (A_KMAJOR) tma_load_2d(sa, ma, &full[s], k, m0); else tma_load_3d(sa, ma, &full[s], 0, k, m0 / 32);
-        if (B_KMAJOR) tma_load_2d(sb, mb, &full[s], k, n0); else tma_load_3d(sb, mb, &full[s], 0, k, n0 / 32);
-        if (i == 0) TL(3);
+      int g = 0;                                                    // k-blocks issued so far (across work items)
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const WorkItem it = decode(w);
+        for (int i = 0; i < it.n_kb; ++i, ++g) {
+          const int s = g % C::kStages, round = g / C::kStages;
+          if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+          const int kb = it.kb_begin + i;
+          const bool seg1 = kb >= nkb0;
+          const int k = (seg1 ? kb - nkb0 : kb) * BK;
+          const CUtensorMap* ma = seg1 ? &maps.a1 : &maps.a0;
+          const CUtensorMap* mb = seg1 ? &maps.b1 : &maps.b0;
+          uint8_t* sa = smem + s * C::kStageBytes + OFF_A;
+          uint8_t* sb = smem + s * C::kStageBytes + OFF_B;
+          mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+          if (A_KMAJOR) tma_load_2d(sa, ma, &full[s], k, it.m0); else tma_load_3d(sa, ma, &full[s], 0, k, it.m0 / 32);
+          if (B_KMAJOR) tma_load_2d(sb, mb, &full[s], k, it.n0); else tma_load_3d(sb, mb, &full[s], 0, k, it.n0 / 32);
+          if (g == 0) TL(3);
+        }
       }
       TL(4);
     }
@@ -297,168 +319,190 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
       constexpr uint32_t b_lbo = B_KMAJOR ? 16 : 4096, b_sbo = B_KMAJOR ? 1024 : 512, b_step = B_KMAJOR ? 32 : 1024;
 #endif
       constexpr uint32_t a_lt = A_KMAJOR ? 2 : 1, b_lt = B_KMAJOR ? 2 : 1;
-      uint32_t accumulate = 0;
-      for (int i = 0; i < my_kb; ++i) {
-        const int s = i % C::kStages, round = i / C::kStages;
-        mbar_wait(kSplit == 3 ? &ready[s] : &full[s], round & 1);
-        if (i == 0) TL(3);
+      int g = 0, local = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
+        const WorkItem it = decode(w);
+        const int acc = local & 1;                                  // accumulator buffer: TMEM columns [128*acc, +128)
+        if (local >= 2) mbar_wait(&tmem_empty[acc], ((local >> 1) - 1) & 1);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * C::kStageBytes);
-        const uint32_t sa = st + OFF_A, sb = st + OFF_B, sal = st + OFF_ALO, sbl = st + OFF_BLO;
-        const uint32_t ta_hi = tmem_base + C::kTmemA + s * 64, ta_lo = ta_hi + 32;     // TMEM columns of this stage's A
+        const uint32_t tacc = tmem_base + acc * 128;
+        uint32_t accumulate = 0;
+        for (int i = 0; i < it.n_kb; ++i, ++g) {
+          const int s = g % C::kStages, round = g / C::kStages;
+          mbar_wait(kSplit == 3 ? &ready[s] : &full[s], round & 1);
+          if (g == 0) TL(3);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * C::kStageBytes);
+          const uint32_t sa = st + OFF_A, sb = st + OFF_B, sal = st + OFF_ALO, sbl = st + OFF_BLO;
+          const uint32_t ta_hi = tmem_base + C::kTmemA + s * 64, ta_lo = ta_hi + 32;   // TMEM columns of this stage's A
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t db = smem_desc(sb + k * b_step, b_lbo, b_sbo, b_lt);
-          if (kSplit == 3) {
-            const uint64_t dbl = smem_desc(sbl + k * b_step, b_lbo, b_sbo, b_lt);
-            if (A_TMEM) {
-              umma_tf32_ts(tmem_base, ta_lo + k * UMMA_K, db, idesc, accumulate);
-              umma_tf32_ts(tmem_base, ta_hi + k * UMMA_K, dbl, idesc, 1);
-              umma_tf32_ts(tmem_base, ta_hi + k * UMMA_K, db, idesc, 1);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t db = smem_desc(sb + k * b_step, b_lbo, b_sbo, b_lt);
+            if (kSplit == 3) {
+              const uint64_t dbl = smem_desc(sbl + k * b_step, b_lbo, b_sbo, b_lt);
+              if (A_TMEM) {
+                umma_tf32_ts(tacc, ta_lo + k * UMMA_K, db, idesc, accumulate);
+                umma_tf32_ts(tacc, ta_hi + k * UMMA_K, dbl, idesc, 1);
+                umma_tf32_ts(tacc, ta_hi + k * UMMA_K, db, idesc, 1);
+              } else {
+                const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt);
+                const uint64_t dal = smem_desc(sal + k * a_step, a_lbo, a_sbo, a_lt);
+                umma_tf32(tacc, dal, db, idesc, accumulate);
+                umma_tf32(tacc, da, dbl, idesc, 1);
+                umma_tf32(tacc, da, db, idesc, 1);
+              }
             } else {
               const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt);
-              const uint64_t dal = smem_desc(sal + k * a_step, a_lbo, a_sbo, a_lt);
-              umma_tf32(tmem_base, dal, db, idesc, accumulate);
-              umma_tf32(tmem_base, da, dbl, idesc, 1);
-              umma_tf32(tmem_base, da, db, idesc, 1);
+              umma_tf32(tacc, da, db, idesc, accumulate);
             }
-          } else {
-            const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt);
-            umma_tf32(tmem_base, da, db, idesc, accumulate);
+            accumulate = 1;
           }
-          accumulate = 1;
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&tmem_full[acc]);
       }
-      umma_commit(tmem_full);
       TL(4);
     }
-  } else {
-    // ===== operand splitter (kSplit == 3), then epilogue =====
+  } else if (warp < 6) {
+    // ===== operand splitter (kSplit == 3) =====
     // The tensor core truncates fp32 operands to tf32, so the landed fp32 tile IS the hi operand; only lo = x - trunc(x)
     // has to be produced (same swizzled offsets as the source tile, so no layout knowledge is needed for B / MN-major A).
-    const int t = threadIdx.x - 64;   // 0..127
     if (kSplit == 3) {
+      const int t = threadIdx.x - 64;                               // 0..127
       const int row = (warp & 3) * 32 + lane;                       // TMEM lane owned by this thread
-      for (int i = 0; i < my_kb; ++i) {
-        const int s = i % C::kStages, round = i / C::kStages;
-        mbar_wait(&full[s], round & 1);
-        if (i == 0) TL(3);
-        uint8_t* stg = smem + s * C::kStageBytes;
-        if (A_TMEM) {
-          // row `row` of the K-major A tile: 8 x 16-byte chunks, chunk c stored at c ^ (row & 7) (SWIZZLE_128B)
-          const uint8_t* arow = stg + OFF_A + row * 128;
-          uint32_t hi[32], lo[32];
+      int g = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const WorkItem it = decode(w);
+        for (int i = 0; i < it.n_kb; ++i, ++g) {
+          const int s = g % C::kStages, round = g / C::kStages;
+          mbar_wait(&full[s], round & 1);
+          if (g == 0) TL(3);
+          uint8_t* stg = smem + s * C::kStageBytes;
+          if (A_TMEM) {
+            // row `row` of the K-major A tile: 8 x 16-byte chunks, chunk c stored at c ^ (row & 7) (SWIZZLE_128B)
+            const uint8_t* arow = stg + OFF_A + row * 128;
+            uint32_t hi[32], lo[32];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
-            hi[4 * c + 0] = __float_as_uint(v.x); lo[4 * c + 0] = __float_as_uint(tf32_lo(v.x));
-            hi[4 * c + 1] = __float_as_uint(v.y); lo[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
-            hi[4 * c + 2] = __float_as_uint(v.z); lo[4 * c + 2] = __float_as_uint(tf32_lo(v.z));
-            hi[4 * c + 3] = __float_as_uint(v.w); lo[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
-          }
-          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::kTmemA + s * 64;
-          tmem_st_32x32(ta, hi);
-          tmem_st_32x32(ta + 32, lo);
-          const float4* bsrc = reinterpret_cast<const float4*>(stg + OFF_B);
-          float4* blo = reinterpret_cast<float4*>(stg + OFF_BLO);
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+              hi[4 * c + 0] = __float_as_uint(v.x); lo[4 * c + 0] = __float_as_uint(tf32_lo(v.x));
+              hi[4 * c + 1] = __float_as_uint(v.y); lo[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
+              hi[4 * c + 2] = __float_as_uint(v.z); lo[4 * c + 2] = __float_as_uint(tf32_lo(v.z));
+              hi[4 * c + 3] = __float_as_uint(v.w); lo[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
+            }
+            const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::kTmemA + s * 64;
+            tmem_st_32x32(ta, hi);
+            tmem_st_32x32(ta + 32, lo);
+            const float4* bsrc = reinterpret_cast<const float4*>(stg + OFF_B);
+            float4* blo = reinterpret_cast<float4*>(stg + OFF_BLO);
 #pragma unroll
-          for (int j = t; j < TILE_BYTES / 16; j += 128) {
-            const float4 v = bsrc[j];
-            blo[j] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-          }
-          tmem_st_wait();
-          tc_fence_before();
-        } else {
-          const float4* src = reinterpret_cast<const float4*>(stg + OFF_A);          // A then B, 2 x 16 KB contiguous
-          float4* lo = reinterpret_cast<float4*>(stg + OFF_ALO);                     // A_lo then B_lo
+            for (int j = t; j < TILE_BYTES / 16; j += 128) {
+              const float4 v = bsrc[j];
+              blo[j] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+            }
+            tmem_st_wait();
+            tc_fence_before();
+          } else {
+            const float4* src = reinterpret_cast<const float4*>(stg + OFF_A);        // A then B, 2 x 16 KB contiguous
+            float4* lo = reinterpret_cast<float4*>(stg + OFF_ALO);                   // A_lo then B_lo
 #pragma unroll 4
-          for (int j = t; j < 2 * TILE_BYTES / 16; j += 128) {
-            const float4 v = src[j];
-            lo[j] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+            for (int j = t; j < 2 * TILE_BYTES / 16; j += 128) {
+              const float4 v = src[j];
+              lo[j] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+            }
           }
+          fence_proxy_async();
+          mbar_arrive(&ready[s]);
+          if (g == 0) TL(4);
         }
-        fence_proxy_async();
-        mbar_arrive(&ready[s]);
-        if (i == 0) TL(4);
       }
       TL(5);
     }
-    // epilogue: TMEM lane quadrant is fixed by warp index % 4.  Each thread drains 32 columns of its own row
-    // (tcgen05.ld 32x32b.x32), the warp transposes the 32x32 block through shared memory (the pipeline stages are
-    // free once tmem_full has fired) and then touches global memory as 4 rows x 128 contiguous bytes per instruction.
+  } else {
+    // ===== epilogue warps (6..9): drain accumulator `acc` of work item i while the other roles run item i+1 =====
+    // TMEM lane quadrant is fixed by warp index % 4.  Each thread drains 32 columns of its own row (tcgen05.ld
+    // 32x32b.x32), the warp transposes the 32x32 block through its private shared-memory patch and then touches global
+    // memory as 4 rows x 128 contiguous bytes per instruction.
     const int quad = warp & 3;
     constexpr int LDS = 36;                                    // padded row stride (floats): conflict-free float4 access
-    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * LDS;
+    float* stage = epi_stage + (warp - 6) * 32 * LDS;
     const int rsub = lane >> 3, q4 = (lane & 7) * 4;
-    const int z = blockIdx.z;
     const float coef = epi.coef();
-    // `src` operand of the axpy epilogue: 8 independent 128-bit loads per thread per 32-column chunk, issued one chunk
-    // ahead (the first chunk before the accumulator is even ready) so their latency hides behind the MMAs / TMEM drain
-    float4 sv[8];
-    auto load_src = [&](int c) {
+    int local = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
+      const WorkItem it = decode(w);
+      const int acc = local & 1, m0 = it.m0, n0 = it.n0, z = it.z;
+      // `src` operand of the axpy epilogue: 8 independent 128-bit loads per thread per 32-column chunk, issued one
+      // chunk ahead (the first chunk before the accumulator is even ready): latency hides behind the MMAs / TMEM drain
+      float4 sv[8];
+      auto load_src = [&](int c) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + quad * 32 + i * 4 + rsub, nb = n0 + c + q4;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* src = (m < M && nb < N) ? epi.src_row(m) : nullptr;
-        if (src != nullptr) {
-          if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(src + nb) & 15) == 0)) {
-            t = *reinterpret_cast<const float4*>(src + nb);
-          } else {
-            t.x = src[nb];
-            if (nb + 1 < N) t.y = src[nb + 1];
-            if (nb + 2 < N) t.z = src[nb + 2];
-            if (nb + 3 < N) t.w = src[nb + 3];
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + quad * 32 + i * 4 + rsub, nb = n0 + c + q4;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* src = (m < M && nb < N) ? epi.src_row(m) : nullptr;
+          if (src != nullptr) {
+            if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(src + nb) & 15) == 0)) {
+              t = *reinterpret_cast<const float4*>(src + nb);
+            } else {
+              t.x = src[nb];
+              if (nb + 1 < N) t.y = src[nb + 1];
+              if (nb + 2 < N) t.z = src[nb + 2];
+              if (nb + 3 < N) t.w = src[nb + 3];
+            }
           }
+          sv[i] = t;
         }
-        sv[i] = t;
-      }
-    };
-    load_src(0);
-    mbar_wait(tmem_full, 0);
-    TL(6);
-    tc_fence_after();
+      };
+      load_src(0);
+      mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+      if (local == 0) TL(6);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
-      if (my_kb > 0) {
-        tmem_ld_32x32(taddr, v);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(stage + lane * LDS + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      __syncwarp();
-      float4 cur[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = sv[i];
-      if (c + 32 < BN) load_src(c + 32);
-      const int nb = n0 + c + q4;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + quad * 32 + i * 4 + rsub;
-        if (m >= M || nb >= N) continue;
-        const float4 a = *reinterpret_cast<const float4*>(stage + (i * 4 + rsub) * LDS + q4);
-        float* out = epi.row_ptr(m, N, z) + nb;
-        const float4 o = make_float4(epi.apply(a.x, cur[i].x, coef), epi.apply(a.y, cur[i].y, coef),
-                                     epi.apply(a.z, cur[i].z, coef), epi.apply(a.w, cur[i].w, coef));
-        if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-          *reinterpret_cast<float4*>(out) = o;
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128 + c);
+        if (it.n_kb > 0) {
+          tmem_ld_32x32(taddr, v);
         } else {
-          out[0] = o.x;
-          if (nb + 1 < N) out[1] = o.y;
-          if (nb + 2 < N) out[2] = o.z;
-          if (nb + 3 < N) out[3] = o.w;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (c + 32 >= BN) {                    // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * LDS + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        float4 cur[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = sv[i];
+        if (c + 32 < BN) load_src(c + 32);
+        const int nb = n0 + c + q4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + quad * 32 + i * 4 + rsub;
+          if (m >= M || nb >= N) continue;
+          const float4 a = *reinterpret_cast<const float4*>(stage + (i * 4 + rsub) * LDS + q4);
+          float* out = epi.row_ptr(m, N, z) + nb;
+          const float4 o = make_float4(epi.apply(a.x, cur[i].x, coef), epi.apply(a.y, cur[i].y, coef),
+                                       epi.apply(a.z, cur[i].z, coef), epi.apply(a.w, cur[i].w, coef));
+          if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+            *reinterpret_cast<float4*>(out) = o;
+          } else {
+            out[0] = o.x;
+            if (nb + 1 < N) out[1] = o.y;
+            if (nb + 2 < N) out[2] = o.z;
+            if (nb + 3 < N) out[3] = o.w;
+          }
         }
       }
     }
+    TL(7);
   }
-  TL(7);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);

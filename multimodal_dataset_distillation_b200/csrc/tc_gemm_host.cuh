@@ -118,8 +118,9 @@ inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st) {
     maps.a1 = maps.a0;
     maps.b1 = maps.b0;
   }
-  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM), splits);
-  launch_k(kern, grid, NUM_THREADS, C::kSmemBytes, st, maps, g.M, g.N, g.K0, g.K1, epi);
+  const int work = ceil_div(g.N, BN) * ceil_div(g.M, BM) * splits;
+  dim3 grid(work < kNumSMs ? work : kNumSMs);                         // persistent: one CTA per SM at most
+  launch_k(kern, grid, NUM_THREADS, C::kSmemBytes, st, maps, g.M, g.N, g.K0, g.K1, splits, epi);
   return VLDD_OK;
 }
 
