@@ -19,6 +19,19 @@ __device__ __forceinline__ float sum_slabs(const float* __restrict__ part, int s
   for (int s = 1; s < splits; ++s) v += part[(size_t)s * stride + idx];
   return v;
 }
+// same sum with four independent accumulators (fixed association, still deterministic): for the 36-slab logits GEMM
+__device__ __forceinline__ float sum_slabs_ilp(const float* __restrict__ part, int splits, size_t stride, size_t idx) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int s = 0;
+  for (; s + 3 < splits; s += 4) {
+    a0 += part[(size_t)(s + 0) * stride + idx];
+    a1 += part[(size_t)(s + 1) * stride + idx];
+    a2 += part[(size_t)(s + 2) * stride + idx];
+    a3 += part[(size_t)(s + 3) * stride + idx];
+  }
+  for (; s < splits; ++s) a0 += part[(size_t)s * stride + idx];
+  return (a0 + a1) + (a2 + a3);
+}
 
 // ------------------------------------------------------------------------------------------------
 // primal, forward
@@ -160,7 +173,21 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
   pdl_enter();
   const float coef = -(*lr) * (scale ? *scale : 1.0f);
   const size_t s = (size_t)blockIdx.x * cols, t = (size_t)idx[blockIdx.x] * cols;
-  for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[t + j] += coef * sum_slabs(part, splits, stride, s + j);
+  if ((cols & 3) == 0 && (stride & 3) == 0 &&
+      ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    for (int j = threadIdx.x; j < (cols >> 2); j += blockDim.x) {
+      float4 v = *reinterpret_cast<const float4*>(part + s + 4 * j);
+      for (int z = 1; z < splits; ++z) {
+        const float4 u = *reinterpret_cast<const float4*>(part + (size_t)z * stride + s + 4 * j);
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      }
+      float4 o = *reinterpret_cast<float4*>(dst + t + 4 * j);
+      o.x += coef * v.x; o.y += coef * v.y; o.z += coef * v.z; o.w += coef * v.w;
+      *reinterpret_cast<float4*>(dst + t + 4 * j) = o;
+    }
+  } else {
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[t + j] += coef * sum_slabs(part, splits, stride, s + j);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -176,7 +203,7 @@ __global__ void __launch_bounds__(128) nce_rows_kernel(const float* __restrict__
   const float sc = *scale;
   float mx = -INFINITY;
   for (int j = threadIdx.x; j < B; j += blockDim.x) {
-    const float v = sc * sum_slabs(part, splits, stride, (size_t)i * B + j);
+    const float v = sc * sum_slabs_ilp(part, splits, stride, (size_t)i * B + j);
     S[(size_t)i * ld + j] = v;
     mx = fmaxf(mx, v);
   }
@@ -392,7 +419,7 @@ __global__ void __launch_bounds__(128) nce_t_rows_kernel(const float* __restrict
   float a = 0.f, b = 0.f;
   for (int j = threadIdx.x; j < B; j += blockDim.x) {
     const size_t ij = (size_t)i * ld + j;
-    const float v = sc * sum_slabs(part, splits, stride, (size_t)i * B + j);
+    const float v = sc * sum_slabs_ilp(part, splits, stride, (size_t)i * B + j);
     Sd[ij] = v;
     a = fmaf(expf(S[ij] - l), v, a);
     b = fmaf(G[ij], v, b);

@@ -280,6 +280,84 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   constexpr int OFF_ALO = 2 * TILE_BYTES;                           // only when A is fed from shared memory
   constexpr int OFF_BLO = (A_TMEM ? 2 : 3) * TILE_BYTES;
 
+  // Drain columns [c_begin, c_end) of accumulator `acc` for work item `it`: TMEM lane quadrant is fixed by warp index % 4.
+  // Each thread drains 32 columns of its own row (tcgen05.ld 32x32b.x32), the warp transposes the 32x32 block through a
+  // private shared-memory patch and then touches global memory as 4 rows x 128 contiguous bytes per instruction.
+  auto drain = [&](const WorkItem& it, int acc, uint32_t parity, int c_begin, int c_end, float* stage, bool release) {
+    const int quad = warp & 3;
+    constexpr int LDS = 36;                                    // padded row stride (floats): conflict-free float4 access
+    const int rsub = lane >> 3, q4 = (lane & 7) * 4;
+    const float coef = epi.coef();
+    const int m0 = it.m0, n0 = it.n0, z = it.z;
+    // `src` operand of the axpy epilogue: 8 independent 128-bit loads per thread per 32-column chunk, issued one chunk
+    // ahead (the first chunk before the accumulator is even ready): latency hides behind the MMAs / TMEM drain
+    float4 sv[8];
+    auto load_src = [&](int c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + quad * 32 + i * 4 + rsub, nb = n0 + c + q4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* src = (m < M && nb < N) ? epi.src_row(m) : nullptr;
+        if (src != nullptr) {
+          if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(src + nb) & 15) == 0)) {
+            t = *reinterpret_cast<const float4*>(src + nb);
+          } else {
+            t.x = src[nb];
+            if (nb + 1 < N) t.y = src[nb + 1];
+            if (nb + 2 < N) t.z = src[nb + 2];
+            if (nb + 3 < N) t.w = src[nb + 3];
+          }
+        }
+        sv[i] = t;
+      }
+    };
+    load_src(c_begin);
+    mbar_wait(&tmem_full[acc], parity);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      float v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128 + c);
+      if (it.n_kb > 0) {
+        tmem_ld_32x32(taddr, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (release && c + 32 >= c_end) {          // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stage + lane * LDS + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+      float4 cur[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = sv[i];
+      if (c + 32 < c_end) load_src(c + 32);
+      const int nb = n0 + c + q4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + quad * 32 + i * 4 + rsub;
+        if (m >= M || nb >= N) continue;
+        const float4 a = *reinterpret_cast<const float4*>(stage + (i * 4 + rsub) * LDS + q4);
+        float* out = epi.row_ptr(m, N, z) + nb;
+        const float4 o = make_float4(epi.apply(a.x, cur[i].x, coef), epi.apply(a.y, cur[i].y, coef),
+                                     epi.apply(a.z, cur[i].z, coef), epi.apply(a.w, cur[i].w, coef));
+        if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+          *reinterpret_cast<float4*>(out) = o;
+        } else {
+          out[0] = o.x;
+          if (nb + 1 < N) out[1] = o.y;
+          if (nb + 2 < N) out[2] = o.z;
+          if (nb + 3 < N) out[3] = o.w;
+        }
+      }
+    }
+  };
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -420,88 +498,22 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     }
   } else {
     // ===== epilogue warps (6..9): drain accumulator `acc` of work item i while the other roles run item i+1 =====
-    // TMEM lane quadrant is fixed by warp index % 4.  Each thread drains 32 columns of its own row (tcgen05.ld
-    // 32x32b.x32), the warp transposes the 32x32 block through its private shared-memory patch and then touches global
-    // memory as 4 rows x 128 contiguous bytes per instruction.
-    const int quad = warp & 3;
-    constexpr int LDS = 36;                                    // padded row stride (floats): conflict-free float4 access
-    float* stage = epi_stage + (warp - 6) * 32 * LDS;
-    const int rsub = lane >> 3, q4 = (lane & 7) * 4;
-    const float coef = epi.coef();
     int local = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
       const WorkItem it = decode(w);
-      const int acc = local & 1, m0 = it.m0, n0 = it.n0, z = it.z;
-      // `src` operand of the axpy epilogue: 8 independent 128-bit loads per thread per 32-column chunk, issued one
-      // chunk ahead (the first chunk before the accumulator is even ready): latency hides behind the MMAs / TMEM drain
-      float4 sv[8];
-      auto load_src = [&](int c) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = m0 + quad * 32 + i * 4 + rsub, nb = n0 + c + q4;
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float* src = (m < M && nb < N) ? epi.src_row(m) : nullptr;
-          if (src != nullptr) {
-            if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(src + nb) & 15) == 0)) {
-              t = *reinterpret_cast<const float4*>(src + nb);
-            } else {
-              t.x = src[nb];
-              if (nb + 1 < N) t.y = src[nb + 1];
-              if (nb + 2 < N) t.z = src[nb + 2];
-              if (nb + 3 < N) t.w = src[nb + 3];
-            }
-          }
-          sv[i] = t;
-        }
-      };
-      load_src(0);
-      mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+      const bool last = w + (int)gridDim.x >= total_work;
+      // the CTA's last item has nothing to overlap with: the (by then idle) splitter warps take the upper two chunks
+      drain(it, local & 1, (local >> 1) & 1, 0, (last && kSplit == 3) ? BN / 2 : BN, epi_stage + (warp - 6) * 32 * 36, !last);
       if (local == 0) TL(6);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128 + c);
-        if (it.n_kb > 0) {
-          tmem_ld_32x32(taddr, v);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        if (c + 32 >= BN) {                    // accumulator fully read: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stage + lane * LDS + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-        float4 cur[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = sv[i];
-        if (c + 32 < BN) load_src(c + 32);
-        const int nb = n0 + c + q4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = m0 + quad * 32 + i * 4 + rsub;
-          if (m >= M || nb >= N) continue;
-          const float4 a = *reinterpret_cast<const float4*>(stage + (i * 4 + rsub) * LDS + q4);
-          float* out = epi.row_ptr(m, N, z) + nb;
-          const float4 o = make_float4(epi.apply(a.x, cur[i].x, coef), epi.apply(a.y, cur[i].y, coef),
-                                       epi.apply(a.z, cur[i].z, coef), epi.apply(a.w, cur[i].w, coef));
-          if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-            *reinterpret_cast<float4*>(out) = o;
-          } else {
-            out[0] = o.x;
-            if (nb + 1 < N) out[1] = o.y;
-            if (nb + 2 < N) out[2] = o.z;
-            if (nb + 3 < N) out[3] = o.w;
-          }
-        }
-      }
     }
     TL(7);
+  }
+  if (kSplit == 3 && warp >= 2 && warp < 6 && total_work > (int)blockIdx.x) {
+    const int n_items = (total_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int local = n_items - 1;
+    const WorkItem it = decode((int)blockIdx.x + local * (int)gridDim.x);
+    // pipeline stage 0 is free once tmem_full of the last item has fired (drain waits for it before touching it)
+    drain(it, local & 1, (local >> 1) & 1, BN / 2, BN, reinterpret_cast<float*>(smem) + (warp - 2) * 32 * 36, false);
   }
   tc_fence_before();
   __syncthreads();
