@@ -220,3 +220,20 @@ def test_segment_prefetcher_streams_host_experts():
         assert torch.equal(sl["th0"].cpu(), host[e, s]) and torch.equal(sl["tgt"].cpu(), host[e, s + 2])
         pre.release(sl)
         pre.prefetch((i + 1) % 3, (i + 2) % 2, 2)
+
+
+@pytest.mark.parametrize("N,B,K,drop", [(500, 100, 2, False), (500, 500, 1, True), (256, 128, 2, False)])
+def test_unrolled_match_coco_shape_full_dims(N, B, K, drop):
+    """BASELINE.json configs[3]: COCO-shaped distillation (500 pairs; minibatches of 100 and the whole set) at the real
+    768 -> 2304 head, so the tensor-core path runs with several M tiles and B x B logits larger than one tile."""
+    pr = R.make_problem(N=N, B=B, K=K, dt=768, d=2304, seed=31, dropout=drop, lr=0.1, scale=2.6593, tgt_eps=0.01)
+    ref = R.unrolled_match_manual(**{k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v)
+                                     for k, v in pr.items()})
+    res = _run_engine(pr)
+    out5 = res["out5"].cpu()
+    assert abs(out5[2].item() - float(ref.loss)) <= RTOL * abs(float(ref.loss))
+    assert abs(out5[3].item() - float(ref.dlr)) <= RTOL * abs(float(ref.dlr)) + 1e-12
+    assert abs(out5[4].item() - float(ref.dscale)) <= RTOL * abs(float(ref.dscale)) + 1e-12
+    assert rel_err(res["dY"], ref.dY) < RTOL
+    assert rel_err(res["dU"], ref.dU) < RTOL
+    assert rel_err(res["theta_K"], ref.theta_K) < RTOL
