@@ -31,7 +31,7 @@ static float* dev_rand(size_t n, unsigned seed, float scale = 1.0f) {
 
 struct Res { double maxerr, maxref; float ms; };
 
-template <bool AK, bool BKm, int kSplit, int kStagesT = 0>
+template <bool AK, bool BKm, int kSplit, int kStagesT = 0, int BN = 128>
 static Res run_case(const char* name, int M, int N, int K0, int K1, int splits, bool axpy) {
   const size_t asz0 = (size_t)M * K0, bsz0 = (size_t)N * K0, asz1 = (size_t)M * (K1 ? K1 : 1), bsz1 = (size_t)N * (K1 ? K1 : 1);
   float *A0 = dev_rand(asz0, 1), *B0 = dev_rand(bsz0, 2), *A1 = dev_rand(asz1, 3), *B1 = dev_rand(bsz1, 4);
@@ -55,9 +55,9 @@ static Res run_case(const char* name, int M, int N, int K0, int K1, int splits, 
     if (flush) CK(cudaMemsetAsync(flush, rep, flush_bytes));
     CK(cudaEventRecord(e0));
     int rc;
-    if (axpy) rc = tc::launch<AK, BKm, kSplit, tc::EpiAxpyTC, kStagesT>(g, 1, tc::EpiAxpyTC{src, Ctc, N, lr}, 0);
+    if (axpy) rc = tc::launch<AK, BKm, kSplit, tc::EpiAxpyTC, kStagesT, BN>(g, 1, tc::EpiAxpyTC{src, Ctc, N, lr}, 0);
     else if (splits > 1) rc = tc::launch<AK, BKm, kSplit, tc::EpiPartial, kStagesT>(g, splits, tc::EpiPartial{part, (long long)csz}, 0);
-    else rc = tc::launch<AK, BKm, kSplit, tc::EpiScale, kStagesT>(g, 1, tc::EpiScale{Ctc, N, 1.0f}, 0);
+    else rc = tc::launch<AK, BKm, kSplit, tc::EpiScale, kStagesT, BN>(g, 1, tc::EpiScale{Ctc, N, 1.0f}, 0);
     if (rc) { printf("%s: launch failed: %s\n", name, g_err); exit(1); }
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
@@ -116,6 +116,10 @@ int main(int argc, char** argv) {
   if (want(c++)) run_case<true, true, 3, 1>("NT sims stages=1", 1000, 5000, 768, 0, 1, false);
   if (want(c++)) run_case<true, true, 1, 2>("NT F2 1xTF32 splits=8 stages=2", 100, 2304, 2304, 0, 8, false);
   if (want(c++)) run_case<true, true, 1, 2>("NT F2 1xTF32 splits=16 stages=2", 100, 2304, 2304, 0, 16, false);
+  if (want(c++)) run_case<false, false, 3, 0, 96>("TN dW2 axpy BN=96", 2304, 2304, 100, 0, 1, true);
+  if (want(c++)) run_case<false, false, 3, 0, 96>("TN dW2t dual axpy BN=96", 2304, 2304, 100, 100, 1, true);
+  if (want(c++)) run_case<true, true, 3, 0, 96>("NT sims BN=96 1000x4992x768", 1000, 4992, 768, 0, 1, false);
+  if (want(c++)) run_case<true, false, 3, 0, 64>("NN small BN=64", 100, 256, 96, 0, 1, false);
   printf("done\n");
   return 0;
 }

@@ -25,7 +25,7 @@
 namespace vldd {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 32;          // BK floats = 128 bytes = one swizzle row
+constexpr int BM = 128, BK = 32;                    // BK floats = 128 bytes = one swizzle row; BN is a template parameter
 constexpr int UMMA_K = 8;                           // tf32
 constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB per operand per stage
 constexpr int NUM_THREADS = 320;                    // producer, MMA, 4 splitter warps, 4 epilogue warps
@@ -33,11 +33,12 @@ constexpr int NUM_THREADS = 320;                    // producer, MMA, 4 splitter
 // Stage layout (kSplit == 3):  K-major A  -> [A | B | B_lo]            48 KB x 4 stages; A_hi / A_lo live in TMEM
 //                              MN-major A -> [A | B | A_lo | B_lo]     64 KB x 3 stages
 //               (kSplit == 1):              [A | B]                    32 KB x 6 stages
-template <int kSplit, bool A_TMEM, int kStagesT = 0>
+template <int kSplit, bool A_TMEM, int kStagesT = 0, int BN = 128>
 struct Cfg {
-  static constexpr int kTiles = kSplit == 3 ? (A_TMEM ? 3 : 4) : 2;
+  static constexpr int kTileB = BN * BK * 4;                              // B tile bytes (12 KB at BN = 96)
+  static constexpr int kStageBytes = kSplit == 3 ? (A_TMEM ? TILE_BYTES + 2 * kTileB : 2 * TILE_BYTES + 2 * kTileB)
+                                                 : TILE_BYTES + kTileB;
   static constexpr int kStages = kStagesT > 0 ? kStagesT : (kSplit == 3 ? (A_TMEM ? 4 : 3) : 6);
-  static constexpr int kStageBytes = kTiles * TILE_BYTES;
   static constexpr int kEpiBytes = 4 * 32 * 36 * 4;                       // private transpose patches of the epilogue warps
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = (kSplit == 3 && A_TMEM) ? 512 : 256;   // 2 accumulators x 128 + kStages x (32 hi + 32 lo)
@@ -216,11 +217,13 @@ struct Maps {
 // Work item w (one per (m-tile, n-tile, k-split)) -> CTA blockIdx.x, blockIdx.x + gridDim.x, ... (persistent loop).
 struct WorkItem { int m0, n0, z, kb_begin, n_kb; };
 
-template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0>
+template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, int splits, Epi epi) {
-  constexpr bool A_TMEM = A_KMAJOR && kSplit == 3;     // K-major A: hi/lo of the A tile are staged in tensor memory
-  using C = Cfg<kSplit, A_TMEM, kStagesT>;
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 128, "N tile: 64, 96 or 128 (32-column epilogue chunks, MN-major boxes)");
+  constexpr bool A_TMEM = kSplit == 3;                 // hi/lo of the A tile are staged in tensor memory (either major)
+  using C = Cfg<kSplit, A_TMEM, kStagesT, BN>;
+  constexpr int TILE_B = C::kTileB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);        // 4 warps x 32 x 36 floats
@@ -276,9 +279,12 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   TL(2);
 
   // byte offsets of the tiles inside a stage
-  constexpr int OFF_A = 0, OFF_B = TILE_BYTES;
-  constexpr int OFF_ALO = 2 * TILE_BYTES;                           // only when A is fed from shared memory
-  constexpr int OFF_BLO = (A_TMEM ? 2 : 3) * TILE_BYTES;
+  constexpr int kHalfN = ((BN / 32 + 1) / 2) * 32;                   // column split of the last item's drain (64 of 96 / 128)
+  //   A in TMEM: [A | B | B_lo]      A in smem: [A | A_lo | B | B_lo]   (A / A_lo and B / B_lo adjacent: one split loop each)
+  constexpr int OFF_A = 0;
+  constexpr int OFF_ALO = TILE_BYTES;                               // only when A is fed from shared memory
+  constexpr int OFF_B = (A_TMEM || kSplit != 3) ? TILE_BYTES : 2 * TILE_BYTES;
+  constexpr int OFF_BLO = OFF_B + TILE_B;
 
   // Drain columns [c_begin, c_end) of accumulator `acc` for work item `it`: TMEM lane quadrant is fixed by warp index % 4.
   // Each thread drains 32 columns of its own row (tcgen05.ld 32x32b.x32), the warp transposes the 32x32 block through a
@@ -374,7 +380,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
           const CUtensorMap* mb = seg1 ? &maps.b1 : &maps.b0;
           uint8_t* sa = smem + s * C::kStageBytes + OFF_A;
           uint8_t* sb = smem + s * C::kStageBytes + OFF_B;
-          mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+          mbar_expect_tx(&full[s], TILE_BYTES + TILE_B);
           if (A_KMAJOR) tma_load_2d(sa, ma, &full[s], k, it.m0); else tma_load_3d(sa, ma, &full[s], 0, k, it.m0 / 32);
           if (B_KMAJOR) tma_load_2d(sb, mb, &full[s], k, it.n0); else tma_load_3d(sb, mb, &full[s], 0, k, it.n0 / 32);
           if (g == 0) TL(3);
@@ -385,7 +391,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc_tf32(!A_KMAJOR, !B_KMAJOR, BM, BN);
+      constexpr uint32_t idesc = instr_desc_tf32(A_TMEM ? false : !A_KMAJOR, !B_KMAJOR, BM, BN);   // TMEM A is row-per-lane
       // K-major  (SWIZZLE_128B):         8-row groups 1024 B apart (SBO), k-step of 8 floats = +32 B inside the row
       // MN-major (SWIZZLE_128B_BASE32B): 32-wide MN chunks 4096 B apart (LBO), 4-k-row groups 512 B apart (SBO),
       //                                  k-step of 8 k-rows = +1024 B
@@ -457,16 +463,28 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
           if (g == 0) TL(3);
           uint8_t* stg = smem + s * C::kStageBytes;
           if (A_TMEM) {
-            // row `row` of the K-major A tile: 8 x 16-byte chunks, chunk c stored at c ^ (row & 7) (SWIZZLE_128B)
-            const uint8_t* arow = stg + OFF_A + row * 128;
             uint32_t hi[32], lo[32];
+            if (A_KMAJOR) {
+              // row `row` of the K-major A tile: 8 x 16-byte chunks, chunk c stored at c ^ (row & 7) (SWIZZLE_128B)
+              const uint8_t* arow = stg + OFF_A + row * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
-              hi[4 * c + 0] = __float_as_uint(v.x); lo[4 * c + 0] = __float_as_uint(tf32_lo(v.x));
-              hi[4 * c + 1] = __float_as_uint(v.y); lo[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
-              hi[4 * c + 2] = __float_as_uint(v.z); lo[4 * c + 2] = __float_as_uint(tf32_lo(v.z));
-              hi[4 * c + 3] = __float_as_uint(v.w); lo[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
+              for (int c = 0; c < 8; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
+                hi[4 * c + 0] = __float_as_uint(v.x); lo[4 * c + 0] = __float_as_uint(tf32_lo(v.x));
+                hi[4 * c + 1] = __float_as_uint(v.y); lo[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
+                hi[4 * c + 2] = __float_as_uint(v.z); lo[4 * c + 2] = __float_as_uint(tf32_lo(v.z));
+                hi[4 * c + 3] = __float_as_uint(v.w); lo[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
+              }
+            } else {
+              // MN-major A tile [chunk = row/32][k][32 floats], 32-byte segments XOR-ed with (k & 3) (SWIZZLE_128B_ATOM_32B):
+              // this thread gathers column `row` over the 32 k-rows (a transpose; each k is one conflict-free warp read)
+              const uint8_t* acol = stg + OFF_A + (warp & 3) * 4096 + (lane & 7) * 4;
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const float v = *reinterpret_cast<const float*>(acol + k * 128 + (((lane >> 3) ^ (k & 3)) << 5));
+                hi[k] = __float_as_uint(v);
+                lo[k] = __float_as_uint(tf32_lo(v));
+              }
             }
             const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::kTmemA + s * 64;
             tmem_st_32x32(ta, hi);
@@ -474,19 +492,26 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
             const float4* bsrc = reinterpret_cast<const float4*>(stg + OFF_B);
             float4* blo = reinterpret_cast<float4*>(stg + OFF_BLO);
 #pragma unroll
-            for (int j = t; j < TILE_BYTES / 16; j += 128) {
+            for (int j = t; j < TILE_B / 16; j += 128) {
               const float4 v = bsrc[j];
               blo[j] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
             }
             tmem_st_wait();
             tc_fence_before();
           } else {
-            const float4* src = reinterpret_cast<const float4*>(stg + OFF_A);        // A then B, 2 x 16 KB contiguous
-            float4* lo = reinterpret_cast<float4*>(stg + OFF_ALO);                   // A_lo then B_lo
+            const float4* asrc = reinterpret_cast<const float4*>(stg + OFF_A);
+            float4* alo = reinterpret_cast<float4*>(stg + OFF_ALO);
 #pragma unroll 4
-            for (int j = t; j < 2 * TILE_BYTES / 16; j += 128) {
-              const float4 v = src[j];
-              lo[j] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+            for (int j = t; j < TILE_BYTES / 16; j += 128) {
+              const float4 v = asrc[j];
+              alo[j] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+            }
+            const float4* bsrc = reinterpret_cast<const float4*>(stg + OFF_B);
+            float4* blo = reinterpret_cast<float4*>(stg + OFF_BLO);
+#pragma unroll 4
+            for (int j = t; j < TILE_B / 16; j += 128) {
+              const float4 v = bsrc[j];
+              blo[j] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
             }
           }
           fence_proxy_async();
@@ -503,7 +528,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
       const WorkItem it = decode(w);
       const bool last = w + (int)gridDim.x >= total_work;
       // the CTA's last item has nothing to overlap with: the (by then idle) splitter warps take the upper two chunks
-      drain(it, local & 1, (local >> 1) & 1, 0, (last && kSplit == 3) ? BN / 2 : BN, epi_stage + (warp - 6) * 32 * 36, !last);
+      drain(it, local & 1, (local >> 1) & 1, 0, (last && kSplit == 3) ? kHalfN : BN, epi_stage + (warp - 6) * 32 * 36, !last);
       if (local == 0) TL(6);
     }
     TL(7);
@@ -513,7 +538,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     const int local = n_items - 1;
     const WorkItem it = decode((int)blockIdx.x + local * (int)gridDim.x);
     // pipeline stage 0 is free once tmem_full of the last item has fired (drain waits for it before touching it)
-    drain(it, local & 1, (local >> 1) & 1, BN / 2, BN, reinterpret_cast<float*>(smem) + (warp - 2) * 32 * 36, false);
+    drain(it, local & 1, (local >> 1) & 1, kHalfN, BN, reinterpret_cast<float*>(smem) + (warp - 2) * 32 * 36, false);
   }
   tc_fence_before();
   __syncthreads();

@@ -28,15 +28,17 @@ inline EncodeTiledFn encode_fn() {
 }
 
 struct MapKey {
-  const void* ptr; int rows, K, ld, kmajor;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && K == o.K && ld == o.ld && kmajor == o.kmajor; }
+  const void* ptr; int rows, K, ld, kmajor, box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && K == o.K && ld == o.ld && kmajor == o.kmajor && box_rows == o.box_rows;
+  }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
     h ^= (size_t)k.K * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
-    h ^= (size_t)(k.ld * 2 + k.kmajor) * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+    h ^= (size_t)(k.ld * 2 + k.kmajor + 1024 * k.box_rows) * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
     return h;
   }
 };
@@ -48,10 +50,10 @@ inline bool operand_ok(const float* ptr, int rows, int K, int ld, bool kmajor) {
   return true;
 }
 
-inline int get_map(const float* ptr, int rows, int K, int ld, bool kmajor, CUtensorMap* out) {
+inline int get_map(const float* ptr, int rows, int K, int ld, bool kmajor, CUtensorMap* out, int box_rows = BM) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  const MapKey key{ptr, rows, K, ld, kmajor ? 1 : 0};
+  const MapKey key{ptr, rows, K, ld, kmajor ? 1 : 0, box_rows};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return VLDD_OK; }
@@ -62,7 +64,7 @@ inline int get_map(const float* ptr, int rows, int K, int ld, bool kmajor, CUten
   if (kmajor) {
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     const cuuint32_t es[2] = {1, 1};
     r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, es,
            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -70,7 +72,7 @@ inline int get_map(const float* ptr, int rows, int K, int ld, bool kmajor, CUten
   } else {
     const cuuint64_t dims[3] = {32, (cuuint64_t)K, (cuuint64_t)(rows / 32)};
     const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
-    const cuuint32_t box[3] = {32, (cuuint32_t)BK, 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)BK, (cuuint32_t)(box_rows / 32)};
     const cuuint32_t es[3] = {1, 1, 1};
     r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, es,
            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -94,10 +96,10 @@ inline bool gemm_ok(const GemmOperands& g) {
   return true;
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0>
+template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128>
 inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st) {
-  using C = Cfg<kSplit, A_KMAJOR && kSplit == 3, kStagesT>;
-  auto kern = tc_gemm_kernel<A_KMAJOR, B_KMAJOR, kSplit, Epi, kStagesT>;
+  using C = Cfg<kSplit, kSplit == 3, kStagesT, BN>;
+  auto kern = tc_gemm_kernel<A_KMAJOR, B_KMAJOR, kSplit, Epi, kStagesT, BN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -107,12 +109,12 @@ inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st) {
   Maps maps;
   int rc = get_map(g.A0, g.M, g.K0, g.lda0, A_KMAJOR, &maps.a0);
   if (rc) return rc;
-  rc = get_map(g.B0, g.N, g.K0, g.ldb0, B_KMAJOR, &maps.b0);
+  rc = get_map(g.B0, g.N, g.K0, g.ldb0, B_KMAJOR, &maps.b0, BN);
   if (rc) return rc;
   if (g.K1 > 0) {
     rc = get_map(g.A1, g.M, g.K1, g.lda1, A_KMAJOR, &maps.a1);
     if (rc) return rc;
-    rc = get_map(g.B1, g.N, g.K1, g.ldb1, B_KMAJOR, &maps.b1);
+    rc = get_map(g.B1, g.N, g.K1, g.ldb1, B_KMAJOR, &maps.b1, BN);
     if (rc) return rc;
   } else {
     maps.a1 = maps.a0;
@@ -127,7 +129,7 @@ inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st) {
 // number of K splits so that tiles x splits fills ONE wave of the 148 SMs without spilling into a second one (the
 // kernel runs one CTA per SM: 18 tiles x 9 splits = 162 CTAs would cost two waves), each split keeping >= 2 k-blocks
 inline int pick_splits(int M, int N, int Ktot) {
-  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int tiles = ceil_div(M, BM) * ceil_div(N, 128);
   const int nkb = ceil_div(Ktot, BK);
   int s = kNumSMs / tiles;
   const int max_s = nkb / 2 > 0 ? nkb / 2 : 1;
