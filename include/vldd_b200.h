@@ -84,6 +84,15 @@ int vldd_sim_rank(const float* img, const float* txt, int n_img, int n_txt, int 
                   const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx, int32_t* ranks_i2t,
                   int32_t* ranks_t2i, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same result as vldd_sim_rank without ever writing the score matrix: two passes of the tcgen05 GEMM whose epilogues
+ * (1) extract the ground-truth scores from the tiles that contain them and (2) count, per image row and per caption
+ * column, the entries ranked ahead of the ground truth.  nnz = img2txt_ptr[n_img] (number of CSR entries).  Requires
+ * 16-byte aligned embeddings and dim % 4 == 0 (tensor-map constraints); workspace is O(n_img + n_txt + tiles). */
+size_t vldd_sim_rank_fused_workspace_bytes(int n_img, int n_txt, int nnz);
+int vldd_sim_rank_fused(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale,
+                        const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx, int nnz,
+                        int32_t* ranks_i2t, int32_t* ranks_t2i, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Host-buffer drop-in for `itm_eval(scores_i2t, scores_t2i, txt2img, img2txt)` (numpy arrays in the reference):
  * copies the matrices to the device, ranks, copies ranks back and fills result9 in the reference's key order
  * {txt_r1, txt_r5, txt_r10, txt_r_mean, img_r1, img_r5, img_r10, img_r_mean, r_mean}.  ranks_*_host may be NULL. */

@@ -168,6 +168,28 @@ int vldd_sim_rank(const float* img, const float* txt, int n_img, int n_txt, int 
   return ranks_cols(s_i2t, n_txt, n_img, n_txt, txt2img, ranks_t2i, S(stream));                   // text -> image: columns
 }
 
+size_t vldd_sim_rank_fused_workspace_bytes(int n_img, int n_txt, int nnz) {
+  if (n_img <= 0 || n_txt <= 0 || nnz < 0) return 256;
+  return sim_rank_fused_workspace_bytes(n_img, n_txt, nnz);
+}
+
+int vldd_sim_rank_fused(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale,
+                        const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx, int nnz,
+                        int32_t* ranks_i2t, int32_t* ranks_t2i, void* workspace, size_t workspace_bytes, void* stream) {
+  VLDD_REQUIRE(n_img >= 0 && n_txt >= 0 && dim > 0 && nnz >= 0 && img && txt, "sim_rank_fused: bad arguments");
+  VLDD_REQUIRE(txt2img && img2txt_ptr && img2txt_idx && ranks_i2t && ranks_t2i, "sim_rank_fused: null ground truth / outputs");
+  if (n_img == 0 || n_txt == 0) return VLDD_OK;
+  VLDD_REQUIRE(sim_rank_fused_ok(img, txt, n_img, n_txt, dim),
+               "sim_rank_fused: operands do not satisfy the tensor-map constraints (16-byte aligned, dim %% 4 == 0); use "
+               "vldd_sim_rank");
+  if (workspace == nullptr || workspace_bytes < vldd_sim_rank_fused_workspace_bytes(n_img, n_txt, nnz)) {
+    set_error("sim_rank_fused: workspace too small (need %zu bytes)", vldd_sim_rank_fused_workspace_bytes(n_img, n_txt, nnz));
+    return VLDD_ERR_WORKSPACE;
+  }
+  return sim_rank_fused(img, txt, n_img, n_txt, dim, scale, txt2img, img2txt_ptr, img2txt_idx, nnz, ranks_i2t, ranks_t2i,
+                        workspace, S(stream));
+}
+
 int vldd_itm_eval_host(const float* scores_i2t_host, const float* scores_t2i_host, int n_img, int n_txt,
                        const int32_t* txt2img_host, const int32_t* img2txt_ptr_host, const int32_t* img2txt_idx_host,
                        int32_t* ranks_i2t_host, int32_t* ranks_t2i_host, double* result9, void* stream) {

@@ -259,6 +259,107 @@ int sim_scores(const float* img, const float* txt, int I, int T, int D, float sc
   return VLDD_OK;
 }
 
+// ---- fused similarity + ranking: the score matrix is never written to HBM --------------------------------------------
+// Two passes of the SAME tcgen05 GEMM kernel (bit-identical tile values): pass 1 visits only the tiles that hold a
+// ground-truth pair and extracts those scores; pass 2 visits every tile and counts, per row and per column, the entries
+// ranked ahead of the ground truth (integer atomics).  Result == ranking the materialised matrix, bit for bit.
+__global__ void __launch_bounds__(256) mark_gt_tiles_kernel(const int32_t* __restrict__ gt_ptr, const int32_t* __restrict__ gt_idx,
+                                                            const int32_t* __restrict__ txt2img, int I, int T, int tiles_n,
+                                                            int* __restrict__ flags) {
+  pdl_enter();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < I) {
+    for (int e = gt_ptr[t]; e < gt_ptr[t + 1]; ++e) {
+      const int c = gt_idx[e];
+      if (c >= 0 && c < T) flags[(t / tc::BM) * tiles_n + c / 128] = 1;
+    }
+  }
+  if (t < T) {
+    const int g = txt2img[t];
+    if (g >= 0 && g < I) flags[(g / tc::BM) * tiles_n + t / 128] = 1;
+  }
+}
+__global__ void __launch_bounds__(256) compact_tiles_kernel(const int* __restrict__ flags, int n, int* __restrict__ list,
+                                                            int* __restrict__ count) {
+  pdl_enter();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n && flags[t]) list[atomicAdd(count, 1)] = t;
+}
+__global__ void __launch_bounds__(256) rank_thresholds_kernel(const int32_t* __restrict__ gt_ptr, const int32_t* __restrict__ gt_idx,
+                                                              const float* __restrict__ gt_val, const int32_t* __restrict__ txt2img,
+                                                              int I, int T, float* __restrict__ row_thr,
+                                                              int32_t* __restrict__ row_thr_idx, int32_t* __restrict__ col_thr_idx) {
+  pdl_enter();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < I) {
+    float bs = -INFINITY;
+    int bc = -1;
+    for (int e = gt_ptr[t]; e < gt_ptr[t + 1]; ++e) {
+      const int c = gt_idx[e];
+      if (c < 0 || c >= T) continue;
+      const float sc = gt_val[e];
+      if (bc < 0 || sc > bs || (sc == bs && c < bc)) { bs = sc; bc = c; }
+    }
+    row_thr[t] = bs;
+    row_thr_idx[t] = bc;
+  }
+  if (t < T) {
+    const int g = txt2img[t];
+    col_thr_idx[t] = (g >= 0 && g < I) ? g : -1;
+  }
+}
+__global__ void __launch_bounds__(256) rank_finalize_kernel(const int32_t* __restrict__ row_thr_idx,
+                                                            const int32_t* __restrict__ col_thr_idx, int I, int T,
+                                                            int32_t* __restrict__ ranks_i2t, int32_t* __restrict__ ranks_t2i) {
+  pdl_enter();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < I && row_thr_idx[t] < 0) ranks_i2t[t] = T;      // no valid ground truth: never retrieved
+  if (t < T && col_thr_idx[t] < 0) ranks_t2i[t] = I;
+}
+
+size_t sim_rank_fused_workspace_bytes(int I, int T, int nnz) {
+  const size_t tiles = (size_t)ceil_div(I, tc::BM) * ceil_div(T, 128);
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  return al((size_t)nnz * 4 + 4) + al((size_t)T * 4) + al((size_t)I * 4) * 2 + al((size_t)T * 4) + al(tiles * 4) * 2 + 256;
+}
+
+bool sim_rank_fused_ok(const float* img, const float* txt, int I, int T, int D) {
+  return tc_enabled() && tc::gemm_ok<true, true>(gemm_ops(img, D, txt, D, I, T, D));
+}
+
+int sim_rank_fused(const float* img, const float* txt, int I, int T, int D, float scale, const int32_t* txt2img,
+                   const int32_t* gt_ptr, const int32_t* gt_idx, int nnz, int32_t* ranks_i2t, int32_t* ranks_t2i,
+                   void* workspace, cudaStream_t st) {
+  const int tiles_m = ceil_div(I, tc::BM), tiles_n = ceil_div(T, 128), tiles = tiles_m * tiles_n;
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  char* p = reinterpret_cast<char*>(workspace);
+  float* gt_val = reinterpret_cast<float*>(p); p += al((size_t)nnz * 4 + 4);
+  float* col_val = reinterpret_cast<float*>(p); p += al((size_t)T * 4);
+  float* row_thr = reinterpret_cast<float*>(p); p += al((size_t)I * 4);
+  int32_t* row_thr_idx = reinterpret_cast<int32_t*>(p); p += al((size_t)I * 4);
+  int32_t* col_thr_idx = reinterpret_cast<int32_t*>(p); p += al((size_t)T * 4);
+  int* flags = reinterpret_cast<int*>(p); p += al((size_t)tiles * 4);
+  int* list = reinterpret_cast<int*>(p); p += al((size_t)tiles * 4);
+  int* count = reinterpret_cast<int*>(p);
+  VLDD_CUDA(cudaMemsetAsync(flags, 0, (size_t)tiles * 4, st));
+  VLDD_CUDA(cudaMemsetAsync(count, 0, 4, st));
+  VLDD_CUDA(cudaMemsetAsync(ranks_i2t, 0, (size_t)I * 4, st));
+  VLDD_CUDA(cudaMemsetAsync(ranks_t2i, 0, (size_t)T * 4, st));
+  const int nmax = I > T ? I : T;
+  launch_k(mark_gt_tiles_kernel, ceil_div(nmax, 256), 256, 0, st, gt_ptr, gt_idx, txt2img, I, T, tiles_n, flags);
+  launch_k(compact_tiles_kernel, ceil_div(tiles, 256), 256, 0, st, (const int*)flags, tiles, list, count);
+  const GemmOperands g = gemm_ops(img, D, txt, D, I, T, D);
+  int rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankExtract{scale, gt_ptr, gt_idx, gt_val, txt2img, col_val}, st, list, count);
+  if (rc) return rc;
+  launch_k(rank_thresholds_kernel, ceil_div(nmax, 256), 256, 0, st, gt_ptr, gt_idx, (const float*)gt_val, txt2img, I, T, row_thr,
+           row_thr_idx, col_thr_idx);
+  rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankCount{scale, row_thr, row_thr_idx, ranks_i2t, col_val, col_thr_idx, ranks_t2i}, st);
+  if (rc) return rc;
+  launch_k(rank_finalize_kernel, ceil_div(nmax, 256), 256, 0, st, (const int32_t*)row_thr_idx, (const int32_t*)col_thr_idx, I, T,
+           ranks_i2t, ranks_t2i);
+  return check_launch("sim_rank_fused");
+}
+
 // Keep each row's k largest entries, everything else := fill (epoch_original.py:95-105).
 // Radix select on the order-preserving integer image of the float, 4 passes of 8 bits, one CTA per row;
 // among entries equal to the k-th value the lower column indices are kept (stable, as the oracle does).

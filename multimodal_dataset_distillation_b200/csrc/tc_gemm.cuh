@@ -175,7 +175,10 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(bool a_mn_major, bool b_m
 }
 
 // ---- epilogues -------------------------------------------------------------------------------------------
+enum EpiKind { kEpiStore = 0, kEpiRankExtract = 1, kEpiRankCount = 2 };
+
 struct EpiPartial {   // raw fp32 tile -> slab z of [splits][M*N]
+  static constexpr int kKind = kEpiStore;
   float* part; long long stride;
   __device__ __forceinline__ float* row_ptr(int m, int N, int z) const { return part + (size_t)z * stride + (size_t)m * N; }
   __device__ __forceinline__ float coef() const { return 1.0f; }
@@ -183,6 +186,7 @@ struct EpiPartial {   // raw fp32 tile -> slab z of [splits][M*N]
   __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
 };
 struct EpiScale {     // C = alpha * acc
+  static constexpr int kKind = kEpiStore;
   float* C; int ldc; float alpha;
   __device__ __forceinline__ float* row_ptr(int m, int, int) const { return C + (size_t)m * ldc; }
   __device__ __forceinline__ float coef() const { return alpha; }
@@ -190,11 +194,40 @@ struct EpiScale {     // C = alpha * acc
   __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
 };
 struct EpiAxpyTC {    // dst = src - (*lr) * acc   (src nullable = 0)
+  static constexpr int kKind = kEpiStore;
   const float* src; float* dst; int ld; const float* lr;
   __device__ __forceinline__ float* row_ptr(int m, int, int) const { return dst + (size_t)m * ld; }
   __device__ __forceinline__ const float* src_row(int m) const { return src ? src + (size_t)m * ld : nullptr; }
   __device__ __forceinline__ float coef() const { return *lr; }
   __device__ __forceinline__ float apply(float acc, float srcv, float c) const { return srcv - c * acc; }
+};
+
+// Retrieval epilogues: the score tile S = alpha * acc never leaves the SM.
+//  pass 1 (extract): only the tiles that contain a ground-truth pair are computed; the scores at the ground-truth
+//                    positions are written out (gt_val[e] for CSR entry e of image m; col_val[t] = S[txt2img[t], t]).
+//  pass 2 (count):   every tile; per row   rank_row[m] += #{n : S > thr or (S == thr and n < thr_idx)}   (image -> text)
+//                                per column rank_col[n] += #{m : S > thr or (S == thr and m < thr_idx)}  (text -> image)
+//                    integer atomics: order-independent, and both passes see bit-identical tile values (same kernel,
+//                    same K order), so the result equals ranking the materialised matrix.
+struct EpiRankExtract {
+  static constexpr int kKind = kEpiRankExtract;
+  float alpha;
+  __device__ __forceinline__ float coef() const { return alpha; }
+  __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
+  __device__ __forceinline__ float* row_ptr(int, int, int) const { return nullptr; }
+  __device__ __forceinline__ float apply(float a, float, float) const { return a; }
+  const int32_t* gt_ptr; const int32_t* gt_idx; float* gt_val;      // img2txt CSR and its score slots
+  const int32_t* col_gt; float* col_val;                            // txt2img and its score slots
+};
+struct EpiRankCount {
+  static constexpr int kKind = kEpiRankCount;
+  float alpha;
+  __device__ __forceinline__ float coef() const { return alpha; }
+  __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
+  __device__ __forceinline__ float* row_ptr(int, int, int) const { return nullptr; }
+  __device__ __forceinline__ float apply(float a, float, float) const { return a; }
+  const float* row_thr; const int32_t* row_thr_idx; int32_t* row_cnt;   // [M]
+  const float* col_thr; const int32_t* col_thr_idx; int32_t* col_cnt;   // [N]
 };
 
 #ifdef VLDD_TC_TIMELINE
@@ -219,7 +252,8 @@ struct WorkItem { int m0, n0, z, kb_begin, n_kb; };
 
 template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, int splits, Epi epi) {
+tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, int splits, Epi epi,
+               const int* __restrict__ work_list, const int* __restrict__ work_count) {
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= 128, "N tile: 64, 96 or 128 (32-column epilogue chunks, MN-major boxes)");
   constexpr bool A_TMEM = kSplit == 3;                 // hi/lo of the A tile are staged in tensor memory (either major)
   using C = Cfg<kSplit, A_TMEM, kStagesT, BN>;
@@ -240,9 +274,12 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   const int nkb0 = (K0 + BK - 1) / BK, nkb1 = (K1 + BK - 1) / BK, nkb = nkb0 + nkb1;
   const int per = (nkb + splits - 1) / splits;
-  const int total_work = tiles_m * tiles_n * splits;
+  // optional device-side work list (tile indices chosen by an earlier kernel, e.g. "tiles holding a ground-truth pair");
+  // it is written by a predecessor kernel, so it may only be read after pdl_wait() -- see below
+  int total_work = tiles_m * tiles_n * splits;
   auto decode = [&](int w) {
     WorkItem it;
+    if (work_list != nullptr) w = work_list[w];
     const int tile = w % (tiles_m * tiles_n);
     it.z = w / (tiles_m * tiles_n);
     it.n0 = (tile % tiles_n) * BN;            // consecutive CTAs take consecutive n-tiles of one m-tile (A reuse in L2)
@@ -277,6 +314,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   TL(1);
   pdl_enter();
   TL(2);
+  if (work_count != nullptr) total_work = *work_count;
 
   // byte offsets of the tiles inside a stage
   constexpr int kHalfN = ((BN / 32 + 1) / 2) * 32;                   // column split of the last item's drain (64 of 96 / 128)
@@ -317,9 +355,16 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         sv[i] = t;
       }
     };
-    load_src(c_begin);
+    if constexpr (Epi::kKind == kEpiStore) load_src(c_begin);
     mbar_wait(&tmem_full[acc], parity);
     tc_fence_after();
+    [[maybe_unused]] int row_count = 0;
+    [[maybe_unused]] float row_thr = 0.f;
+    [[maybe_unused]] int row_thr_idx = -1;
+    const int my_m = m0 + quad * 32 + lane;                     // the accumulator row this thread drains
+    if constexpr (Epi::kKind == kEpiRankCount) {
+      if (my_m < M) { row_thr = epi.row_thr[my_m]; row_thr_idx = epi.row_thr_idx[my_m]; }
+    }
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
       float v[32];
@@ -334,33 +379,81 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
       }
+      if constexpr (Epi::kKind != kEpiStore) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= coef;               // the score, exactly as EpiScale would have stored it
+      }
+      if constexpr (Epi::kKind == kEpiRankCount) {
+        if (my_m < M && row_thr_idx >= 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c + j;
+            row_count += (n < N) && ((v[j] > row_thr) || (v[j] == row_thr && n < row_thr_idx));
+          }
+        }
+      }
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<float4*>(stage + lane * LDS + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       __syncwarp();
-      float4 cur[8];
+      if constexpr (Epi::kKind == kEpiStore) {
+        float4 cur[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cur[i] = sv[i];
-      if (c + 32 < c_end) load_src(c + 32);
-      const int nb = n0 + c + q4;
+        for (int i = 0; i < 8; ++i) cur[i] = sv[i];
+        if (c + 32 < c_end) load_src(c + 32);
+        const int nb = n0 + c + q4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + quad * 32 + i * 4 + rsub;
-        if (m >= M || nb >= N) continue;
-        const float4 a = *reinterpret_cast<const float4*>(stage + (i * 4 + rsub) * LDS + q4);
-        float* out = epi.row_ptr(m, N, z) + nb;
-        const float4 o = make_float4(epi.apply(a.x, cur[i].x, coef), epi.apply(a.y, cur[i].y, coef),
-                                     epi.apply(a.z, cur[i].z, coef), epi.apply(a.w, cur[i].w, coef));
-        if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-          *reinterpret_cast<float4*>(out) = o;
-        } else {
-          out[0] = o.x;
-          if (nb + 1 < N) out[1] = o.y;
-          if (nb + 2 < N) out[2] = o.z;
-          if (nb + 3 < N) out[3] = o.w;
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + quad * 32 + i * 4 + rsub;
+          if (m >= M || nb >= N) continue;
+          const float4 a = *reinterpret_cast<const float4*>(stage + (i * 4 + rsub) * LDS + q4);
+          float* out = epi.row_ptr(m, N, z) + nb;
+          const float4 o = make_float4(epi.apply(a.x, cur[i].x, coef), epi.apply(a.y, cur[i].y, coef),
+                                       epi.apply(a.z, cur[i].z, coef), epi.apply(a.w, cur[i].w, coef));
+          if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+            *reinterpret_cast<float4*>(out) = o;
+          } else {
+            out[0] = o.x;
+            if (nb + 1 < N) out[1] = o.y;
+            if (nb + 2 < N) out[2] = o.z;
+            if (nb + 3 < N) out[3] = o.w;
+          }
+        }
+      } else if constexpr (Epi::kKind == kEpiRankExtract) {
+        // rows: the ground-truth captions of image my_m that fall into this 32-column chunk
+        if (my_m < M) {
+          for (int e = epi.gt_ptr[my_m]; e < epi.gt_ptr[my_m + 1]; ++e) {
+            const int cidx = epi.gt_idx[e] - (n0 + c);
+            if (cidx >= 0 && cidx < 32) epi.gt_val[e] = stage[lane * LDS + cidx];
+          }
+        }
+        // columns: lane j owns caption n; its image row may sit in this warp's 32-row quadrant
+        const int n = n0 + c + lane;
+        if (n < N) {
+          const int g = epi.col_gt[n] - (m0 + quad * 32);
+          if (g >= 0 && g < 32) epi.col_val[n] = stage[g * LDS + lane];
+        }
+      } else {   // kEpiRankCount, column direction: lane j counts the 32 rows of this quadrant for caption n
+        const int n = n0 + c + lane;
+        if (n < N) {
+          const float thr = epi.col_thr[n];
+          const int tidx = epi.col_thr_idx[n];
+          if (tidx >= 0) {
+            int cnt = 0;
+            const int mbase = m0 + quad * 32;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              const float sv_ = stage[rr * LDS + lane];
+              cnt += (mbase + rr < M) && ((sv_ > thr) || (sv_ == thr && mbase + rr < tidx));
+            }
+            if (cnt) atomicAdd(epi.col_cnt + n, cnt);
+          }
         }
       }
+    }
+    if constexpr (Epi::kKind == kEpiRankCount) {
+      if (row_count) atomicAdd(epi.row_cnt + my_m, row_count);
     }
   };
 

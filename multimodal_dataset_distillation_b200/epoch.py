@@ -109,8 +109,10 @@ def epoch_test_metrics(dataloader, model, device, bert_test_embed):
     n_img, n_txt = image_embeds.shape[0], text_embeds.shape[0]
     t2i, ptr, idx = ops.maps_to_arrays(ds.txt2img, ds.img2txt, n_img, n_txt)
     dev = image_embeds.device
-    r1, r2 = ops.sim_rank(image_embeds, text_embeds, torch.from_numpy(t2i).to(dev), torch.from_numpy(ptr).to(dev),
-                          torch.from_numpy(idx).to(dev), ops.LOGIT_SCALE_EVAL)
+    # large galleries: ranking fused into the GEMM epilogue (no [I,T] matrix in HBM); small ones: one GEMM + rank kernels
+    rank_fn = ops.sim_rank_fused if (n_img * n_txt >= 50_000_000 and image_embeds.shape[1] % 4 == 0) else ops.sim_rank
+    r1, r2 = rank_fn(image_embeds, text_embeds, torch.from_numpy(t2i).to(dev), torch.from_numpy(ptr).to(dev),
+                     torch.from_numpy(idx).to(dev), ops.LOGIT_SCALE_EVAL)
     return ranks_to_result(r1, r2)
 
 

@@ -201,6 +201,24 @@ def sim_rank(img: torch.Tensor, txt: torch.Tensor, txt2img: torch.Tensor, img2tx
     return r1, r2
 
 
+def sim_rank_fused(img: torch.Tensor, txt: torch.Tensor, txt2img: torch.Tensor, img2txt_ptr: torch.Tensor,
+                   img2txt_idx: torch.Tensor, scale: float = LOGIT_SCALE_EVAL, workspace: torch.Tensor | None = None):
+    """Embeddings -> ranks of both directions with the ranking fused into the GEMM epilogue (no score matrix in HBM)."""
+    img, txt = _req(img, "img"), _req(txt, "txt")
+    I, T, D = img.shape[0], txt.shape[0], img.shape[1]
+    idx = _req(img2txt_idx, "img2txt_idx", torch.int32)
+    nnz = idx.numel()
+    need = lib().vldd_sim_rank_fused_workspace_bytes(I, T, nnz)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=img.device)
+    r1 = torch.empty(I, dtype=torch.int32, device=img.device)
+    r2 = torch.empty(T, dtype=torch.int32, device=img.device)
+    check(lib().vldd_sim_rank_fused(_ptr(img), _ptr(txt), I, T, D, float(scale), _ptr(_req(txt2img, "txt2img", torch.int32)),
+                                    _ptr(_req(img2txt_ptr, "img2txt_ptr", torch.int32)), _ptr(idx), nnz, _ptr(r1), _ptr(r2),
+                                    _ptr(workspace), workspace.numel(), _stream()), "sim_rank_fused")
+    return r1, r2
+
+
 RESULT_KEYS = ("txt_r1", "txt_r5", "txt_r10", "txt_r_mean", "img_r1", "img_r5", "img_r10", "img_r_mean", "r_mean")
 
 

@@ -36,6 +36,19 @@ def run(I, C, D, reps=5):
         ref = int((S[k] > S[k, best]).sum())
         ok &= abs(int(r1[i]) - ref) <= 2          # fp32 summation-order near-ties only
     rec = [(r1 < k).float().mean().item() * 100 for k in (1, 5, 10)]
+    wsf = torch.empty(ops.lib().vldd_sim_rank_fused_workspace_bytes(I, T, T), dtype=torch.uint8, device="cuda")
+    f1, f2 = ops.sim_rank_fused(img, txt, t2i, ptr, idx, 14.285714, wsf)
+    same = bool(torch.equal(f1, r1) and torch.equal(f2, r2))
+    tf = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.sim_rank_fused(img, txt, t2i, ptr, idx, 14.285714, wsf)
+        e1.record()
+        torch.cuda.synchronize()
+        tf.append(e0.elapsed_time(e1))
+    msf = sorted(tf)[len(tf) // 2]
+    print(f"   fused epilogue: {msf:9.3f} ms  {I * T / msf / 1e6:9.2f} G pairs/s  workspace {wsf.numel() / 2**20:.2f} MiB  equal-to-materialised={same}")
     print(f"I={I:6d} T={T:7d} D={D}: {ms:9.3f} ms  {I * T / ms / 1e6:9.2f} G pairs/s  GEMM {2 * I * T * D / ms / 1e9:7.1f} TFLOP/s(fp32-equiv) "
           f"workspace {ws.numel() / 2**30:.2f} GiB  i2t R@1/5/10 = {rec[0]:.1f}/{rec[1]:.1f}/{rec[2]:.1f}  spot-check {'ok' if ok else 'MISMATCH'}")
 

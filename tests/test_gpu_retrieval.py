@@ -190,3 +190,46 @@ def test_sim_rank_random_maps_and_ties(I, T, D):
     assert np.array_equal(S, (2.0 * img @ txt.T).astype(np.float32))            # small half-integers: exact in any order
     assert np.array_equal(r1.cpu().numpy(), RR.ranks_i2t(S, img2txt))
     assert np.array_equal(r2.cpu().numpy(), RR.ranks_t2i(np.ascontiguousarray(S.T), txt2img))
+
+
+@pytest.mark.parametrize("I,T,D,C", [(1000, 5000, 768, 5), (130, 257, 64, 0), (513, 1030, 128, 0), (64, 64, 32, 1), (300, 37, 16, 0)])
+def test_sim_rank_fused_equals_materialised(I, T, D, C):
+    """GEMM with rank epilogues (no score matrix in HBM) == similarity GEMM + rank kernels, bit for bit."""
+    from multimodal_dataset_distillation_b200 import ops
+    rng = np.random.default_rng(I + T)
+    if C:                                    # Flickr-like block structure
+        img, txt = RR.synthetic_retrieval(I, T // I, D, seed=I)
+        txt2img, img2txt = RR.flickr_maps(I, T // I)
+    else:                                    # arbitrary, inconsistent maps + heavy ties (half-integer embeddings)
+        img = (rng.integers(-2, 3, size=(I, D)) / 2).astype(np.float32)
+        txt = (rng.integers(-2, 3, size=(T, D)) / 2).astype(np.float32)
+        img2txt = {i: sorted(rng.choice(T, size=rng.integers(1, min(T, 4) + 1), replace=False).tolist()) for i in range(I)}
+        txt2img = {t: int(rng.integers(0, I)) for t in range(T)}
+    t2i, ptr, idx = ops.maps_to_arrays(txt2img, img2txt, I, T)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    a1, a2 = ops.sim_rank(dev(img), dev(txt), dev(t2i), dev(ptr), dev(idx), 14.285714)
+    b1, b2 = ops.sim_rank_fused(dev(img), dev(txt), dev(t2i), dev(ptr), dev(idx), 14.285714)
+    assert torch.equal(a1, b1) and torch.equal(a2, b2)
+    if not C:
+        S = (np.float32(14.285714) * (img @ txt.T)).astype(np.float32)
+        s1, _ = ops.sim_scores(dev(img), dev(txt), 14.285714, want_t2i=False)
+        if np.array_equal(s1.cpu().numpy(), S):          # exact products: the oracle on numpy scores must agree too
+            assert np.array_equal(b1.cpu().numpy(), RR.ranks_i2t(S, img2txt))
+            assert np.array_equal(b2.cpu().numpy(), RR.ranks_t2i(np.ascontiguousarray(S.T), txt2img))
+
+
+def test_sim_rank_fused_invalid_ground_truth():
+    from multimodal_dataset_distillation_b200 import ops
+    rng = np.random.default_rng(5)
+    I, T, D = 40, 90, 32
+    img, txt = rng.standard_normal((I, D)).astype(np.float32), rng.standard_normal((T, D)).astype(np.float32)
+    t2i = rng.integers(0, I, size=T).astype(np.int32)
+    t2i[3], t2i[77] = -1, I + 5                                   # captions without a valid image
+    ptr = np.arange(I + 1, dtype=np.int32)
+    idx = rng.integers(0, T, size=I).astype(np.int32)
+    idx[7] = T + 3                                                # image whose only caption index is out of range
+    dev = lambda a: torch.from_numpy(a).cuda()
+    a1, a2 = ops.sim_rank(dev(img), dev(txt), dev(t2i), dev(ptr), dev(idx), 1.0)
+    b1, b2 = ops.sim_rank_fused(dev(img), dev(txt), dev(t2i), dev(ptr), dev(idx), 1.0)
+    assert torch.equal(a1, b1) and torch.equal(a2, b2)
+    assert int(b1[7]) == T and int(b2[3]) == I and int(b2[77]) == I
