@@ -133,7 +133,7 @@ def epoch(e, dataloader, net, optimizer_img, optimizer_txt, args, scaler=None):
                 loss, acc = net(image, caption, e)
         else:
             loss, acc = net(image, caption, e)
-        loss_avg += float(loss) * n_b
+        loss_avg += loss.item() * n_b
         acc_avg += acc
         num_exp += n_b
         optimizer_img.zero_grad()
