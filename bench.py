@@ -158,6 +158,17 @@ def bench_dominant_kernel(dev, experts, reps=40):
                 flops=2 * M * N * K)
 
 
+def workload_config(world):
+    return {"workload": "configs[2]: full distill inner loop, Flickr30K-shaped (N=B=100 pairs, syn_steps=8, "
+                        "expert_epochs=1, max_start_epoch=2, text_projection 768->2304 in train mode (fresh "
+                        "dropout-0.1 masks every iteration), image side = frozen 2304-d embeddings)",
+            "unit_of_work": "one expert segment: 8-step unroll + matching loss + reverse sweep + outer SGD; "
+                            "one segment per rank per step, grads all-reduced (NCCL) when n_gpus > 1",
+            "l2_policy": "inputs larger than L2: steps rotate over 4 experts x 2 start epochs (340 MB of "
+                         "snapshots) and the per-iteration working set is ~450 MB vs 126 MB L2",
+            "parallelism": f"dp{world} (one expert segment per GPU)"}
+
+
 def run_ours(opt):
     import torch.distributed as dist
     from multimodal_dataset_distillation_b200 import distill, ops, epoch
@@ -257,14 +268,7 @@ def run_ours(opt):
             "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "configs[2]: full distill inner loop, Flickr30K-shaped (N=B=100 pairs, syn_steps=8, "
-                                   "expert_epochs=1, max_start_epoch=2, text_projection 768->2304 in train mode (fresh "
-                                   "dropout-0.1 masks every iteration), image side = frozen 2304-d embeddings)",
-                       "unit_of_work": "one expert segment: 8-step unroll + matching loss + reverse sweep + outer SGD; "
-                                       "one segment per rank per step, grads all-reduced (NCCL) when n_gpus > 1",
-                       "l2_policy": "inputs larger than L2: steps rotate over 4 experts x 2 start epochs (340 MB of "
-                                    "snapshots) and the per-iteration working set is ~450 MB vs 126 MB L2",
-                       "parallelism": f"dp{world} (one expert segment per GPU)"},
+            "config": workload_config(world),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "segment (theta_start, theta_target, perms) copied from pinned host memory every step "
@@ -376,7 +380,7 @@ def run_reference(opt):
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": opt.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[2]: full distill inner loop, Flickr30K-shaped (N=B=100 pairs, syn_steps=8)"},
+            "config": workload_config(1),
             "cpu_baseline": {"value": v, "unit": "iters/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 

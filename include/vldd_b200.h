@@ -62,6 +62,9 @@ int vldd_momentum_sgd(float* p, const float* g, float* buf, float lr, float mome
 int vldd_ranks_from_scores(const float* scores_i2t, const float* scores_t2i, int n_img, int n_txt,
                            const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx,
                            int32_t* ranks_i2t, int32_t* ranks_t2i, void* stream);
+/* Text->image ranks taken column-wise from the [n_img, n_txt] image->text matrix (no transpose needed): rank of row
+ * txt2img[t] inside column t.   epoch.py:231-235 applied to sims_matrix.t() (epoch_original.py:101). */
+int vldd_ranks_cols(const float* scores_i2t, int n_img, int n_txt, const int32_t* txt2img, int32_t* ranks_t2i, void* stream);
 /* Caption-sharded ranking (multi-GPU; `scores` holds columns [col_offset, col_offset+cols) of the full matrix, ground
  * truth indices are GLOBAL).  best_gt: per row the best local ground-truth (score, global index; -inf / -1 if none).
  * count: per row #{local j : s_j > thr_score or (s_j == thr_score and global j < thr_idx)}.  Summed over shards this is

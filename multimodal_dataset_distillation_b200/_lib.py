@@ -24,6 +24,7 @@ _SIGS = {
     "vldd_match_loss_bwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P]),
     "vldd_momentum_sgd": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int, C.c_int64, _P]),
     "vldd_ranks_from_scores": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "vldd_ranks_cols": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "vldd_rank_best_gt": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "vldd_rank_count": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "vldd_recall_counts": (C.c_int, [_P, C.c_int, _P, _P]),

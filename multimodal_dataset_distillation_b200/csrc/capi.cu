@@ -114,6 +114,11 @@ int vldd_ranks_from_scores(const float* scores_i2t, const float* scores_t2i, int
   return VLDD_OK;
 }
 
+int vldd_ranks_cols(const float* scores_i2t, int n_img, int n_txt, const int32_t* txt2img, int32_t* ranks_t2i, void* stream) {
+  VLDD_REQUIRE(n_img >= 0 && n_txt >= 0 && (n_txt == 0 || (scores_i2t && txt2img && ranks_t2i)), "ranks_cols: bad arguments");
+  return ranks_cols(scores_i2t, n_txt, n_img, n_txt, txt2img, ranks_t2i, S(stream));
+}
+
 int vldd_rank_best_gt(const float* scores, int rows, int cols, int col_offset, const int32_t* gt_ptr,
                       const int32_t* gt_idx, float* best_score, int32_t* best_idx, void* stream) {
   VLDD_REQUIRE(rows >= 0 && cols >= 0 && (rows == 0 || (scores && gt_ptr && gt_idx && best_score && best_idx)),

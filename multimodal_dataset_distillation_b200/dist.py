@@ -85,7 +85,7 @@ class CudaBackend:
         self.ops = ops
 
     def scores(self, img, txt_shard, scale):
-        return self.ops.sim_scores(img, txt_shard, scale)
+        return self.ops.sim_scores(img, txt_shard, scale, want_t2i=False)[0]        # one GEMM: [I, T_r]
 
     def best_gt(self, s_i2t, lo, gt_ptr, gt_idx):
         return self.ops.rank_best_gt(s_i2t, lo, gt_ptr, gt_idx)
@@ -93,14 +93,8 @@ class CudaBackend:
     def count(self, s_i2t, lo, thr_s, thr_i):
         return self.ops.rank_count(s_i2t, lo, thr_s, thr_i)
 
-    def ranks_t2i(self, s_t2i, txt2img_shard):
-        n_txt_local, n_img = s_t2i.shape
-        _, r = self.ops.ranks_from_scores(None, s_t2i, txt2img_shard, gt_ptr_dummy(s_t2i.device), gt_ptr_dummy(s_t2i.device))
-        return r
-
-
-def gt_ptr_dummy(device):
-    return torch.zeros(2, dtype=torch.int32, device=device)
+    def ranks_t2i(self, s_i2t, txt2img_shard):
+        return self.ops.ranks_cols(s_i2t, txt2img_shard)        # a caption's column is complete locally (images replicated)
 
 
 def sharded_ranks(img, txt_shard, lo: int, txt2img_shard, img2txt_ptr, img2txt_idx, scale: float, group=None,
@@ -111,8 +105,8 @@ def sharded_ranks(img, txt_shard, lo: int, txt2img_shard, img2txt_ptr, img2txt_i
     img2txt CSR with GLOBAL caption indices.
     """
     be = backend or CudaBackend()
-    s_i2t, s_t2i = be.scores(img, txt_shard, scale)
-    ranks_t = be.ranks_t2i(s_t2i, txt2img_shard)
+    s_i2t = be.scores(img, txt_shard, scale)
+    ranks_t = be.ranks_t2i(s_i2t, txt2img_shard)
     cand_s, cand_i = be.best_gt(s_i2t, lo, img2txt_ptr, img2txt_idx)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world > 1:

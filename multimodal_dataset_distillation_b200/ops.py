@@ -139,6 +139,15 @@ def ranks_from_scores(scores_i2t, scores_t2i, txt2img: torch.Tensor, img2txt_ptr
     return (r1 if s1 is not None else None), (r2 if s2 is not None else None)
 
 
+def ranks_cols(scores_i2t: torch.Tensor, txt2img: torch.Tensor) -> torch.Tensor:
+    """Text->image ranks read column-wise from the image->text matrix [I, T] (T may be a caption shard)."""
+    s = _req(scores_i2t, "scores_i2t")
+    I, T = s.shape
+    out = torch.empty(T, dtype=torch.int32, device=s.device)
+    check(lib().vldd_ranks_cols(_ptr(s), I, T, _ptr(_req(txt2img, "txt2img", torch.int32)), _ptr(out), _stream()), "ranks_cols")
+    return out
+
+
 def rank_best_gt(scores: torch.Tensor, col_offset: int, gt_ptr: torch.Tensor, gt_idx: torch.Tensor):
     """Best local ground-truth candidate per row of a column shard: (score[rows] f32, global index[rows] i32)."""
     s = _req(scores, "scores")

@@ -26,7 +26,7 @@ class NumpyBackend:
 
     def scores(self, img, txt_shard, scale):
         S = (np.float32(scale) * img.numpy()) @ txt_shard.numpy().T
-        return torch.from_numpy(S.astype(np.float32)), torch.from_numpy(np.ascontiguousarray(S.T).astype(np.float32))
+        return torch.from_numpy(S.astype(np.float32))
 
     def best_gt(self, s_i2t, lo, gt_ptr, gt_idx):
         S, ptr, idx = s_i2t.numpy(), gt_ptr.numpy(), gt_idx.numpy()
@@ -50,8 +50,8 @@ class NumpyBackend:
                 out[r] = np.count_nonzero(S[r] > float(thr_s[r])) + np.count_nonzero((S[r] == float(thr_s[r])) & (cols < int(thr_i[r])))
         return torch.from_numpy(out)
 
-    def ranks_t2i(self, s_t2i, txt2img_shard):
-        return torch.from_numpy(RR.ranks_t2i(s_t2i.numpy(), txt2img_shard.numpy()))
+    def ranks_t2i(self, s_i2t, txt2img_shard):
+        return torch.from_numpy(RR.ranks_t2i(np.ascontiguousarray(s_i2t.numpy().T), txt2img_shard.numpy()))
 
 
 def _make_case(seed, n_img, caps, dim, quant):

@@ -162,15 +162,17 @@ def test_caption_sharded_ranks_match_single_gpu(world):
     cands, shards = [], []
     for r in range(world):
         lo, hi = D.shard_bounds(T, world, r)
-        s1, s2 = be.scores(dev(img), dev(txt[lo:hi].copy()), 14.285714)
+        s1 = be.scores(dev(img), dev(txt[lo:hi].copy()), 14.285714)
         assert torch.equal(s1, s_full[:, lo:hi])                        # same arithmetic per element regardless of tiling
-        shards.append((lo, hi, s1, s2))
+        shards.append((lo, hi, s1, None))
         cands.append(be.best_gt(s1, lo, dev(ptr), dev(idx)))
     thr_s, thr_i = D.merge_candidates(torch.stack([c[0] for c in cands]), torch.stack([c[1] for c in cands]))
     counts = sum(be.count(s1, lo, thr_s, thr_i) for lo, hi, s1, s2 in shards)
     assert torch.equal(counts, ref_i)
-    got_t = torch.cat([be.ranks_t2i(s2, dev(t2i[lo:hi].copy())) for lo, hi, s1, s2 in shards])
-    assert torch.equal(got_t, ref_t)
+    got_t = torch.cat([be.ranks_t2i(s1, dev(t2i[lo:hi].copy())) for lo, hi, s1, s2 in shards])
+    ref_t_cols = ops.ranks_cols(s_full, dev(t2i))
+    assert torch.equal(got_t, ref_t_cols)
+    assert (got_t != ref_t).float().mean() < 0.05        # ref_t ranks the separately computed transpose GEMM (rounding near ties)
 
 
 @pytest.mark.parametrize("I,T,D", [(1, 1, 4), (3, 7, 8), (37, 300, 20), (300, 37, 12), (513, 1030, 64)])
