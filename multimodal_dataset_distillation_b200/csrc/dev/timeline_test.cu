@@ -19,10 +19,10 @@ static void report(const char* name, int nctas) {
   std::vector<long long> tl(148 * 10 * 16);
   CK(cudaMemcpyFromSymbol(tl.data(), tc::g_timeline, tl.size() * 8));
   long long t0 = (1ll << 62);
-  for (int c = 0; c < nctas; ++c) if (tl[(c * 8 + 0) * 16 + 0] && tl[(c * 8 + 0) * 16 + 0] < t0) t0 = tl[(c * 8 + 0) * 16 + 0];
+  for (int c = 0; c < nctas; ++c) if (tl[(c * 10 + 0) * 16 + 0] && tl[(c * 10 + 0) * 16 + 0] < t0) t0 = tl[(c * 10 + 0) * 16 + 0];
   printf("%s (ns since first CTA start; cta: start prologue_done | producer first_issue all_issued | mma first_ready last_commit | splitter first_full first_done all_done | epi tmem_full done | exit)\n", name);
   for (int c : {0, 1, nctas / 2, nctas - 1}) {
-    auto T = [&](int w, int s) { long long v = tl[(c * 8 + w) * 16 + s]; return v ? (long long)(v - t0) : -1ll; };
+    auto T = [&](int w, int s) { long long v = tl[(c * 10 + w) * 16 + s]; return v ? (long long)(v - t0) : -1ll; };
     printf("  cta %3d: %6lld %6lld | %6lld %6lld | %6lld %6lld | %6lld %6lld %6lld | %6lld %6lld | %6lld\n", c, T(0, 0), T(0, 2), T(0, 3), T(0, 4),
            T(1, 3), T(1, 4), T(2, 3), T(2, 4), T(2, 5), T(6, 6), T(6, 7), T(0, 8));
   }

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gemm_dispatch.cuh"
 #include "head_kernels.cuh"
+#include "nce_cluster.cuh"
 #include "row_kernels_v4.cuh"
 #include "kernels.h"
 #include "engine.h"
@@ -147,6 +148,9 @@ int zero_square_matrices(const Dims& m, Work& w, cudaStream_t st) {
   return VLDD_OK;
 }
 
+// grid of the element-wise kernels that take the 128-bit path when the row length allows (4 elements per thread)
+inline int ew_grid(size_t n);
+inline int ew_grid4(size_t n, int d) { return (d & 3) == 0 ? ew_grid(n / 4) : ew_grid(n); }
 inline int ew_grid(size_t n) {
   size_t g = (n + 255) / 256;
   const size_t cap = (size_t)kNumSMs * 8;
@@ -154,6 +158,27 @@ inline int ew_grid(size_t n) {
 }
 
 #define CHECK_RC(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+// InfoNCE as one cluster launch (nce_cluster.cuh) is opt-in, VLDD_NCE=cluster.  Measured on B200 at the Flickr shape
+// (bench.py, ms / iteration): three / four small launches 1.906, one 8-CTA cluster launch 1.936 -- the 36-slab logits
+// reduction (1.4 MB from L2) is spread over 100 SMs by the row kernels but over only 8 by the cluster, and under
+// programmatic dependent launch consecutive small kernels cost little more than their execution time.
+bool nce_fused(int B, int ld) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("VLDD_NCE");
+    mode = (e && strcmp(e, "cluster") == 0) ? 1 : 0;
+    if (mode == 1) {
+      const int cap = 200 * 1024;
+      if (cudaFuncSetAttribute(nce_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap) != cudaSuccess ||
+          cudaFuncSetAttribute(nce_t_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap) != cudaSuccess) {
+        cudaGetLastError();
+        mode = 0;
+      }
+    }
+  }
+  return mode == 1 && nce_cluster_ok(B, ld);
+}
 
 // VLDD_PROFILE=1: serialise everything on one stream and time every launch with events (developer aid; prints a
 // per-call-site table to stderr at the end of vldd_unrolled_match).
@@ -246,7 +271,7 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   int sp = 1;
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, W1, dt, B, d, dt), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,true> A=s.Yb", st);
-  launch_k(epi_p_kernel, ew_grid(Bd), 256, 0, st, w.pa, sp, Bd, b1, B, d, s.p, s.h);
+  launch_k(epi_p_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, b1, B, d, s.p, s.h);
   prof_mark("epi_p_kernel", st);
   // f = h W2^T + b2 ; r = mask f + p ; LN ; normalise
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.h, d, W2, d, B, d, d), w.pa, &sp, st)));
@@ -261,12 +286,18 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   // S = scale * Xb Yn^T ; lse ; G ; loss
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, s.yn, d, B, B, d), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,true> A=s.Xb", st);
-  launch_k(nce_rows_kernel, B, 128, 0, st, w.pa, sp, (size_t)B * B, scale, B, Bp, s.S, s.lse_r);
-  prof_mark("nce_rows_kernel", st);
-  launch_k(nce_cols_kernel, B, 128, 0, st, s.S, B, Bp, s.lse_c);
-  prof_mark("nce_cols_kernel", st);
-  launch_k(nce_grad_kernel, B, 128, 0, st, s.S, s.lse_r, s.lse_c, B, Bp, s.G, ce_out);
-  prof_mark("nce_grad_kernel", st);
+  if (nce_fused(B, Bp)) {
+    launch_cluster_k(nce_cluster_kernel, kNceCluster, kNceThreads, nce_cluster_smem_bytes(B, Bp), st, w.pa, sp, (size_t)B * B,
+                     scale, B, Bp, s.S, s.lse_r, s.lse_c, s.G, ce_out);
+    prof_mark("nce_cluster_kernel", st);
+  } else {
+    launch_k(nce_rows_kernel, B, 128, 0, st, w.pa, sp, (size_t)B * B, scale, B, Bp, s.S, s.lse_r);
+    prof_mark("nce_rows_kernel", st);
+    launch_k(nce_cols_kernel, B, 128, 0, st, s.S, B, Bp, s.lse_c);
+    prof_mark("nce_cols_kernel", st);
+    launch_k(nce_grad_kernel, B, 128, 0, st, s.S, s.lse_r, s.lse_c, B, Bp, s.G, ce_out);
+    prof_mark("nce_grad_kernel", st);
+  }
   // dyn_raw[j,:] = sum_i G[i,j] Xb[i,:]
   // (G is stored with leading dimension Bp and zero padding columns: rows B..Bp-1 of the product are zeros)
   CHECK_RC((gemm_store<false, false>(gemm_ops(s.G, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st)));
@@ -287,7 +318,7 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   // dh = df W2 ; dp = dh gelu'(p) + dr
   CHECK_RC((gemm_partial<true, false>(gemm_ops(s.df, d, W2, d, B, d, d), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,false> A=s.df", st);
-  launch_k(epi_dp_kernel, ew_grid(Bd), 256, 0, st, w.pa, sp, Bd, s.p, s.dr, Bd, s.dh, s.dp);
+  launch_k(epi_dp_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, s.p, s.dr, Bd, s.dh, s.dp);
   prof_mark("epi_dp_kernel", st);
   // branch 2: theta_{k+1}[W1] = theta_k[W1] - lr dp^T Yb ;  main: small params
   CHECK_RC(lane_edge(st, L.s2));
@@ -319,7 +350,7 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   int sp = 1;
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,true> A=s.Yb", st);
-  launch_k(epi_pd_kernel, ew_grid(Bd), 256, 0, st, w.pa, sp, Bd, c1, s.p, B, d, w.pd, w.hd);
+  launch_k(epi_pd_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, c1, s.p, B, d, w.pd, w.hd);
   prof_mark("epi_pd_kernel", st);
   // fd = hd W2^T + h V2^T + c2 ; LN / normalise tangents
   CHECK_RC((gemm_partial<true, true>(gemm_ops2(w.hd, d, W2, d, d, s.h, d, V2, d, d, B, d), w.pa, &sp, st)));
@@ -334,12 +365,19 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   // Sd = scale Xb Ynd^T ; rho, kappa, Gd ; L_dot ; dlr, dscale
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, w.ynd, d, B, B, d), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,true> A=s.Xb", st);
-  launch_k(nce_t_rows_kernel, B, 128, 0, st, w.pa, sp, (size_t)B * B, scale, s.S, s.lse_r, s.G, B, Bp, w.Sd, w.rho, w.rowA);
-  prof_mark("nce_t_rows_kernel", st);
-  launch_k(nce_t_cols_kernel, B, 128, 0, st, s.S, s.lse_c, w.Sd, B, Bp, w.kap);
-  prof_mark("nce_t_cols_kernel", st);
-  launch_k(nce_t_grad_kernel, B, 128, 0, st, s.S, s.lse_r, s.lse_c, w.Sd, w.rho, w.kap, B, Bp, w.Gd, w.rowB);
-  prof_mark("nce_t_grad_kernel", st);
+  const bool fused_nce = nce_fused(B, Bp);
+  if (fused_nce) {
+    launch_cluster_k(nce_t_cluster_kernel, kNceCluster, kNceThreads, nce_cluster_smem_bytes(B, Bp), st, w.pa, sp,
+                     (size_t)B * B, scale, s.S, s.lse_r, s.lse_c, s.G, B, Bp, w.Gd, lr, dlr, dscale);
+    prof_mark("nce_t_cluster_kernel", st);
+  } else {
+    launch_k(nce_t_rows_kernel, B, 128, 0, st, w.pa, sp, (size_t)B * B, scale, s.S, s.lse_r, s.G, B, Bp, w.Sd, w.rho, w.rowA);
+    prof_mark("nce_t_rows_kernel", st);
+    launch_k(nce_t_cols_kernel, B, 128, 0, st, s.S, s.lse_c, w.Sd, B, Bp, w.kap);
+    prof_mark("nce_t_cols_kernel", st);
+    launch_k(nce_t_grad_kernel, B, 128, 0, st, s.S, s.lse_r, s.lse_c, w.Sd, w.rho, w.kap, B, Bp, w.Gd, w.rowB);
+    prof_mark("nce_t_grad_kernel", st);
+  }
   // branch 1: dXn_dot = scale (Gd Yn + G Ynd)  ->  dXn[perm] -= lr * scale * raw
   CHECK_RC(lane_edge(st, L.s1));
   L.s1_busy = true;
@@ -347,8 +385,10 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   prof_mark("gemm_store<true,false> A=w.Gd", L.s1);
   launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pc, 1, Bd, perm, d, lr, scale, w.dXn);
   prof_mark("scatter_add_rows_kernel", L.s1);
-  launch_k(nce_t_finish_kernel, 1, 128, 0, st, w.rowA, w.rowB, B, lr, scale, dlr, dscale);
-  prof_mark("nce_t_finish_kernel", st);
+  if (!fused_nce) {
+    launch_k(nce_t_finish_kernel, 1, 128, 0, st, w.rowA, w.rowB, B, lr, scale, dlr, dscale);
+    prof_mark("nce_t_finish_kernel", st);
+  }
   // dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
   CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st)));
   prof_mark("gemm_store<false,false> A=w.Gd", st);
@@ -369,7 +409,7 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   // dhd = dfd W2 + df V2 ; dpd
   CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), w.pa, &sp, st)));
   prof_mark("gemm_partial<true,false> A=w.dfd", st);
-  launch_k(epi_dpd_kernel, ew_grid(Bd), 256, 0, st, w.pa, sp, Bd, s.p, w.pd, s.dh, w.drd, Bd, w.dpd);
+  launch_k(epi_dpd_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, s.p, w.pd, s.dh, w.drd, Bd, w.dpd);
   prof_mark("epi_dpd_kernel", st);
   // branch 1 (after dXn): dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.)
   CHECK_RC(lane_edge(st, L.s1));
@@ -609,7 +649,7 @@ int proj_head_forward(const float* theta, const float* Y, const float* mask, int
   float* part = h + Rd;
   int sp = 1;
   CHECK_RC((gemm_partial<true, true>(gemm_ops(Y, dt, theta + m.oW1, dt, rows, d, dt), part, &sp, st)));
-  launch_k(epi_p_kernel, ew_grid(Rd), 256, 0, st, part, sp, Rd, theta + m.ob1, rows, d, p, h);
+  launch_k(epi_p_kernel, ew_grid4(Rd, d), 256, 0, st, part, sp, Rd, theta + m.ob1, rows, d, p, h);
   CHECK_RC((gemm_partial<true, true>(gemm_ops(h, d, theta + m.oW2, d, rows, d, d), part, &sp, st)));
   if (row_v4_ok(d))
     VLDD_ROW_V4_DISPATCH(d, ln_fwd_v4_kernel, (rows, 256, 0, st), (part, sp, Rd, theta + m.ob2, mask, p, theta + m.og,

@@ -14,23 +14,73 @@ namespace vldd {
 
 constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default (networks.py:637)
 
+// float4 helpers (shared with row_kernels_v4.cuh)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 operator*(float a, float4 b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
+
+// Slab sums.  These kernels are latency-bound (a few hundred KB per launch, L2-resident), so what matters is how many
+// L2 round trips sit on the critical path: every variant issues ALL its slab loads before the first addition
+// (predicated, fully unrolled up to kMaxSlabsMlp) and then adds in the fixed order s = 0, 1, 2, ... -- the same
+// association as a plain sequential loop, so results do not depend on which variant ran.
+constexpr int kMaxSlabsMlp = 8;      // tc::pick_splits never exceeds 8 for the skinny weight GEMMs (18 tiles on 148 SMs)
+
 __device__ __forceinline__ float sum_slabs(const float* __restrict__ part, int splits, size_t stride, size_t idx) {
+  if (splits <= kMaxSlabsMlp) {
+    float t[kMaxSlabsMlp];
+#pragma unroll
+    for (int s = 0; s < kMaxSlabsMlp; ++s) t[s] = s < splits ? part[(size_t)s * stride + idx] : 0.f;
+    float v = t[0];
+#pragma unroll
+    for (int s = 1; s < kMaxSlabsMlp; ++s) v += t[s];
+    return v;
+  }
   float v = part[idx];
   for (int s = 1; s < splits; ++s) v += part[(size_t)s * stride + idx];
   return v;
 }
-// same sum with four independent accumulators (fixed association, still deterministic): for the 36-slab logits GEMM
-__device__ __forceinline__ float sum_slabs_ilp(const float* __restrict__ part, int splits, size_t stride, size_t idx) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int s = 0;
-  for (; s + 3 < splits; s += 4) {
-    a0 += part[(size_t)(s + 0) * stride + idx];
-    a1 += part[(size_t)(s + 1) * stride + idx];
-    a2 += part[(size_t)(s + 2) * stride + idx];
-    a3 += part[(size_t)(s + 3) * stride + idx];
+__device__ __forceinline__ float4 sum_slabs4(const float* __restrict__ part, int splits, size_t stride, size_t idx) {
+  if (splits <= kMaxSlabsMlp) {
+    float4 t[kMaxSlabsMlp];
+#pragma unroll
+    for (int s = 0; s < kMaxSlabsMlp; ++s) t[s] = s < splits ? ld4(part + (size_t)s * stride + idx) : f4(0.f);
+    float4 v = t[0];
+#pragma unroll
+    for (int s = 1; s < kMaxSlabsMlp; ++s) v = v + t[s];
+    return v;
   }
-  for (; s < splits; ++s) a0 += part[(size_t)s * stride + idx];
-  return (a0 + a1) + (a2 + a3);
+  float4 v = ld4(part + idx);
+  for (int s = 1; s < splits; ++s) v = v + ld4(part + (size_t)s * stride + idx);
+  return v;
+}
+// Sum with four interleaved accumulators (slab s goes to accumulator s % 4, the tail beyond the last multiple of four
+// to accumulator 0; result (a0 + a1) + (a2 + a3)), loads issued twelve at a time: for the 36-slab logits GEMM.
+__device__ __forceinline__ float sum_slabs_ilp(const float* __restrict__ part, int splits, size_t stride, size_t idx) {
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  const int n4 = splits & ~3;
+  for (int s0 = 0; s0 < splits; s0 += 12) {
+    float t[12];
+#pragma unroll
+    for (int u = 0; u < 12; ++u) t[u] = (s0 + u < splits) ? part[(size_t)(s0 + u) * stride + idx] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 12; ++u) {
+      if (s0 + u < n4) a[u & 3] += t[u];
+      else a[0] += t[u];                        // tail slabs (and the zeros past `splits`)
+    }
+  }
+  return (a[0] + a[1]) + (a[2] + a[3]);
+}
+
+// 128-bit path of the element-wise kernels: every pointer 16-byte aligned, row length and slab stride multiples of 4
+__device__ __forceinline__ bool vec4_ok(int d, size_t stride, const void* a, const void* b = nullptr, const void* c = nullptr,
+                                        const void* e = nullptr, const void* f = nullptr, const void* g = nullptr) {
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                         reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(g);
+  return (d & 3) == 0 && (stride & 3) == 0 && (bits & 15) == 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -42,6 +92,20 @@ __global__ void __launch_bounds__(256) epi_p_kernel(const float* __restrict__ pa
                                                     float* __restrict__ p, float* __restrict__ h) {
   pdl_enter();
   const size_t n = (size_t)rows * d;
+  if (vec4_ok(d, stride, part, b1, p, h)) {
+    for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+      const float4 pv = sum_slabs4(part, splits, stride, i) + ld4(b1 + (int)(i % d));
+      float4 hv;
+      float d1, d2;
+      gelu_parts(pv.x, hv.x, d1, d2);
+      gelu_parts(pv.y, hv.y, d1, d2);
+      gelu_parts(pv.z, hv.z, d1, d2);
+      gelu_parts(pv.w, hv.w, d1, d2);
+      st4(p + i, pv);
+      st4(h + i, hv);
+    }
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % d);
     const float pv = sum_slabs(part, splits, stride, i) + b1[c];
@@ -176,11 +240,7 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
   if ((cols & 3) == 0 && (stride & 3) == 0 &&
       ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
     for (int j = threadIdx.x; j < (cols >> 2); j += blockDim.x) {
-      float4 v = *reinterpret_cast<const float4*>(part + s + 4 * j);
-      for (int z = 1; z < splits; ++z) {
-        const float4 u = *reinterpret_cast<const float4*>(part + (size_t)z * stride + s + 4 * j);
-        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-      }
+      const float4 v = sum_slabs4(part, splits, stride, s + 4 * j);
       float4 o = *reinterpret_cast<float4*>(dst + t + 4 * j);
       o.x += coef * v.x; o.y += coef * v.y; o.z += coef * v.z; o.w += coef * v.w;
       *reinterpret_cast<float4*>(dst + t + 4 * j) = o;
@@ -296,6 +356,20 @@ __global__ void __launch_bounds__(256) epi_dp_kernel(const float* __restrict__ p
                                                      const float* __restrict__ p, const float* __restrict__ dr,
                                                      size_t n, float* __restrict__ dh, float* __restrict__ dp) {
   pdl_enter();
+  if (vec4_ok((int)(n & 3), stride, part, p, dr, dh, dp)) {
+    for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+      const float4 v = sum_slabs4(part, splits, stride, i), pv = ld4(p + i), drv = ld4(dr + i);
+      float phi, d2;
+      float4 d1;
+      gelu_parts(pv.x, phi, d1.x, d2);
+      gelu_parts(pv.y, phi, d1.y, d2);
+      gelu_parts(pv.z, phi, d1.z, d2);
+      gelu_parts(pv.w, phi, d1.w, d2);
+      st4(dh + i, v);
+      st4(dp + i, make_float4(fmaf(v.x, d1.x, drv.x), fmaf(v.y, d1.y, drv.y), fmaf(v.z, d1.z, drv.z), fmaf(v.w, d1.w, drv.w)));
+    }
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = sum_slabs(part, splits, stride, i);
     float phi, d1, d2;
@@ -352,6 +426,20 @@ __global__ void __launch_bounds__(256) epi_pd_kernel(const float* __restrict__ p
                                                      int d, float* __restrict__ pd, float* __restrict__ hd) {
   pdl_enter();
   const size_t n = (size_t)rows * d;
+  if (vec4_ok(d, stride, part, c1, p, pd, hd)) {
+    for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+      const float4 v = sum_slabs4(part, splits, stride, i) + ld4(c1 + (int)(i % d)), pv = ld4(p + i);
+      float phi, d2;
+      float4 d1;
+      gelu_parts(pv.x, phi, d1.x, d2);
+      gelu_parts(pv.y, phi, d1.y, d2);
+      gelu_parts(pv.z, phi, d1.z, d2);
+      gelu_parts(pv.w, phi, d1.w, d2);
+      st4(pd + i, v);
+      st4(hd + i, d1 * v);
+    }
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % d);
     const float v = sum_slabs(part, splits, stride, i) + c1[c];
@@ -539,6 +627,21 @@ __global__ void __launch_bounds__(256) epi_dpd_kernel(const float* __restrict__ 
                                                       const float* __restrict__ dh, const float* __restrict__ drd,
                                                       size_t n, float* __restrict__ dpd) {
   pdl_enter();
+  if (vec4_ok((int)(n & 3), stride, part, p, pd, dh, drd, dpd)) {
+    for (size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i < n; i += 4 * (size_t)gridDim.x * blockDim.x) {
+      const float4 v = sum_slabs4(part, splits, stride, i), pv = ld4(p + i), pdv = ld4(pd + i), dhv = ld4(dh + i),
+                   drv = ld4(drd + i);
+      float phi;
+      float4 d1, d2;
+      gelu_parts(pv.x, phi, d1.x, d2.x);
+      gelu_parts(pv.y, phi, d1.y, d2.y);
+      gelu_parts(pv.z, phi, d1.z, d2.z);
+      gelu_parts(pv.w, phi, d1.w, d2.w);
+      st4(dpd + i, make_float4(fmaf(v.x, d1.x, fmaf(dhv.x * d2.x, pdv.x, drv.x)), fmaf(v.y, d1.y, fmaf(dhv.y * d2.y, pdv.y, drv.y)),
+                               fmaf(v.z, d1.z, fmaf(dhv.z * d2.z, pdv.z, drv.z)), fmaf(v.w, d1.w, fmaf(dhv.w * d2.w, pdv.w, drv.w))));
+    }
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = sum_slabs(part, splits, stride, i);
     float phi, d1, d2;

@@ -6,21 +6,8 @@
 
 namespace vldd {
 
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float4 f4(float a) { return make_float4(a, a, a, a); }
-__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
-__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
-__device__ __forceinline__ float4 operator*(float a, float4 b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
 __device__ __forceinline__ float hsum(float4 a) { return (a.x + a.y) + (a.z + a.w); }
 __device__ __forceinline__ float hdot(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
-
-__device__ __forceinline__ float4 sum_slabs4(const float* __restrict__ part, int splits, size_t stride, size_t idx) {
-  float4 v = ld4(part + idx);
-  for (int s = 1; s < splits; ++s) v = v + ld4(part + (size_t)s * stride + idx);
-  return v;
-}
 
 // two simultaneous block sums (one barrier round trip instead of two)
 __device__ __forceinline__ float2 block_sum2(float a, float b, float2* scratch) {
@@ -37,6 +24,39 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* scratch) 
 }
 __device__ __forceinline__ float block_sum1(float a, float2* scratch) { return block_sum2(a, 0.f, scratch).x; }
 
+// These kernels are latency-bound (100 rows x 9 KB, L2-resident): what they cost is the number of dependent L2 round
+// trips.  Every operand a later phase needs is therefore loaded up front, next to the slab loads (predicated 128-bit
+// loads, all in flight together; ~150 registers per thread at NV = 3, one CTA per SM anyway), so that after each block
+// reduction only arithmetic and stores remain.
+#define VLDD_LDP(ok, ptr) ((ok) ? ld4(ptr) : f4(0.f))
+
+// acc[i] = sum over slabs of element (base + 4 * (threadIdx.x + 256 i)), all NV x splits loads issued before the first add
+template <int NV>
+__device__ __forceinline__ void load_slab_rows(float4 (&acc)[NV], const float* __restrict__ part, int splits, size_t stride,
+                                               size_t base, int d4) {
+  if (splits <= kMaxSlabsMlp) {
+    float4 t[NV][kMaxSlabsMlp];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = threadIdx.x + 256 * i;
+#pragma unroll
+      for (int z = 0; z < kMaxSlabsMlp; ++z) t[i][z] = VLDD_LDP(j < d4 && z < splits, part + (size_t)z * stride + base + 4 * j);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      acc[i] = t[i][0];
+#pragma unroll
+      for (int z = 1; z < kMaxSlabsMlp; ++z) acc[i] = acc[i] + t[i][z];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = threadIdx.x + 256 * i;
+      acc[i] = j < d4 ? sum_slabs4(part, splits, stride, base + 4 * j) : f4(0.f);
+    }
+  }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_v4_kernel(const float* __restrict__ part, int splits, size_t stride,
                                                         const float* __restrict__ b2, const float* __restrict__ mask,
@@ -48,17 +68,29 @@ __global__ void __launch_bounds__(256) ln_fwd_v4_kernel(const float* __restrict_
   __shared__ float2 scratch[32];
   const int row = blockIdx.x, d4 = d >> 2;
   const size_t base = (size_t)row * d;
-  float4 r[NV];
+  float4 r[NV], bb[NV], mk[NV], pp[NV], gm[NV], bt[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = threadIdx.x + 256 * i;
+    const bool ok = j < d4;
+    bb[i] = VLDD_LDP(ok, b2 + 4 * j);
+    mk[i] = VLDD_LDP(ok && mask != nullptr, mask + base + 4 * j);
+    pp[i] = VLDD_LDP(ok, p + base + 4 * j);
+    gm[i] = VLDD_LDP(ok, gamma + 4 * j);
+    bt[i] = VLDD_LDP(ok, beta + 4 * j);
+  }
+  load_slab_rows<NV>(r, part, splits, stride, base, d4);
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int j = threadIdx.x + 256 * i;
-    r[i] = f4(0.f);
     if (j < d4) {
-      float4 f = sum_slabs4(part, splits, stride, base + 4 * j) + ld4(b2 + 4 * j);
-      if (mask) f = f * ld4(mask + base + 4 * j);
-      r[i] = f + ld4(p + base + 4 * j);
+      float4 f = r[i] + bb[i];
+      if (mask) f = f * mk[i];
+      r[i] = f + pp[i];
       s += hsum(r[i]);
+    } else {
+      r[i] = f4(0.f);
     }
   }
   const float mu = block_sum1(s, scratch) / d;
@@ -76,7 +108,7 @@ __global__ void __launch_bounds__(256) ln_fwd_v4_kernel(const float* __restrict_
     if (j < d4) {
       const float4 rh = rstd * r[i];
       if (rhat) st4(rhat + base + 4 * j, rh);
-      r[i] = ld4(gamma + 4 * j) * rh + ld4(beta + 4 * j);
+      r[i] = gm[i] * rh + bt[i];
       zz += hdot(r[i], r[i]);
     }
   }
@@ -107,16 +139,24 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_v4_kernel(const float* __rest
   __shared__ float2 scratch[32];
   const int row = blockIdx.x, d4 = d >> 2;
   const size_t base = (size_t)row * d;
+  float4 a[NV], y[NV], rh[NV], gm[NV], mk[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = threadIdx.x + 256 * i;
+    const bool ok = j < d4;
+    a[i] = VLDD_LDP(ok, raw + base + 4 * j);
+    y[i] = VLDD_LDP(ok, yn + base + 4 * j);
+    rh[i] = VLDD_LDP(ok, rhat + base + 4 * j);
+    gm[i] = VLDD_LDP(ok, gamma + 4 * j);
+    mk[i] = VLDD_LDP(ok && mask != nullptr, mask + base + 4 * j);
+  }
   const float sc = *scale, inz = 1.0f / nz_p[row], rstd = rstd_p[row];
-  float4 a[NV], y[NV], rh[NV];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int j = threadIdx.x + 256 * i;
     if (j < d4) {
-      a[i] = sc * ld4(raw + base + 4 * j);
-      y[i] = ld4(yn + base + 4 * j);
-      rh[i] = ld4(rhat + base + 4 * j);
+      a[i] = sc * a[i];
       st4(dyn + base + 4 * j, a[i]);
       s += hdot(y[i], a[i]);
     }
@@ -129,7 +169,7 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_v4_kernel(const float* __rest
     if (j < d4) {
       const float4 dzv = inz * (a[i] - q * y[i]);
       st4(dz + base + 4 * j, dzv);
-      a[i] = ld4(gamma + 4 * j) * dzv;     // drhat
+      a[i] = gm[i] * dzv;     // drhat
       s1 += hsum(a[i]);
       s2 += hdot(a[i], rh[i]);
     }
@@ -142,7 +182,7 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_v4_kernel(const float* __rest
     if (j < d4) {
       const float4 v = rstd * (a[i] - f4(m1) - m2 * rh[i]);
       st4(dr + base + 4 * j, v);
-      st4(df + base + 4 * j, mask ? v * ld4(mask + base + 4 * j) : v);
+      st4(df + base + 4 * j, mask ? v * mk[i] : v);
     }
   }
   if (threadIdx.x == 0) q_out[row] = q;
@@ -161,18 +201,30 @@ __global__ void __launch_bounds__(256) ln_tangent_v4_kernel(const float* __restr
   __shared__ float2 scratch[32];
   const int row = blockIdx.x, d4 = d >> 2;
   const size_t base = (size_t)row * d;
+  float4 rd[NV], rh[NV], y[NV], cc[NV], mk[NV], pp[NV], gm[NV], gd[NV], bd[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = threadIdx.x + 256 * i;
+    const bool ok = j < d4;
+    cc[i] = VLDD_LDP(ok, c2 + 4 * j);
+    mk[i] = VLDD_LDP(ok && mask != nullptr, mask + base + 4 * j);
+    pp[i] = VLDD_LDP(ok, pd + base + 4 * j);
+    rh[i] = VLDD_LDP(ok, rhat + base + 4 * j);
+    y[i] = VLDD_LDP(ok, yn + base + 4 * j);
+    gm[i] = VLDD_LDP(ok, gamma + 4 * j);
+    gd[i] = VLDD_LDP(ok, gammad + 4 * j);
+    bd[i] = VLDD_LDP(ok, betad + 4 * j);
+  }
+  load_slab_rows<NV>(rd, part, splits, stride, base, d4);
   const float rstd = rstd_p[row], nz = nz_p[row];
-  float4 rd[NV], rh[NV], y[NV];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int j = threadIdx.x + 256 * i;
     if (j < d4) {
-      float4 f = sum_slabs4(part, splits, stride, base + 4 * j) + ld4(c2 + 4 * j);
-      if (mask) f = f * ld4(mask + base + 4 * j);
-      rd[i] = f + ld4(pd + base + 4 * j);
-      rh[i] = ld4(rhat + base + 4 * j);
-      y[i] = ld4(yn + base + 4 * j);
+      float4 f = rd[i] + cc[i];
+      if (mask) f = f * mk[i];
+      rd[i] = f + pp[i];
       s1 += hsum(rd[i]);
       s2 += hdot(rh[i], rd[i]);
     }
@@ -186,7 +238,7 @@ __global__ void __launch_bounds__(256) ln_tangent_v4_kernel(const float* __restr
     if (j < d4) {
       const float4 rhd = rstd * (rd[i] - f4(mrd) - t * rh[i]);
       st4(rhatd + base + 4 * j, rhd);
-      rd[i] = ld4(gammad + 4 * j) * rh[i] + ld4(gamma + 4 * j) * rhd + ld4(betad + 4 * j);   // zd
+      rd[i] = gd[i] * rh[i] + gm[i] * rhd + bd[i];   // zd
       s3 += hdot(y[i], rd[i]);
     }
   }
@@ -215,35 +267,44 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_tangent_v4_kernel(
   __shared__ float2 scratch[32];
   const int row = blockIdx.x, d4 = d >> 2;
   const size_t base = (size_t)row * d;
+  float4 a[NV], y[NV], yd[NV], dy[NV], dzv[NV], gm[NV], gd[NV], rh[NV], rhd[NV], drv[NV], mk[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = threadIdx.x + 256 * i;
+    const bool ok = j < d4;
+    a[i] = VLDD_LDP(ok, raw + base + 4 * j);
+    y[i] = VLDD_LDP(ok, yn + base + 4 * j);
+    yd[i] = VLDD_LDP(ok, ynd + base + 4 * j);
+    dy[i] = VLDD_LDP(ok, dyn + base + 4 * j);
+    dzv[i] = VLDD_LDP(ok, dz + base + 4 * j);
+    gm[i] = VLDD_LDP(ok, gamma + 4 * j);
+    gd[i] = VLDD_LDP(ok, gammad + 4 * j);
+    rh[i] = VLDD_LDP(ok, rhat + base + 4 * j);
+    rhd[i] = VLDD_LDP(ok, rhatd + base + 4 * j);
+    drv[i] = VLDD_LDP(ok, dr + base + 4 * j);
+    mk[i] = VLDD_LDP(ok && mask != nullptr, mask + base + 4 * j);
+  }
   const float sc = *scale, nz = nz_p[row], nzd = nzd_p[row], q = q_p[row], rstd = rstd_p[row], t = t_p[row];
   const float inz = 1.0f / nz;
-  float4 a[NV], y[NV], yd[NV];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int j = threadIdx.x + 256 * i;
     if (j < d4) {
-      a[i] = sc * ld4(raw + base + 4 * j);           // dynd
-      y[i] = ld4(yn + base + 4 * j);
-      yd[i] = ld4(ynd + base + 4 * j);
-      s += hdot(yd[i], ld4(dyn + base + 4 * j)) + hdot(y[i], a[i]);
+      a[i] = sc * a[i];           // dynd
+      s += hdot(yd[i], dy[i]) + hdot(y[i], a[i]);
     }
   }
   const float qd = block_sum1(s, scratch);
-  float4 rh[NV], rhd[NV];
   float s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int j = threadIdx.x + 256 * i;
     if (j < d4) {
-      const float4 dzv = ld4(dz + base + 4 * j);
-      const float4 v = inz * (a[i] - q * yd[i] - qd * y[i]) - (nzd * inz) * dzv;
+      const float4 v = inz * (a[i] - q * yd[i] - qd * y[i]) - (nzd * inz) * dzv[i];
       st4(dzd + base + 4 * j, v);
-      const float4 g = ld4(gamma + 4 * j);
-      const float4 drh = g * dzv;
-      a[i] = ld4(gammad + 4 * j) * dzv + g * v;      // drhatd
-      rh[i] = ld4(rhat + base + 4 * j);
-      rhd[i] = ld4(rhatd + base + 4 * j);
+      const float4 drh = gm[i] * dzv[i];
+      a[i] = gd[i] * dzv[i] + gm[i] * v;      // drhatd
       s1 += hsum(a[i]);
       s2 += hdot(a[i], rh[i]) + hdot(drh, rhd[i]);
       s3 += hdot(drh, rh[i]);
@@ -256,9 +317,9 @@ __global__ void __launch_bounds__(256) norm_ln_bwd_tangent_v4_kernel(
   for (int i = 0; i < NV; ++i) {
     const int j = threadIdx.x + 256 * i;
     if (j < d4) {
-      const float4 v = (-(rstd * t)) * ld4(dr + base + 4 * j) + rstd * (a[i] - f4(m1d) - m2 * rhd[i] - m2d * rh[i]);
+      const float4 v = (-(rstd * t)) * drv[i] + rstd * (a[i] - f4(m1d) - m2 * rhd[i] - m2d * rh[i]);
       st4(drd + base + 4 * j, v);
-      st4(dfd + base + 4 * j, mask ? v * ld4(mask + base + 4 * j) : v);
+      st4(dfd + base + 4 * j, mask ? v * mk[i] : v);
     }
   }
 }
