@@ -122,6 +122,23 @@ int vldd_contrastive_step(const float* theta, const float* Y, const float* U, co
                           int B, int dt, int d, float* loss, float* g_theta, float* dY, float* dU, float* dscale,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* CLIPModel_full.forward from the encoder outputs on, with the gradients loss.backward() produces.   networks.py:866-889:
+ *   txt = text_projection(Y; theta) (868-870), row-normalise both (873-874), logits = scale * Xn Yn^T (877-878; the
+ *   reference passes scale = exp(log(1/0.07))), loss = (CE(logits) + CE(logits^T)) / 2 (881-882),
+ *   top1 = {#rows whose argmax is the diagonal, #columns whose argmax is the diagonal} (884-885; acc = (top1[0]+top1[1])/2).
+ * Same workspace and gradient outputs as vldd_contrastive_step; top1 may be NULL.   Used by epoch.py:59-98 (`epoch`). */
+int vldd_clip_loss(const float* theta, const float* Y, const float* U, const float* scale, const float* mask, int B, int dt,
+                   int d, float* loss, int32_t* top1, float* g_theta, float* dY, float* dU, float* dscale, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Nearest bank row per query by cosine similarity, first index on ties.   distill.py:89-95 (`nearest_neighbor`:
+ * sklearn cosine_similarity(query, database) + np.argmax per query; rows are L2-normalised, all-zero rows left as is).
+ * idx_out[n_query] int32; cos_out[n_query] (nullable) = the winning cosine.  Workspace holds the normalised copies and
+ * the [n_query, n_bank] cosine matrix. */
+size_t vldd_nearest_rows_workspace_bytes(int n_query, int n_bank, int dim);
+int vldd_nearest_rows(const float* query, const float* bank, int n_query, int n_bank, int dim, int32_t* idx_out,
+                      float* cos_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The whole inner loop of one expert segment and its backward.   distill.py:509-606:
  *   for k < K: idx = perms[k] (510-511); g = grad(InfoNCE(head(Y[idx]; theta_k), U[idx]), theta_k) (524-567);
  *              theta_{k+1} = theta_k - lr g (583);

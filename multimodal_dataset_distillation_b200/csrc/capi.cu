@@ -267,6 +267,31 @@ int vldd_contrastive_step(const float* theta, const float* Y, const float* U, co
                           S(stream));
 }
 
+int vldd_clip_loss(const float* theta, const float* Y, const float* U, const float* scale, const float* mask, int B, int dt,
+                   int d, float* loss, int32_t* top1, float* g_theta, float* dY, float* dU, float* dscale, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  VLDD_REQUIRE(theta && Y && U && scale && loss && g_theta, "clip_loss: null pointer");
+  return clip_loss(theta, Y, U, scale, mask, B, dt, d, loss, top1, g_theta, dY, dU, dscale, workspace, workspace_bytes,
+                   S(stream));
+}
+
+size_t vldd_nearest_rows_workspace_bytes(int n_query, int n_bank, int dim) {
+  return nearest_rows_workspace_bytes(n_query, n_bank, dim);
+}
+
+int vldd_nearest_rows(const float* query, const float* bank, int n_query, int n_bank, int dim, int32_t* idx_out,
+                      float* cos_out, void* workspace, size_t workspace_bytes, void* stream) {
+  VLDD_REQUIRE(n_query >= 0 && n_bank > 0 && dim > 0, "nearest_rows: bad sizes (n_query=%d n_bank=%d dim=%d)", n_query, n_bank, dim);
+  if (n_query == 0) return VLDD_OK;
+  VLDD_REQUIRE(query && bank && idx_out && workspace, "nearest_rows: null pointer");
+  if (workspace_bytes < nearest_rows_workspace_bytes(n_query, n_bank, dim)) {
+    set_error("nearest_rows: workspace too small: need %zu bytes, got %zu", nearest_rows_workspace_bytes(n_query, n_bank, dim),
+              workspace_bytes);
+    return VLDD_ERR_WORKSPACE;
+  }
+  return nearest_rows(query, bank, n_query, n_bank, dim, idx_out, cos_out, workspace, S(stream));
+}
+
 size_t vldd_bench_skinny_gemm_workspace_bytes(int M, int N, int K) { return skinny_gemm_workspace_bytes(M, N, K); }
 
 int vldd_bench_skinny_gemm(const float* A, const float* W, int M, int N, int K, float* partial, size_t partial_bytes,

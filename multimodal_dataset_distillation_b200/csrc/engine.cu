@@ -623,6 +623,44 @@ int contrastive_step(const float* theta, const float* Y, const float* U, const f
   return check_launch("contrastive_step");
 }
 
+// Top-1 retrieval hits inside the batch, both directions (networks.py:884-886: argmax over rows / columns of the logits
+// equals the diagonal index; torch.argmax returns the FIRST maximum, so a tie counts only for the lowest index).
+//   top1[0] = #{i : argmax_j S_ij == i}     top1[1] = #{j : argmax_i S_ij == j}
+__global__ void __launch_bounds__(128) nce_top1_kernel(const float* __restrict__ S, int B, int ld, int32_t* __restrict__ top1) {
+  pdl_enter();
+  __shared__ int scratch[34];
+  const int i = blockIdx.x;
+  const float sii = S[(size_t)i * ld + i];
+  int ahead_r = 0, ahead_c = 0;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    const float r = S[(size_t)i * ld + j], c = S[(size_t)j * ld + i];
+    ahead_r += (r > sii) || (r == sii && j < i);
+    ahead_c += (c > sii) || (c == sii && j < i);
+  }
+  ahead_r = block_sum<int>(ahead_r, scratch);
+  ahead_c = block_sum<int>(ahead_c, scratch);
+  if (threadIdx.x == 0) {
+    if (ahead_r == 0) atomicAdd(top1 + 0, 1);
+    if (ahead_c == 0) atomicAdd(top1 + 1, 1);
+  }
+}
+
+// CLIPModel_full.forward from the encoder outputs on (networks.py:866-889): text head, normalise, logits, symmetric
+// cross-entropy, top-1 counters -- plus the first-order gradients (what loss.backward() hands the two optimisers).
+int clip_loss(const float* theta, const float* Y, const float* U, const float* scale, const float* mask, int B, int dt,
+              int d, float* loss, int32_t* top1, float* g_theta, float* dY, float* dU, float* dscale, void* workspace,
+              size_t workspace_bytes, cudaStream_t st) {
+  CHECK_RC(contrastive_step(theta, Y, U, scale, mask, B, dt, d, loss, g_theta, dY, dU, dscale, workspace, workspace_bytes, st));
+  if (top1 != nullptr) {
+    const Dims m = make_dims(B, B, 1, dt, d);
+    Work w;
+    carve(w, m, workspace);
+    VLDD_CUDA(cudaMemsetAsync(top1, 0, 2 * sizeof(int32_t), st));
+    launch_k(nce_top1_kernel, B, 128, 0, st, (const float*)w.sv[0].S, B, m.Bp, top1);
+  }
+  return check_launch("clip_loss");
+}
+
 // text_projection forward over `rows` embeddings (eval-mode when mask == nullptr): z = LN(...), zn = z/|z|.
 //   reference: epoch_original.py:77-78 (text head over the cached BERT test embeddings, then normalise)
 size_t proj_head_workspace_bytes(int rows, int dt, int d) {

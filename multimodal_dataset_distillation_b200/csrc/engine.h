@@ -15,6 +15,9 @@ size_t contrastive_step_workspace_bytes(int B, int dt, int d);
 int contrastive_step(const float* theta, const float* Y, const float* U, const float* scale, const float* mask, int B,
                      int dt, int d, float* loss, float* g_theta, float* dY, float* dU, float* dscale, void* workspace,
                      size_t workspace_bytes, cudaStream_t st);
+int clip_loss(const float* theta, const float* Y, const float* U, const float* scale, const float* mask, int B, int dt,
+              int d, float* loss, int32_t* top1, float* g_theta, float* dY, float* dU, float* dscale, void* workspace,
+              size_t workspace_bytes, cudaStream_t st);
 size_t proj_head_workspace_bytes(int rows, int dt, int d);
 int proj_head_forward(const float* theta, const float* Y, const float* mask, int rows, int dt, int d, float* z,
                       float* zn, void* workspace, size_t workspace_bytes, cudaStream_t st);

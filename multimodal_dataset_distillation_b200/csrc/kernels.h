@@ -32,6 +32,9 @@ bool sim_rank_fused_ok(const float* img, const float* txt, int I, int T, int D);
 int sim_rank_fused(const float* img, const float* txt, int I, int T, int D, float scale, const int32_t* txt2img,
                    const int32_t* gt_ptr, const int32_t* gt_idx, int nnz, int32_t* ranks_i2t, int32_t* ranks_t2i,
                    void* workspace, cudaStream_t st);
+size_t nearest_rows_workspace_bytes(int Q, int T, int D);
+int nearest_rows(const float* query, const float* bank, int Q, int T, int D, int32_t* idx_out, float* cos_out,
+                 void* workspace, cudaStream_t st);
 int topk_fill_rows(const float* S, float* out, int nrows, int ncols, int k, float fill, cudaStream_t st);
 
 }  // namespace vldd

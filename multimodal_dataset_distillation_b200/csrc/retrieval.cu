@@ -259,6 +259,68 @@ int sim_scores(const float* img, const float* txt, int I, int T, int D, float sc
   return VLDD_OK;
 }
 
+// ---- nearest neighbour by cosine similarity (distill.py:89-95: sklearn cosine_similarity + np.argmax per query) ----------
+__global__ void __launch_bounds__(256) unit_rows_kernel(const float* __restrict__ x, int d, float* __restrict__ out) {
+  pdl_enter();
+  __shared__ float scratch[34];
+  const size_t base = (size_t)blockIdx.x * d;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) s = fmaf(x[base + j], x[base + j], s);
+  s = block_sum<float>(s, scratch);
+  // sklearn.preprocessing.normalize leaves all-zero rows unchanged (norm 0 -> divide by 1)
+  const float inv = s > 0.f ? 1.0f / sqrtf(s) : 1.0f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) out[base + j] = x[base + j] * inv;
+}
+// first index of the row maximum (np.argmax semantics), optionally the maximum itself
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ S, int64_t ld, int ncols,
+                                                          int32_t* __restrict__ idx_out, float* __restrict__ val_out) {
+  pdl_enter();
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const float* row = S + (size_t)blockIdx.x * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < ncols; j += blockDim.x) {
+    const float v = row[j];
+    if (v > best || (v == best && j < bi) || bi == 0x7fffffff) { best = v; bi = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sv[wid] = best; si[wid] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (si[w] != 0x7fffffff && (bi == 0x7fffffff || sv[w] > best || (sv[w] == best && si[w] < bi))) { best = sv[w]; bi = si[w]; }
+    idx_out[blockIdx.x] = bi == 0x7fffffff ? 0 : bi;
+    if (val_out) val_out[blockIdx.x] = best;
+  }
+}
+
+size_t nearest_rows_workspace_bytes(int Q, int T, int D) {
+  if (Q <= 0 || T <= 0 || D <= 0) return 0;
+  return ((size_t)Q * D + (size_t)T * D + (size_t)Q * T) * sizeof(float) + 3 * 256;
+}
+
+int nearest_rows(const float* query, const float* bank, int Q, int T, int D, int32_t* idx_out, float* cos_out,
+                 void* workspace, cudaStream_t st) {
+  auto align = [](size_t b) { return (b + 255) / 256 * 256; };
+  char* base = reinterpret_cast<char*>(workspace);
+  float* qn = reinterpret_cast<float*>(base);
+  float* bn = reinterpret_cast<float*>(base + align((size_t)Q * D * sizeof(float)));
+  float* S = reinterpret_cast<float*>(base + align((size_t)Q * D * sizeof(float)) + align((size_t)T * D * sizeof(float)));
+  launch_k(unit_rows_kernel, Q, 256, 0, st, query, D, qn);
+  launch_k(unit_rows_kernel, T, 256, 0, st, bank, D, bn);
+  int rc = sim_scores(qn, bn, Q, T, D, 1.0f, S, nullptr, st);
+  if (rc) return rc;
+  launch_k(argmax_rows_kernel, Q, 256, 0, st, (const float*)S, (int64_t)T, T, idx_out, cos_out);
+  return check_launch("nearest_rows");
+}
+
 // ---- fused similarity + ranking: the score matrix is never written to HBM --------------------------------------------
 // Two passes of the SAME tcgen05 GEMM kernel (bit-identical tile values): pass 1 visits only the tiles that hold a
 // ground-truth pair and extracts those scores; pass 2 visits every tile and counts, per row and per column, the entries

@@ -133,6 +133,24 @@ class UnrolledMatch(torch.autograd.Function):
                 None, None, None, None, None)
 
 
+def nearest_neighbor(sentences, query_embeddings, database_embeddings):
+    """distill.py:89-95: for every synthetic text embedding the training caption whose embedding is most cosine-similar.
+
+    The reference loops over the queries on the CPU (sklearn cosine_similarity against all ~145k captions per query);
+    here both sets are normalised and compared with one tensor-core GEMM + a row arg-max on the device.  Accepts numpy
+    arrays or tensors on any device, returns a list of sentences like the reference.
+    """
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    if dev is None:
+        raise RuntimeError("nearest_neighbor needs a CUDA device (this library has no CPU path)")
+    q = torch.as_tensor(query_embeddings).to(dev, torch.float32)
+    b = torch.as_tensor(database_embeddings).to(dev, torch.float32)
+    if q.dim() == 1:
+        q = q.reshape(1, -1)
+    idx = ops.nearest_rows(q.contiguous(), b.contiguous()).cpu().tolist()
+    return [sentences[i] for i in idx]
+
+
 def flatten_snapshot(params, device=None) -> torch.Tensor:
     """torch.cat([p.reshape(-1) ...]) of one snapshot (distill.py:471-476), done once per buffer instead of per iteration."""
     flat = torch.cat([torch.as_tensor(p).reshape(-1).float() for p in params], 0)

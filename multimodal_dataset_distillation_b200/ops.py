@@ -289,6 +289,47 @@ def contrastive_step(theta: torch.Tensor, Y: torch.Tensor, U: torch.Tensor, scal
     return dict(loss=loss[0], g_theta=g, dY=dY, dU=dU, dscale=dsc[0])
 
 
+def clip_loss(theta: torch.Tensor, Y: torch.Tensor, U: torch.Tensor, scale=LOGIT_SCALE_EVAL, mask: torch.Tensor | None = None):
+    """networks.py:866-889 from the encoder outputs on: dict(loss, top1[2] int32, g_theta, dY, dU, dscale).
+
+    top1 = (#image rows whose best caption is their own, #captions whose best image is their own); the reference's
+    ``acc`` is ``top1.sum() / 2``.
+    """
+    theta, Y, U = _req(_flat(theta), "theta"), _req(Y, "Y"), _req(U, "U")
+    B, dt = Y.shape
+    d = U.shape[1]
+    if U.shape[0] != B:
+        raise ValueError("image and text batches differ in size")
+    if theta.numel() != head_numel(dt, d):
+        raise ValueError(f"theta has {theta.numel()} elements, expected {head_numel(dt, d)}")
+    dev = Y.device
+    sc = _scalar(scale, dev, "scale")
+    mask = None if mask is None else _req(mask, "mask")
+    loss = torch.empty(1, device=dev)
+    top1 = torch.empty(2, dtype=torch.int32, device=dev)
+    g = torch.empty_like(theta)
+    dY, dU, dsc = torch.empty_like(Y), torch.empty_like(U), torch.empty(1, device=dev)
+    ws = torch.empty(lib().vldd_contrastive_step_workspace_bytes(B, dt, d), dtype=torch.uint8, device=dev)
+    check(lib().vldd_clip_loss(_ptr(theta), _ptr(Y), _ptr(U), _ptr(sc), _ptr(mask), B, dt, d, _ptr(loss), _ptr(top1), _ptr(g),
+                               _ptr(dY), _ptr(dU), _ptr(dsc), _ptr(ws), ws.numel(), _stream()), "clip_loss")
+    return dict(loss=loss[0], top1=top1, g_theta=g, dY=dY, dU=dU, dscale=dsc[0])
+
+
+def nearest_rows(query: torch.Tensor, bank: torch.Tensor, return_cos: bool = False):
+    """Index of the most cosine-similar bank row per query row, first index on ties (distill.py:89-95)."""
+    q, b = _req(query, "query"), _req(bank, "bank")
+    if q.dim() != 2 or b.dim() != 2 or q.shape[1] != b.shape[1]:
+        raise ValueError(f"query {tuple(q.shape)} and bank {tuple(b.shape)} must be 2-D with equal width")
+    Q, D = q.shape
+    T = b.shape[0]
+    idx = torch.empty(Q, dtype=torch.int32, device=q.device)
+    cos = torch.empty(Q, dtype=torch.float32, device=q.device) if return_cos else None
+    ws = torch.empty(max(lib().vldd_nearest_rows_workspace_bytes(Q, T, D), 1), dtype=torch.uint8, device=q.device)
+    check(lib().vldd_nearest_rows(_ptr(q), _ptr(b), Q, T, D, _ptr(idx), _ptr(cos), _ptr(ws), ws.numel(), _stream()),
+          "nearest_rows")
+    return (idx, cos) if return_cos else idx
+
+
 class UnrollWorkspace:
     """Caller-owned device state of the unroll engine, sized once per (N, B, K, dt, d).
 

@@ -75,6 +75,24 @@ def row_normalise(x):
     return x / x.norm(dim=1, keepdim=True)
 
 
+def clip_forward_ref(theta, Y, U, scale=math.exp(math.log(1 / 0.07)), mask=None, dt=768, d=2304):
+    """networks.py:866-889 restated from the encoder outputs on: (loss, top1_rows, top1_cols); acc = (rows + cols) / 2.
+
+    txt = text_projection(Y) (868-870); both sides row-normalised (873-874); logits = scale * Xn Yn^T with
+    scale = exp(log(1/0.07)) (877-878); loss = (CE(logits) + CE(logits^T)) / 2 (881-882); torch.argmax over rows /
+    columns compared with arange(B) (884-885).  Differentiable in theta, Y, U (loss.backward() in epoch.py:86).
+    """
+    xn = row_normalise(U)
+    yn = row_normalise(head_forward(theta, Y, dt, d, mask))
+    logits = scale * xn @ yn.t()
+    gt = torch.arange(logits.shape[0])
+    loss = (F.cross_entropy(logits, gt) + F.cross_entropy(logits.t(), gt)) / 2
+    top_r = int((torch.argmax(logits, 1) == gt).sum())
+    top_c = int((torch.argmax(logits, 0) == gt).sum())
+    return loss, top_r, top_c
+
+
+
 @dataclass
 class UnrollResult:
     loss: torch.Tensor          # txt_param_loss (= grand_loss in Mode A)

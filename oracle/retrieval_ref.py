@@ -154,3 +154,39 @@ def synthetic_retrieval(n_img, caps_per_img, dim, seed=0, corr=0.15, dtype=np.fl
     txt = rng.standard_normal((n_img * caps_per_img, dim)).astype(dtype)
     txt += dtype(corr) * np.repeat(img, caps_per_img, axis=0)
     return l2_normalise(img), l2_normalise(txt)
+
+
+# ---- nearest-neighbour caption lookup (distill.py:89-95) -------------------------------------------------------------
+def nearest_problem(tag: str):
+    """Seeded (query, bank) pair: 'small' has an exact duplicate row (first index must win) and an all-zero row;
+    'mid' is 100 queries against 3000 rows of BERT-like 768-d embeddings."""
+    Q, T, D = {"small": (7, 50, 12), "mid": (100, 3000, 768)}[tag]
+    rng = np.random.default_rng(5 if tag == "small" else 6)
+    bank = (rng.standard_normal((T, D)) * 0.5253 - 0.0094).astype(np.float32)
+    query = (bank[rng.integers(0, T, Q)] + 0.3 * rng.standard_normal((Q, D))).astype(np.float32)
+    if tag == "small":
+        bank[10] = bank[3]
+        query[0] = 2.0 * bank[3]
+        bank[20] = 0.0
+    return query, bank
+
+
+def nearest_neighbor_ref(query: np.ndarray, bank: np.ndarray) -> np.ndarray:
+    """distill.py:89-95 restated: per query argmax of sklearn's cosine_similarity (rows L2-normalised, all-zero rows kept
+    as zeros: sklearn.preprocessing.normalize divides by 1 when the norm is 0), first index on ties (np.argmax)."""
+    def unit(x):
+        x = np.asarray(x, dtype=np.float64)
+        n = np.sqrt((x * x).sum(axis=1, keepdims=True))
+        n[n == 0.0] = 1.0
+        return x / n
+    return np.argmax(unit(query) @ unit(bank).T, axis=1).astype(np.int32)
+
+
+def cosine_matrix(query: np.ndarray, bank: np.ndarray) -> np.ndarray:
+    """sklearn.metrics.pairwise.cosine_similarity restated in float64 (zero rows stay zero)."""
+    def unit(x):
+        x = np.asarray(x, dtype=np.float64)
+        n = np.sqrt((x * x).sum(axis=1, keepdims=True))
+        n[n == 0.0] = 1.0
+        return x / n
+    return unit(query) @ unit(bank).T
