@@ -31,6 +31,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at VERSION level) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 CFG = dict(N=100, B=100, K=8, dt=768, d=2304, experts=4, snapshots=3)
 RET = dict(I=1000, C=5, D=768)

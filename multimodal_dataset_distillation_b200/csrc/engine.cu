@@ -159,6 +159,16 @@ inline int ew_grid(size_t n) {
 
 #define CHECK_RC(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 
+// VLDD_EARLY_LOADS=0 disables the pre-wait operand loads of the tensor-core GEMMs (A/B runs)
+bool early_loads() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLDD_EARLY_LOADS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // InfoNCE as one cluster launch (nce_cluster.cuh) is opt-in, VLDD_NCE=cluster.  Measured on B200 at the Flickr shape
 // (bench.py, ms / iteration): three / four small launches 1.906, one 8-CTA cluster launch 1.936 -- the 36-slab logits
 // reduction (1.4 MB from L2) is spread over 100 SMs by the row kernels but over only 8 by the cluster, and under
@@ -260,8 +270,16 @@ int lanes_join(Lanes& L) {
 // ---------------------------------------------------------------------------------------------------
 // One forward (first-order) step.  th_src/th_dst: theta_k -> theta_{k+1} (th_src == nullptr: dst = -lr*g).
 // ---------------------------------------------------------------------------------------------------
+// `chain`: the call sits inside the engine's own launch chain (unrolled_match), where every kernel triggers its
+// dependents only after its own griddepcontrol.wait has returned; operands produced two or more kernels upstream
+// (weights of this step, the gathered minibatch) may then be fetched before the wait (tc_gemm.cuh, old_mask:
+// bit 0 = A operands, bit 1 = B operands).  step_index < 0 or !chain: no early loads.
 int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float* upd_src, float* upd_dst,
-                 const float* lr, const float* scale, const float* mask, float* ce_out, Lanes& L) {
+                 const float* lr, const float* scale, const float* mask, float* ce_out, Lanes& L, bool chain = false,
+                 int step_index = 0) {
+  const int kOldA = chain ? 1 : 0, kOldB = chain ? 2 : 0;
+  // theta_k[W1] comes from the side-stream GEMM joined right here (one hop) unless this is step 0 (staged before the call)
+  const int p_mask = !chain ? 0 : (step_index == 0 ? 2 : 1);
   cudaStream_t st = L.main;
   CHECK_RC(lanes_join(L));          // theta_k must be complete (previous step's weight-gradient branches)
   const int B = m.B, d = m.d, dt = m.dt, Bp = m.Bp;
@@ -269,12 +287,12 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   const float *W1 = th + m.oW1, *b1 = th + m.ob1, *W2 = th + m.oW2, *b2 = th + m.ob2, *gam = th + m.og, *bet = th + m.obt;
   // p = Yb W1^T + b1 ; h = gelu(p)
   int sp = 1;
-  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, W1, dt, B, d, dt), w.pa, &sp, st)));
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, W1, dt, B, d, dt), w.pa, &sp, st, p_mask)));
   prof_mark("gemm_partial<true,true> A=s.Yb", st);
   launch_k(epi_p_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, b1, B, d, s.p, s.h);
   prof_mark("epi_p_kernel", st);
   // f = h W2^T + b2 ; r = mask f + p ; LN ; normalise
-  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.h, d, W2, d, B, d, d), w.pa, &sp, st)));
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.h, d, W2, d, B, d, d), w.pa, &sp, st, kOldB)));
   prof_mark("gemm_partial<true,true> A=s.h", st);
   if (row_v4_ok(d))
     VLDD_ROW_V4_DISPATCH(d, ln_fwd_v4_kernel, (B, 256, 0, st), (w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr,
@@ -284,7 +302,7 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
                                                      s.rstd, s.nz);
   prof_mark("ln_fwd_kernel", st);
   // S = scale * Xb Yn^T ; lse ; G ; loss
-  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, s.yn, d, B, B, d), w.pa, &sp, st)));
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, s.yn, d, B, B, d), w.pa, &sp, st, kOldA)));
   prof_mark("gemm_partial<true,true> A=s.Xb", st);
   if (nce_fused(B, Bp)) {
     launch_cluster_k(nce_cluster_kernel, kNceCluster, kNceThreads, nce_cluster_smem_bytes(B, Bp), st, w.pa, sp, (size_t)B * B,
@@ -300,7 +318,7 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   }
   // dyn_raw[j,:] = sum_i G[i,j] Xb[i,:]
   // (G is stored with leading dimension Bp and zero padding columns: rows B..Bp-1 of the product are zeros)
-  CHECK_RC((gemm_store<false, false>(gemm_ops(s.G, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st)));
+  CHECK_RC((gemm_store<false, false>(gemm_ops(s.G, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st, kOldB)));
   prof_mark("gemm_store<false,false> A=s.G", st);
   if (row_v4_ok(d))
     VLDD_ROW_V4_DISPATCH(d, norm_ln_bwd_v4_kernel, (B, 256, 0, st), (w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d,
@@ -316,7 +334,7 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
                                     upd_dst + m.oW2, d, lr, L.s1)));
   prof_mark("gemm_axpy<false,false> A=s.df", L.s1);
   // dh = df W2 ; dp = dh gelu'(p) + dr
-  CHECK_RC((gemm_partial<true, false>(gemm_ops(s.df, d, W2, d, B, d, d), w.pa, &sp, st)));
+  CHECK_RC((gemm_partial<true, false>(gemm_ops(s.df, d, W2, d, B, d, d), w.pa, &sp, st, kOldB)));
   prof_mark("gemm_partial<true,false> A=s.df", st);
   launch_k(epi_dp_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, s.p, s.dr, Bd, s.dh, s.dp);
   prof_mark("epi_dp_kernel", st);
@@ -340,7 +358,11 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
 // ---------------------------------------------------------------------------------------------------
 int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const float* v, float* a_out,
                  const float* lr, const float* scale, const float* mask, const int64_t* perm, float* dY, float* dlr,
-                 float* dscale, Lanes& L) {
+                 float* dscale, Lanes& L, bool v_fresh) {
+  // early operand loads (see forward_step): theta_k and the saved activations are steps old; v = a_{k+1} is two hops
+  // upstream (its W1 block was written by the main-stream GEMM before the column-sum kernel) except in the first
+  // reverse step, where the matching-loss backward kernel that wrote it is the immediate predecessor
+  const int kOldA = early_loads() ? 1 : 0, kOldB = early_loads() ? 2 : 0;
   cudaStream_t st = L.main;
   const int B = m.B, d = m.d, dt = m.dt, Bp = m.Bp;
   const size_t Bd = (size_t)B * d;
@@ -348,12 +370,12 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   const float *V1 = v + m.oW1, *c1 = v + m.ob1, *V2 = v + m.oW2, *c2 = v + m.ob2, *gamd = v + m.og, *betd = v + m.obt;
   // pd = Yb V1^T + c1 ; hd = gelu'(p) pd
   int sp = 1;
-  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), w.pa, &sp, st)));
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), w.pa, &sp, st, v_fresh ? kOldA : (kOldA | kOldB))));
   prof_mark("gemm_partial<true,true> A=s.Yb", st);
   launch_k(epi_pd_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, c1, s.p, B, d, w.pd, w.hd);
   prof_mark("epi_pd_kernel", st);
   // fd = hd W2^T + h V2^T + c2 ; LN / normalise tangents
-  CHECK_RC((gemm_partial<true, true>(gemm_ops2(w.hd, d, W2, d, d, s.h, d, V2, d, d, B, d), w.pa, &sp, st)));
+  CHECK_RC((gemm_partial<true, true>(gemm_ops2(w.hd, d, W2, d, d, s.h, d, V2, d, d, B, d), w.pa, &sp, st, kOldB)));
   prof_mark("gemm_partial<true,true> A=w.hd", st);
   if (row_v4_ok(d))
     VLDD_ROW_V4_DISPATCH(d, ln_tangent_v4_kernel, (B, 256, 0, st), (w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz,
@@ -363,7 +385,7 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
                                                          gamd, betd, d, w.rhatd, w.ynd, w.t, w.nzd);
   prof_mark("ln_tangent_kernel", st);
   // Sd = scale Xb Ynd^T ; rho, kappa, Gd ; L_dot ; dlr, dscale
-  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, w.ynd, d, B, B, d), w.pa, &sp, st)));
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, w.ynd, d, B, B, d), w.pa, &sp, st, kOldA)));
   prof_mark("gemm_partial<true,true> A=s.Xb", st);
   const bool fused_nce = nce_fused(B, Bp);
   if (fused_nce) {
@@ -390,7 +412,7 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
     prof_mark("nce_t_finish_kernel", st);
   }
   // dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
-  CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st)));
+  CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st, kOldB)));
   prof_mark("gemm_store<false,false> A=w.Gd", st);
   if (row_v4_ok(d))
     VLDD_ROW_V4_DISPATCH(d, norm_ln_bwd_tangent_v4_kernel, (B, 256, 0, st), (w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd, s.dz, s.rhat, w.rhatd, s.rstd,
@@ -407,7 +429,7 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
                                     lr, L.s2)));
   prof_mark("gemm_axpy<false,false> A=w.dfd", L.s2);
   // dhd = dfd W2 + df V2 ; dpd
-  CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), w.pa, &sp, st)));
+  CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), w.pa, &sp, st, kOldB)));
   prof_mark("gemm_partial<true,false> A=w.dfd", st);
   launch_k(epi_dpd_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, s.p, w.pd, s.dh, w.drd, Bd, w.dpd);
   prof_mark("epi_dpd_kernel", st);
@@ -419,7 +441,7 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pe, sp_y, (size_t)B * dt, perm, dt, lr, nullptr, dY);
   prof_mark("scatter_add_rows_kernel", L.s1);
   // main: a_k[W1] = a_{k+1}[W1] - lr dpd^T Yb ; small params by column sums
-  CHECK_RC((gemm_axpy<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), v + m.oW1, a_out + m.oW1, dt, lr, st)));
+  CHECK_RC((gemm_axpy<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), v + m.oW1, a_out + m.oW1, dt, lr, st, kOldB)));
   prof_mark("gemm_axpy<false,false> A=w.dpd", st);
   launch_k(colsum_tangent_update_kernel, ceil_div(d, 16), 256, 0, st, 
       w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
@@ -478,7 +500,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
     Saved& s = w.sv[k];
     const float* th = w.traj + (size_t)k * m.P;
     CHECK_RC(forward_step(m, w, s, th, th, w.traj + (size_t)(k + 1) * m.P, lr, scale, masks ? masks + k * Bd : nullptr,
-                          ce ? ce + k : nullptr, L));
+                          ce ? ce + k : nullptr, L, early_loads(), k));
   }
   CHECK_RC(lanes_join(L));
   const float* thK = w.traj + (size_t)K * m.P;
@@ -492,7 +514,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   for (int k = K - 1; k >= 0; --k) {
     const float* th = w.traj + (size_t)k * m.P;
     CHECK_RC(tangent_step(m, w, w.sv[k], th, a_cur, a_nxt, lr, scale, masks ? masks + k * Bd : nullptr,
-                          perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L));
+                          perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L, k == K - 1 || !early_loads()));
     float* t = a_cur; a_cur = a_nxt; a_nxt = t;
   }
   launch_k(row_normalise_bwd_kernel, N, 256, 0, st, w.Xn, w.un, w.dXn, nullptr, d, dU);

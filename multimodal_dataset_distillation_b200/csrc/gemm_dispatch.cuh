@@ -45,11 +45,11 @@ inline int max_splits(int M, int N, int Ktot) {
 
 // partial slabs: part[z][M*N], returns the split count through *splits
 template <bool AK, bool BKm>
-inline int gemm_partial(const GemmOperands& g, float* part, int* splits, cudaStream_t st) {
+inline int gemm_partial(const GemmOperands& g, float* part, int* splits, cudaStream_t st, int old_mask = 0) {
   const int Kt = g.K0 + g.K1;
   if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) {
     *splits = tc::pick_splits(g.M, g.N, Kt);
-    return tc::launch<AK, BKm, 3, tc::EpiPartial, VLDD_STAGES_PARTIAL>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st);
+    return tc::launch<AK, BKm, 3, tc::EpiPartial, VLDD_STAGES_PARTIAL>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st, nullptr, nullptr, old_mask);
   }
   *splits = simt_pick_splits(g.M, g.N, Kt);
   launch_gemm<AK, BKm>(g, *splits, part, EpiStore{}, st);
@@ -57,20 +57,22 @@ inline int gemm_partial(const GemmOperands& g, float* part, int* splits, cudaStr
 }
 // C = alpha * A B
 template <bool AK, bool BKm>
-inline int gemm_store(const GemmOperands& g, float* C, int ldc, float alpha, cudaStream_t st) {
-  if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) return tc::launch<AK, BKm, 3>(g, 1, tc::EpiScale{C, ldc, alpha}, st);
+inline int gemm_store(const GemmOperands& g, float* C, int ldc, float alpha, cudaStream_t st, int old_mask = 0) {
+  if (tc_enabled() && tc::gemm_ok<AK, BKm>(g))
+    return tc::launch<AK, BKm, 3>(g, 1, tc::EpiScale{C, ldc, alpha}, st, nullptr, nullptr, old_mask);
   launch_gemm<AK, BKm>(g, 1, nullptr, EpiStore{C, ldc, alpha}, st);
   return VLDD_OK;
 }
 // dst = src - (*lr) * A B      (src nullable)
 template <bool AK, bool BKm>
-inline int gemm_axpy(const GemmOperands& g, const float* src, float* dst, int ld, const float* lr, cudaStream_t st) {
+inline int gemm_axpy(const GemmOperands& g, const float* src, float* dst, int ld, const float* lr, cudaStream_t st,
+                     int old_mask = 0) {
   if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) {
     // 128 x 96 tiles when they divide N: 2304 x 2304 -> 432 work items = 2.92 per SM (three even rounds) instead of
     // 324 = 2.19 (28 CTAs run a third round while 120 idle)
     if (g.N % 96 == 0 && ceil_div(g.M, tc::BM) * (g.N / 128) > kNumSMs)
-      return tc::launch<AK, BKm, 3, tc::EpiAxpyTC, VLDD_STAGES_AXPY, 96>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st);
-    return tc::launch<AK, BKm, 3, tc::EpiAxpyTC, VLDD_STAGES_AXPY>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st);
+      return tc::launch<AK, BKm, 3, tc::EpiAxpyTC, VLDD_STAGES_AXPY, 96>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st, nullptr, nullptr, old_mask);
+    return tc::launch<AK, BKm, 3, tc::EpiAxpyTC, VLDD_STAGES_AXPY>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st, nullptr, nullptr, old_mask);
   }
   launch_gemm<AK, BKm>(g, 1, nullptr, EpiAxpy{src, dst, ld, lr}, st);
   return VLDD_OK;

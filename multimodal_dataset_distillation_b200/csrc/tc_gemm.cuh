@@ -253,7 +253,7 @@ struct WorkItem { int m0, n0, z, kb_begin, n_kb; };
 template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, int splits, Epi epi,
-               const int* __restrict__ work_list, const int* __restrict__ work_count) {
+               const int* __restrict__ work_list, const int* __restrict__ work_count, int old_mask) {
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= 128, "N tile: 64, 96 or 128 (32-column epilogue chunks, MN-major boxes)");
   constexpr bool A_TMEM = kSplit == 3;                 // hi/lo of the A tile are staged in tensor memory (either major)
   using C = Cfg<kSplit, A_TMEM, kStagesT, BN>;
@@ -310,11 +310,18 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above is independent of the preceding kernel: under programmatic dependent launch it overlaps that
-  // kernel's tail; from here on global memory written by predecessors is read
+  // kernel's tail; from here on global memory written by predecessors is read.
+  // `old_mask` (bit 0: A operands, bit 1: B operands) marks operands that were complete before the programmatic
+  // predecessor even started (weights written a step ago, gathered minibatches): the producer issues their TMA loads for
+  // the first pipeline stages BEFORE griddepcontrol.wait, so the weight fetch overlaps the predecessor's execution.
+  // (Safe: every kernel of the library triggers its dependents only after its own wait returned, so when this grid
+  // runs, everything older than its immediate predecessor has completed and is visible.)
   TL(1);
-  pdl_enter();
+  if (warp != 0) {
+    pdl_enter();
+    if (work_count != nullptr) total_work = *work_count;
+  }
   TL(2);
-  if (work_count != nullptr) total_work = *work_count;
 
   // byte offsets of the tiles inside a stage
   constexpr int kHalfN = ((BN / 32 + 1) / 2) * 32;                   // column split of the last item's drain (64 of 96 / 128)
@@ -460,26 +467,48 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      auto issue = [&](const WorkItem& it, int i, int s, bool load_a, bool load_b) {
+        const int kb = it.kb_begin + i;
+        const bool seg1 = kb >= nkb0;
+        const int k = (seg1 ? kb - nkb0 : kb) * BK;
+        const CUtensorMap* ma = seg1 ? &maps.a1 : &maps.a0;
+        const CUtensorMap* mb = seg1 ? &maps.b1 : &maps.b0;
+        uint8_t* sa = smem + s * C::kStageBytes + OFF_A;
+        uint8_t* sb = smem + s * C::kStageBytes + OFF_B;
+        if (load_a) { if (A_KMAJOR) tma_load_2d(sa, ma, &full[s], k, it.m0); else tma_load_3d(sa, ma, &full[s], 0, k, it.m0 / 32); }
+        if (load_b) { if (B_KMAJOR) tma_load_2d(sb, mb, &full[s], k, it.n0); else tma_load_3d(sb, mb, &full[s], 0, k, it.n0 / 32); }
+      };
+      // early loads of the operands that do not depend on the programmatic predecessor (first item, first kStages k-blocks)
+      int pre = 0;
+      const bool a_old = (old_mask & 1) != 0, b_old = (old_mask & 2) != 0;
+      if (old_mask != 0 && work_list == nullptr && work_count == nullptr && (int)blockIdx.x < total_work) {
+        const WorkItem it0 = decode(blockIdx.x);
+        pre = min(C::kStages, it0.n_kb);
+        for (int i = 0; i < pre; ++i) {
+          mbar_expect_tx(&full[i], TILE_BYTES + TILE_B);        // both tiles of the stage; the rest follows after the wait
+          issue(it0, i, i, a_old, b_old);
+        }
+      }
+      pdl_enter();
+      if (work_count != nullptr) total_work = *work_count;
       int g = 0;                                                    // k-blocks issued so far (across work items)
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const WorkItem it = decode(w);
         for (int i = 0; i < it.n_kb; ++i, ++g) {
           const int s = g % C::kStages, round = g / C::kStages;
-          if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
-          const int kb = it.kb_begin + i;
-          const bool seg1 = kb >= nkb0;
-          const int k = (seg1 ? kb - nkb0 : kb) * BK;
-          const CUtensorMap* ma = seg1 ? &maps.a1 : &maps.a0;
-          const CUtensorMap* mb = seg1 ? &maps.b1 : &maps.b0;
-          uint8_t* sa = smem + s * C::kStageBytes + OFF_A;
-          uint8_t* sb = smem + s * C::kStageBytes + OFF_B;
-          mbar_expect_tx(&full[s], TILE_BYTES + TILE_B);
-          if (A_KMAJOR) tma_load_2d(sa, ma, &full[s], k, it.m0); else tma_load_3d(sa, ma, &full[s], 0, k, it.m0 / 32);
-          if (B_KMAJOR) tma_load_2d(sb, mb, &full[s], k, it.n0); else tma_load_3d(sb, mb, &full[s], 0, k, it.n0 / 32);
+          if (g < pre) {
+            issue(it, i, s, !a_old, !b_old);
+          } else {
+            if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+            mbar_expect_tx(&full[s], TILE_BYTES + TILE_B);
+            issue(it, i, s, true, true);
+          }
           if (g == 0) TL(3);
         }
       }
       TL(4);
+    } else {
+      pdl_enter();
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====

@@ -98,7 +98,7 @@ inline bool gemm_ok(const GemmOperands& g) {
 
 template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128>
 inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st, const int* work_list = nullptr,
-                  const int* work_count = nullptr) {
+                  const int* work_count = nullptr, int old_mask = 0) {
   using C = Cfg<kSplit, kSplit == 3, kStagesT, BN>;
   auto kern = tc_gemm_kernel<A_KMAJOR, B_KMAJOR, kSplit, Epi, kStagesT, BN>;
   static bool configured = false;
@@ -123,7 +123,7 @@ inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st, c
   }
   const int work = ceil_div(g.N, BN) * ceil_div(g.M, BM) * splits;
   dim3 grid(work < kNumSMs ? work : kNumSMs);                         // persistent: one CTA per SM at most
-  launch_k(kern, grid, NUM_THREADS, C::kSmemBytes, st, maps, g.M, g.N, g.K0, g.K1, splits, epi, work_list, work_count);
+  launch_k(kern, grid, NUM_THREADS, C::kSmemBytes, st, maps, g.M, g.N, g.K0, g.K1, splits, epi, work_list, work_count, old_mask);
   return VLDD_OK;
 }
 

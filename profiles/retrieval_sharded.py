@@ -25,6 +25,7 @@ def main():
         txt_s, t2i_s = txt[lo:hi].contiguous(), t2i[lo:hi].contiguous()
         for _ in range(2):
             r_i, r_t = D.sharded_ranks(img, txt_s, lo, t2i_s, ptr, idx, 14.285714)
+            D.sharded_result(r_i, r_t, T)
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
