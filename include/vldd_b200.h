@@ -131,6 +131,22 @@ int vldd_clip_loss(const float* theta, const float* Y, const float* U, const flo
                    int d, float* loss, int32_t* top1, float* g_theta, float* dY, float* dU, float* dscale, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* Bidirectional InfoNCE on already row-normalised features as a twice-differentiable node ("Mode B": any image tower
+ * under PyTorch autograd, e.g. pixels -> NFNet through ReparamModule as in distill.py:524-567, with the loss of
+ * distill.py:548-551 and autograd.grad(create_graph=True) on top of it).
+ *   vldd_infonce_grad: loss[1] = (CE(S) + CE(S^T)) / 2 with S = scale * xn yn^T; dxn[B,d], dyn[B,d], dscale[1] (nullable)
+ *                      = its gradient.
+ *   vldd_infonce_hvp:  for a direction (cx[B,d], cy[B,d], cs[1]):  Ldot[1] = <grad L, direction> and
+ *                      hx[B,d], hy[B,d], hs[1] = the gradient of Ldot w.r.t. (xn, yn, scale), i.e. the Hessian of the loss
+ *                      applied to the direction -- what the backward of the first-order gradients needs.
+ * scale, cs: device scalars.  Stateless: both take the same workspace (vldd_infonce_workspace_bytes). */
+size_t vldd_infonce_workspace_bytes(int B, int d);
+int vldd_infonce_grad(const float* xn, const float* yn, const float* scale, int B, int d, float* loss, float* dxn, float* dyn,
+                      float* dscale, void* workspace, size_t workspace_bytes, void* stream);
+int vldd_infonce_hvp(const float* xn, const float* yn, const float* scale, const float* cx, const float* cy, const float* cs,
+                     int B, int d, float* Ldot, float* hx, float* hy, float* hs, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 /* Nearest bank row per query by cosine similarity, first index on ties.   distill.py:89-95 (`nearest_neighbor`:
  * sklearn cosine_similarity(query, database) + np.argmax per query; rows are L2-normalised, all-zero rows left as is).
  * idx_out[n_query] int32; cos_out[n_query] (nullable) = the winning cosine.  Workspace holds the normalised copies and

@@ -42,6 +42,9 @@ _SIGS = {
     "vldd_contrastive_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P,
                                         C.c_size_t, _P]),
     "vldd_clip_loss": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vldd_infonce_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "vldd_infonce_grad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vldd_infonce_hvp": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vldd_nearest_rows_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "vldd_nearest_rows": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "vldd_bench_skinny_gemm_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -275,6 +275,21 @@ int vldd_clip_loss(const float* theta, const float* Y, const float* U, const flo
                    S(stream));
 }
 
+size_t vldd_infonce_workspace_bytes(int B, int d) { return infonce_workspace_bytes(B, d); }
+
+int vldd_infonce_grad(const float* xn, const float* yn, const float* scale, int B, int d, float* loss, float* dxn, float* dyn,
+                      float* dscale, void* workspace, size_t workspace_bytes, void* stream) {
+  VLDD_REQUIRE(xn && yn && scale && loss, "infonce_grad: null pointer");
+  return infonce_grad(xn, yn, scale, B, d, loss, dxn, dyn, dscale, workspace, workspace_bytes, S(stream));
+}
+
+int vldd_infonce_hvp(const float* xn, const float* yn, const float* scale, const float* cx, const float* cy, const float* cs,
+                     int B, int d, float* Ldot, float* hx, float* hy, float* hs, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  VLDD_REQUIRE(xn && yn && scale && cx && cy && cs && Ldot && hx && hy && hs, "infonce_hvp: null pointer");
+  return infonce_hvp(xn, yn, scale, cx, cy, cs, B, d, Ldot, hx, hy, hs, workspace, workspace_bytes, S(stream));
+}
+
 size_t vldd_nearest_rows_workspace_bytes(int n_query, int n_bank, int dim) {
   return nearest_rows_workspace_bytes(n_query, n_bank, dim);
 }

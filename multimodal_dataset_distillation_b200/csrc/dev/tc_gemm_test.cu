@@ -120,6 +120,8 @@ int main(int argc, char** argv) {
   if (want(c++)) run_case<false, false, 3, 0, 96>("TN dW2t dual axpy BN=96", 2304, 2304, 100, 100, 1, true);
   if (want(c++)) run_case<true, true, 3, 0, 96>("NT sims BN=96 1000x4992x768", 1000, 4992, 768, 0, 1, false);
   if (want(c++)) run_case<true, false, 3, 0, 64>("NN small BN=64", 100, 256, 96, 0, 1, false);
+  if (want(c++)) run_case<true, true, 1>("NT big 1xTF32 8192x8192x2048", 8192, 8192, 2048, 0, 1, false);
+  if (want(c++)) run_case<true, true, 3>("NT big 3xTF32 8192x8192x2048", 8192, 8192, 2048, 0, 1, false);
   printf("done\n");
   return 0;
 }

@@ -393,7 +393,8 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
                      (size_t)B * B, scale, s.S, s.lse_r, s.lse_c, s.G, B, Bp, w.Gd, lr, dlr, dscale);
     prof_mark("nce_t_cluster_kernel", st);
   } else {
-    launch_k(nce_t_rows_kernel, B, 128, 0, st, w.pa, sp, (size_t)B * B, scale, s.S, s.lse_r, s.G, B, Bp, w.Sd, w.rho, w.rowA);
+    launch_k(nce_t_rows_kernel, B, 128, 0, st, w.pa, sp, (size_t)B * B, scale, s.S, s.lse_r, s.G, B, Bp, w.Sd, w.rho, w.rowA,
+             (const float*)nullptr);
     prof_mark("nce_t_rows_kernel", st);
     launch_k(nce_t_cols_kernel, B, 128, 0, st, s.S, s.lse_c, w.Sd, B, Bp, w.kap);
     prof_mark("nce_t_cols_kernel", st);
@@ -681,6 +682,156 @@ int clip_loss(const float* theta, const float* Y, const float* U, const float* s
     launch_k(nce_top1_kernel, B, 128, 0, st, (const float*)w.sv[0].S, B, m.Bp, top1);
   }
   return check_launch("clip_loss");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// "Mode B" building block: the bidirectional InfoNCE loss on already-normalised features as a node that PyTorch can
+// differentiate TWICE (distill.py:548-551 under autograd.grad(create_graph=True) with an arbitrary image tower, e.g.
+// pixels -> NFNet under ReparamModule, distill.py:524-567).  Two stateless entry points:
+//   infonce_grad: L, dL/dxn = s G yn, dL/dyn = s G^T xn, dL/ds = sum(G o S) / s
+//   infonce_hvp : for a direction (cx, cy, cs) -- the cotangents autograd hands to the first-order gradients --
+//                 Ldot = <grad L, direction> and the gradient of Ldot w.r.t. (xn, yn, s):
+//                   Sd = cs S/s + s (cx yn^T + xn cy^T) ; Gd = Hess_S(L) Sd (nce_t_* kernels)
+//                   hx = s (Gd yn + G cy) + cs G yn ; hy = s (Gd^T xn + G^T cx) + cs G^T xn
+//                   hs = (sum Gd o S + sum G o Sd) / s - cs sum(G o S) / s^2
+// ---------------------------------------------------------------------------------------------------
+struct NceWork {
+  float *S, *G, *Sd, *Gd;                        // [B, Bp]
+  float *lse_r, *lse_c, *rho, *kap, *rowA, *rowB, *rowC;   // [B]
+  float *part;                                   // split-K slabs of the B x B GEMMs
+  float *t1, *t2;                                // [Bp, d] GEMM outputs
+  float *scal;                                   // 8 scalars
+  size_t bytes;
+};
+static void carve_nce(NceWork& w, int B, int d, void* base) {
+  Bump b{reinterpret_cast<char*>(base), 0, 0};
+  const int Bp = (B + 31) / 32 * 32;
+  const size_t BB = (size_t)B * Bp;
+  w.S = b.f(BB); w.G = b.f(BB); w.Sd = b.f(BB); w.Gd = b.f(BB);
+  w.lse_r = b.f(B); w.lse_c = b.f(B); w.rho = b.f(B); w.kap = b.f(B); w.rowA = b.f(B); w.rowB = b.f(B); w.rowC = b.f(B);
+  w.part = b.f((size_t)max_splits(B, B, 2 * d) * B * B);
+  w.t1 = b.f((size_t)Bp * d); w.t2 = b.f((size_t)Bp * d);
+  w.scal = b.f(8);
+  w.bytes = b.off;
+}
+size_t infonce_workspace_bytes(int B, int d) {
+  if (B <= 0 || d <= 0) return 0;
+  NceWork w;
+  carve_nce(w, B, d, nullptr);
+  return w.bytes;
+}
+// out = (*a) * x + (b ? (*b) * y : 0)
+__global__ void __launch_bounds__(256) lincomb_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                      const float* __restrict__ y, const float* __restrict__ b, size_t n,
+                                                      float* __restrict__ out) {
+  pdl_enter();
+  const float ca = *a, cb = b ? *b : 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = y ? fmaf(cb, y[i], ca * x[i]) : ca * x[i];
+}
+// rowC[i] = sum_j G_ij S_ij
+__global__ void __launch_bounds__(128) rowdot_kernel(const float* __restrict__ G, const float* __restrict__ S, int B, int ld,
+                                                     float* __restrict__ out) {
+  pdl_enter();
+  __shared__ float scratch[34];
+  float a = 0.f;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) a = fmaf(G[(size_t)blockIdx.x * ld + j], S[(size_t)blockIdx.x * ld + j], a);
+  a = block_sum<float>(a, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = a;
+}
+// Ldot = sum rowA ; hs = (sum rowB + sum rowA) / s - cs * sum rowC / s^2
+__global__ void __launch_bounds__(128) nce_hvp_finish_kernel(const float* __restrict__ rowA, const float* __restrict__ rowB,
+                                                             const float* __restrict__ rowC, int B,
+                                                             const float* __restrict__ scale, const float* __restrict__ cs,
+                                                             float* __restrict__ Ldot, float* __restrict__ hs) {
+  pdl_enter();
+  __shared__ float scratch[34];
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) { a += rowA[i]; b += rowB[i]; c += rowC[i]; }
+  a = block_sum<float>(a, scratch);
+  b = block_sum<float>(b, scratch);
+  c = block_sum<float>(c, scratch);
+  if (threadIdx.x == 0) {
+    const float s = *scale;
+    *Ldot = a;
+    *hs = (b + a) / s - (*cs) * c / (s * s);
+  }
+}
+
+// S, lse, G (and the loss) from normalised features: shared first half of both entry points
+static int nce_primal(NceWork& w, const float* xn, const float* yn, const float* scale, int B, int d, float* loss,
+                      cudaStream_t st) {
+  const int Bp = (B + 31) / 32 * 32;
+  if (Bp != B) {
+    const size_t bytes = (size_t)B * Bp * sizeof(float);
+    VLDD_CUDA(cudaMemsetAsync(w.S, 0, bytes, st));
+    VLDD_CUDA(cudaMemsetAsync(w.G, 0, bytes, st));
+    VLDD_CUDA(cudaMemsetAsync(w.Sd, 0, bytes, st));
+    VLDD_CUDA(cudaMemsetAsync(w.Gd, 0, bytes, st));
+  }
+  int sp = 1;
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(xn, d, yn, d, B, B, d), w.part, &sp, st)));
+  launch_k(nce_rows_kernel, B, 128, 0, st, w.part, sp, (size_t)B * B, scale, B, Bp, w.S, w.lse_r);
+  launch_k(nce_cols_kernel, B, 128, 0, st, w.S, B, Bp, w.lse_c);
+  launch_k(nce_grad_kernel, B, 128, 0, st, w.S, w.lse_r, w.lse_c, B, Bp, w.G, loss);
+  return VLDD_OK;
+}
+
+int infonce_grad(const float* xn, const float* yn, const float* scale, int B, int d, float* loss, float* dxn, float* dyn,
+                 float* dscale, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  VLDD_REQUIRE(B > 0 && d > 0, "infonce: bad dims B=%d d=%d", B, d);
+  NceWork w;
+  carve_nce(w, B, d, workspace);
+  if (workspace == nullptr || workspace_bytes < w.bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return VLDD_ERR_WORKSPACE;
+  }
+  const int Bp = (B + 31) / 32 * 32;
+  const size_t Bd = (size_t)B * d;
+  CHECK_RC(nce_primal(w, xn, yn, scale, B, d, loss, st));
+  if (dxn) {
+    CHECK_RC((gemm_store<true, false>(gemm_ops(w.G, Bp, yn, d, B, d, B), w.t1, d, 1.0f, st)));
+    launch_k(lincomb_kernel, ew_grid(Bd), 256, 0, st, (const float*)w.t1, scale, (const float*)nullptr, (const float*)nullptr, Bd, dxn);
+  }
+  if (dyn) {
+    CHECK_RC((gemm_store<false, false>(gemm_ops(w.G, Bp, xn, d, Bp, d, B), w.t2, d, 1.0f, st)));
+    launch_k(lincomb_kernel, ew_grid(Bd), 256, 0, st, (const float*)w.t2, scale, (const float*)nullptr, (const float*)nullptr, Bd, dyn);
+  }
+  if (dscale) launch_k(dot_over_scale_kernel, 1, 256, 0, st, (const float*)w.G, (const float*)w.S, (size_t)B * Bp, scale, dscale);
+  return check_launch("infonce_grad");
+}
+
+int infonce_hvp(const float* xn, const float* yn, const float* scale, const float* cx, const float* cy, const float* cs,
+                int B, int d, float* Ldot, float* hx, float* hy, float* hs, void* workspace, size_t workspace_bytes,
+                cudaStream_t st) {
+  VLDD_REQUIRE(B > 0 && d > 0, "infonce_hvp: bad dims B=%d d=%d", B, d);
+  NceWork w;
+  carve_nce(w, B, d, workspace);
+  if (workspace == nullptr || workspace_bytes < w.bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return VLDD_ERR_WORKSPACE;
+  }
+  const int Bp = (B + 31) / 32 * 32;
+  const size_t Bd = (size_t)B * d;
+  CHECK_RC(nce_primal(w, xn, yn, scale, B, d, nullptr, st));
+  // Sd = cs S/s + s (cx yn^T + xn cy^T)
+  int sp = 1;
+  CHECK_RC((gemm_partial<true, true>(gemm_ops2(cx, d, yn, d, d, xn, d, cy, d, d, B, B), w.part, &sp, st)));
+  launch_k(nce_t_rows_kernel, B, 128, 0, st, w.part, sp, (size_t)B * B, scale, w.S, w.lse_r, w.G, B, Bp, w.Sd, w.rho, w.rowA, cs);
+  launch_k(nce_t_cols_kernel, B, 128, 0, st, w.S, w.lse_c, w.Sd, B, Bp, w.kap);
+  launch_k(nce_t_grad_kernel, B, 128, 0, st, w.S, w.lse_r, w.lse_c, w.Sd, w.rho, w.kap, B, Bp, w.Gd, w.rowB);
+  launch_k(rowdot_kernel, B, 128, 0, st, (const float*)w.G, (const float*)w.S, B, Bp, w.rowC);
+  launch_k(nce_hvp_finish_kernel, 1, 128, 0, st, (const float*)w.rowA, (const float*)w.rowB, (const float*)w.rowC, B, scale, cs,
+           Ldot, hs);
+  // hx = s (Gd yn + G cy) + cs (G yn)
+  CHECK_RC((gemm_store<true, false>(gemm_ops2(w.Gd, Bp, yn, d, B, w.G, Bp, cy, d, B, B, d), w.t1, d, 1.0f, st)));
+  CHECK_RC((gemm_store<true, false>(gemm_ops(w.G, Bp, yn, d, B, d, B), w.t2, d, 1.0f, st)));
+  launch_k(lincomb_kernel, ew_grid(Bd), 256, 0, st, (const float*)w.t1, scale, (const float*)w.t2, cs, Bd, hx);
+  // hy = s (Gd^T xn + G^T cx) + cs (G^T xn)
+  CHECK_RC((gemm_store<false, false>(gemm_ops2(w.Gd, Bp, xn, d, B, w.G, Bp, cx, d, B, Bp, d), w.t1, d, 1.0f, st)));
+  CHECK_RC((gemm_store<false, false>(gemm_ops(w.G, Bp, xn, d, Bp, d, B), w.t2, d, 1.0f, st)));
+  launch_k(lincomb_kernel, ew_grid(Bd), 256, 0, st, (const float*)w.t1, scale, (const float*)w.t2, cs, Bd, hy);
+  return check_launch("infonce_hvp");
 }
 
 // text_projection forward over `rows` embeddings (eval-mode when mask == nullptr): z = LN(...), zn = z/|z|.

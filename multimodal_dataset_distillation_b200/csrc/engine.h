@@ -18,6 +18,12 @@ int contrastive_step(const float* theta, const float* Y, const float* U, const f
 int clip_loss(const float* theta, const float* Y, const float* U, const float* scale, const float* mask, int B, int dt,
               int d, float* loss, int32_t* top1, float* g_theta, float* dY, float* dU, float* dscale, void* workspace,
               size_t workspace_bytes, cudaStream_t st);
+size_t infonce_workspace_bytes(int B, int d);
+int infonce_grad(const float* xn, const float* yn, const float* scale, int B, int d, float* loss, float* dxn, float* dyn,
+                 float* dscale, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int infonce_hvp(const float* xn, const float* yn, const float* scale, const float* cx, const float* cy, const float* cs,
+                int B, int d, float* Ldot, float* hx, float* hy, float* hs, void* workspace, size_t workspace_bytes,
+                cudaStream_t st);
 size_t proj_head_workspace_bytes(int rows, int dt, int d);
 int proj_head_forward(const float* theta, const float* Y, const float* mask, int rows, int dt, int d, float* z,
                       float* zn, void* workspace, size_t workspace_bytes, cudaStream_t st);

@@ -495,19 +495,23 @@ __global__ void __launch_bounds__(256) ln_tangent_kernel(const float* __restrict
 // InfoNCE, tangent
 // ------------------------------------------------------------------------------------------------
 // row i: Sd[i,:] = scale * slabs ; rho_i = sum_j Pr_ij Sd_ij ; rowLd[i] = sum_j G_ij Sd_ij
+// (scale_dot != nullptr: the logit scale itself moves along the direction, Sd += (*scale_dot / scale) * S)
 __global__ void __launch_bounds__(128) nce_t_rows_kernel(const float* __restrict__ part, int splits, size_t stride,
                                                          const float* __restrict__ scale, const float* __restrict__ S,
                                                          const float* __restrict__ lse_r, const float* __restrict__ G,
                                                          int B, int ld, float* __restrict__ Sd, float* __restrict__ rho,
-                                                         float* __restrict__ rowLd) {
+                                                         float* __restrict__ rowLd,
+                                                         const float* __restrict__ scale_dot = nullptr) {
   pdl_enter();
   __shared__ float scratch[34];
   const int i = blockIdx.x;
   const float sc = *scale, l = lse_r[i];
+  const float rel = scale_dot ? (*scale_dot) / sc : 0.f;
   float a = 0.f, b = 0.f;
   for (int j = threadIdx.x; j < B; j += blockDim.x) {
     const size_t ij = (size_t)i * ld + j;
-    const float v = sc * sum_slabs_ilp(part, splits, stride, (size_t)i * B + j);
+    float v = sc * sum_slabs_ilp(part, splits, stride, (size_t)i * B + j);
+    if (scale_dot) v = fmaf(rel, S[ij], v);
     Sd[ij] = v;
     a = fmaf(expf(S[ij] - l), v, a);
     b = fmaf(G[ij], v, b);

@@ -330,6 +330,40 @@ def nearest_rows(query: torch.Tensor, bank: torch.Tensor, return_cos: bool = Fal
     return (idx, cos) if return_cos else idx
 
 
+def _nce_args(xn, yn, scale):
+    xn, yn = _req(xn, "xn"), _req(yn, "yn")
+    if xn.dim() != 2 or xn.shape != yn.shape:
+        raise ValueError(f"xn {tuple(xn.shape)} and yn {tuple(yn.shape)} must be equal 2-D shapes")
+    B, d = xn.shape
+    sc = _scalar(scale, xn.device, "scale")
+    ws = torch.empty(max(lib().vldd_infonce_workspace_bytes(B, d), 1), dtype=torch.uint8, device=xn.device)
+    return xn, yn, sc, B, d, ws
+
+
+def infonce_grad(xn: torch.Tensor, yn: torch.Tensor, scale):
+    """Bidirectional InfoNCE on row-normalised features (distill.py:548-551): dict(loss, dxn, dyn, dscale)."""
+    xn, yn, sc, B, d, ws = _nce_args(xn, yn, scale)
+    loss = torch.empty(1, device=xn.device)
+    dxn, dyn, dsc = torch.empty_like(xn), torch.empty_like(yn), torch.empty(1, device=xn.device)
+    check(lib().vldd_infonce_grad(_ptr(xn), _ptr(yn), _ptr(sc), B, d, _ptr(loss), _ptr(dxn), _ptr(dyn), _ptr(dsc), _ptr(ws),
+                                  ws.numel(), _stream()), "infonce_grad")
+    return dict(loss=loss[0], dxn=dxn, dyn=dyn, dscale=dsc[0])
+
+
+def infonce_hvp(xn: torch.Tensor, yn: torch.Tensor, scale, cx: torch.Tensor, cy: torch.Tensor, cs):
+    """Hessian of the InfoNCE loss applied to the direction (cx, cy, cs): dict(Ldot, hx, hy, hs)."""
+    xn, yn, sc, B, d, ws = _nce_args(xn, yn, scale)
+    cx, cy = _req(cx, "cx"), _req(cy, "cy")
+    if cx.shape != xn.shape or cy.shape != yn.shape:
+        raise ValueError("direction shapes must match the features")
+    csv = _scalar(cs, xn.device, "cs")
+    Ldot, hs = torch.empty(1, device=xn.device), torch.empty(1, device=xn.device)
+    hx, hy = torch.empty_like(xn), torch.empty_like(yn)
+    check(lib().vldd_infonce_hvp(_ptr(xn), _ptr(yn), _ptr(sc), _ptr(cx), _ptr(cy), _ptr(csv), B, d, _ptr(Ldot), _ptr(hx),
+                                 _ptr(hy), _ptr(hs), _ptr(ws), ws.numel(), _stream()), "infonce_hvp")
+    return dict(Ldot=Ldot[0], hx=hx, hy=hy, hs=hs[0])
+
+
 class UnrollWorkspace:
     """Caller-owned device state of the unroll engine, sized once per (N, B, K, dt, d).
 
