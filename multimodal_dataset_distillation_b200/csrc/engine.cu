@@ -234,29 +234,44 @@ struct Lanes {
   bool s1_busy, s2_busy;
 };
 std::mutex g_lane_mu;
-cudaStream_t g_side1 = nullptr, g_side2 = nullptr;
-std::vector<cudaEvent_t> g_events;
-size_t g_event_next = 0;
+// side streams, event pool and capture stream are per device (a process may drive several GPUs)
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  cudaStream_t side1 = nullptr, side2 = nullptr, capture = nullptr;
+  std::vector<cudaEvent_t> events;
+  size_t event_next = 0;
+};
+DeviceState g_dev[kMaxDevices];
+DeviceState* g_cur = nullptr;        // state of the device the current call runs on (set under g_graph_mu / g_lane_mu)
+
+int current_device_state(DeviceState** out) {
+  int dev = 0;
+  VLDD_CUDA(cudaGetDevice(&dev));
+  VLDD_REQUIRE(dev >= 0 && dev < kMaxDevices, "device ordinal %d out of range", dev);
+  *out = &g_dev[dev];
+  return VLDD_OK;
+}
 
 int lanes_init(Lanes& L, cudaStream_t main) {
   std::lock_guard<std::mutex> lock(g_lane_mu);
-  if (g_side1 == nullptr) {
-    VLDD_CUDA(cudaStreamCreateWithFlags(&g_side1, cudaStreamNonBlocking));
-    VLDD_CUDA(cudaStreamCreateWithFlags(&g_side2, cudaStreamNonBlocking));
+  CHECK_RC(current_device_state(&g_cur));
+  if (g_cur->side1 == nullptr) {
+    VLDD_CUDA(cudaStreamCreateWithFlags(&g_cur->side1, cudaStreamNonBlocking));
+    VLDD_CUDA(cudaStreamCreateWithFlags(&g_cur->side2, cudaStreamNonBlocking));
   }
-  L.main = main; L.s1 = g_side1; L.s2 = g_side2; L.s1_busy = false; L.s2_busy = false;
+  L.main = main; L.s1 = g_cur->side1; L.s2 = g_cur->side2; L.s1_busy = false; L.s2_busy = false;
   if (prof_enabled()) { L.s1 = main; L.s2 = main; }
-  g_event_next = 0;
+  g_cur->event_next = 0;
   return VLDD_OK;
 }
 int lane_edge(cudaStream_t from, cudaStream_t to) {   // everything enqueued on `from` so far happens-before later work on `to`
   if (from == to) return VLDD_OK;
-  if (g_event_next == g_events.size()) {
+  if (g_cur->event_next == g_cur->events.size()) {
     cudaEvent_t e;
     VLDD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    g_events.push_back(e);
+    g_cur->events.push_back(e);
   }
-  cudaEvent_t e = g_events[g_event_next++];
+  cudaEvent_t e = g_cur->events[g_cur->event_next++];
   VLDD_CUDA(cudaEventRecord(e, from));
   VLDD_CUDA(cudaStreamWaitEvent(to, e, 0));
   return VLDD_OK;
@@ -534,7 +549,6 @@ struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t last_use; };
 std::mutex g_graph_mu;
 std::vector<GraphEntry> g_graphs;
 uint64_t g_graph_clock = 0;
-cudaStream_t g_capture_stream = nullptr;
 constexpr size_t kMaxGraphs = 32;
 
 bool graphs_enabled() {
@@ -578,7 +592,10 @@ int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, 
   for (auto& e : g_graphs)
     if (e.key == key) { exec = e.exec; e.last_use = ++g_graph_clock; break; }
   if (exec == nullptr) {
-    if (g_capture_stream == nullptr) VLDD_CUDA(cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking));
+    DeviceState* ds = nullptr;
+    CHECK_RC(current_device_state(&ds));
+    if (ds->capture == nullptr) VLDD_CUDA(cudaStreamCreateWithFlags(&ds->capture, cudaStreamNonBlocking));
+    cudaStream_t g_capture_stream = ds->capture;
     VLDD_CUDA(cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal));
     const int rc = unrolled_match_body(m, w, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K, g_capture_stream);
     cudaGraph_t graph = nullptr;
