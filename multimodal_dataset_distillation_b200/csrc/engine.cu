@@ -373,10 +373,10 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
 // ---------------------------------------------------------------------------------------------------
 int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const float* v, float* a_out,
                  const float* lr, const float* scale, const float* mask, const int64_t* perm, float* dY, float* dlr,
-                 float* dscale, Lanes& L, bool v_fresh) {
-  // early operand loads (see forward_step): theta_k and the saved activations are steps old; v = a_{k+1} is two hops
-  // upstream (its W1 block was written by the main-stream GEMM before the column-sum kernel) except in the first
-  // reverse step, where the matching-loss backward kernel that wrote it is the immediate predecessor
+                 float* dscale, Lanes& L) {
+  // early operand loads (see forward_step): theta_k and the saved activations are steps old.  v = a_{k+1} is NOT old for the
+  // first GEMM: its W1 block is written by the previous reverse step's last main-stream kernel (or, in the first reverse
+  // step, by the matching-loss backward kernel), i.e. by the immediate predecessor; from the second GEMM on it is.
   const int kOldA = early_loads() ? 1 : 0, kOldB = early_loads() ? 2 : 0;
   cudaStream_t st = L.main;
   const int B = m.B, d = m.d, dt = m.dt, Bp = m.Bp;
@@ -385,7 +385,7 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   const float *V1 = v + m.oW1, *c1 = v + m.ob1, *V2 = v + m.oW2, *c2 = v + m.ob2, *gamd = v + m.og, *betd = v + m.obt;
   // pd = Yb V1^T + c1 ; hd = gelu'(p) pd
   int sp = 1;
-  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), w.pa, &sp, st, v_fresh ? kOldA : (kOldA | kOldB))));
+  CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), w.pa, &sp, st, kOldA)));
   prof_mark("gemm_partial<true,true> A=s.Yb", st);
   launch_k(epi_pd_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, c1, s.p, B, d, w.pd, w.hd);
   prof_mark("epi_pd_kernel", st);
@@ -423,9 +423,9 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   prof_mark("gemm_store<true,false> A=w.Gd", L.s1);
   launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pc, 1, Bd, perm, d, lr, scale, w.dXn);
   prof_mark("scatter_add_rows_kernel", L.s1);
-  if (!fused_nce) {
-    launch_k(nce_t_finish_kernel, 1, 128, 0, st, w.rowA, w.rowB, B, lr, scale, dlr, dscale);
-    prof_mark("nce_t_finish_kernel", st);
+  if (!fused_nce) {        // the dlr / dscale accumulation is off the critical path: side stream, ordered step to step
+    launch_k(nce_t_finish_kernel, 1, 128, 0, L.s1, w.rowA, w.rowB, B, lr, scale, dlr, dscale);
+    prof_mark("nce_t_finish_kernel", L.s1);
   }
   // dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
   CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st, kOldB)));
@@ -456,13 +456,14 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   prof_mark("gemm_partial<true,false> A=w.dpd", L.s1);
   launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pe, sp_y, (size_t)B * dt, perm, dt, lr, nullptr, dY);
   prof_mark("scatter_add_rows_kernel", L.s1);
+  // small parameters of a_k by column sums: also on the side stream, next to the main stream's W1 GEMM
+  launch_k(colsum_tangent_update_kernel, ceil_div(d, 16), 256, 0, L.s1, 
+      w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
+      v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
+  prof_mark("colsum_tangent_update_kernel", L.s1);
   // main: a_k[W1] = a_{k+1}[W1] - lr dpd^T Yb ; small params by column sums
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), v + m.oW1, a_out + m.oW1, dt, lr, st, kOldB)));
   prof_mark("gemm_axpy<false,false> A=w.dpd", st);
-  launch_k(colsum_tangent_update_kernel, ceil_div(d, 16), 256, 0, st, 
-      w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
-      v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
-  prof_mark("colsum_tangent_update_kernel", st);
   CHECK_RC(lanes_join(L));          // a_k, dXn, dY complete before the next reverse step reuses the scratch buffers
   return check_launch("tangent_step");
 }
@@ -530,7 +531,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   for (int k = K - 1; k >= 0; --k) {
     const float* th = w.traj + (size_t)k * m.P;
     CHECK_RC(tangent_step(m, w, w.sv[k], th, a_cur, a_nxt, lr, scale, masks ? masks + k * Bd : nullptr,
-                          perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L, k == K - 1 || !early_loads()));
+                          perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L));
     float* t = a_cur; a_cur = a_nxt; a_nxt = t;
   }
   launch_k(row_normalise_bwd_kernel, N, 256, 0, st, w.Xn, w.un, w.dXn, nullptr, d, dU);
