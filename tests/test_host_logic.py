@@ -116,3 +116,42 @@ def test_expert_buffer_format_roundtrip(tmp_path):
     assert torch.equal(flat[1, 2], torch.cat([p.reshape(-1) for p in traj[1][2]]))
     with pytest.raises(AssertionError, match="No buffers detected"):
         distill.load_expert_buffers(str(tmp_path / "nope"), "txt", None, device="cpu")
+
+
+def test_networks_mirror_layout_and_errors(golden):
+    """networks.ProjectionHead has the reference's module tree (flat layout == ReparamModule's, golden 'reparam' names);
+    CLIPModel_full refuses to guess an image encoder and every kernel-backed call refuses CPU tensors."""
+    import types
+    from multimodal_dataset_distillation_b200 import networks, ops, infonce, distill
+    from multimodal_dataset_distillation_b200.reparam_module import ReparamModule
+    head = networks.ProjectionHead(768, 2304)
+    rp = ReparamModule(networks.ProjectionHead(768, 2304))
+    assert [f"{mn}.{n}" for mn, n in rp._param_infos] == golden["reparam"]["names"]
+    flat = head.flat_param()
+    assert flat.numel() == golden["reparam"]["param_numel"] == ops.head_numel(768, 2304)
+    off = 0
+    for p in head.parameters():                                   # parameters() order == flat order
+        assert torch.equal(flat[off:off + p.numel()], p.detach().reshape(-1))
+        off += p.numel()
+    head.eval()
+    assert head.dropout_mask(4, "cpu") is None
+    head.train()
+    m = head.dropout_mask(64, "cpu")
+    assert m.shape == (64, 2304) and set(torch.unique(m).tolist()) <= {0.0, 1.0 / 0.9} or torch.allclose(
+        torch.unique(m), torch.tensor([0.0, 1.0 / 0.9]))
+    with pytest.raises(ValueError):
+        networks.CLIPModel_full(types.SimpleNamespace(distill=True))
+    net = networks.CLIPModel_full(types.SimpleNamespace(distill=True), image_encoder=nn.Identity(), image_embedding=16,
+                                  text_embedding=8)
+    assert abs(net.logit_scale - 1 / 0.07) < 1e-9
+    with pytest.raises(RuntimeError):
+        net(torch.randn(4, 16), torch.randn(4, 8), 0)            # CPU tensors: no CPU path
+    with pytest.raises(TypeError):
+        net(torch.randn(4, 16), ["a caption"] * 4, 0)             # raw captions without a text encoder
+    with pytest.raises(RuntimeError):
+        infonce.infonce_loss(torch.randn(4, 8), torch.randn(4, 8), 1.0)
+    with pytest.raises(RuntimeError):
+        ops.nearest_rows(torch.randn(2, 8), torch.randn(5, 8))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            distill.nearest_neighbor(["a", "b"], np.zeros((1, 4), np.float32), np.zeros((2, 4), np.float32))
