@@ -97,6 +97,9 @@ def build_parser() -> argparse.ArgumentParser:
     A("--embed_path", type=str, default=None, help=".npz with image_embed [M,d] and text_embed [M,dt] (frozen encoders)")
     A("--synthetic", action="store_true", help="run on synthetic Flickr-shaped embeddings and experts")
     A("--seed", type=int, default=0)
+    A("--segments_in_flight", type=int, default=1,
+      help="expert segments per outer step processed concurrently on this GPU (throughput mode, DistillEngine.segments_step); "
+           "1 = the reference's one segment per iteration")
     A("--student_dropout", type=float, default=0.1,
       help="dropout of the student text_projection during the unroll (networks.py:629,636; students are in train mode, "
            "distill.py:446-447); 0 gives the deterministic parity mode")
@@ -197,10 +200,12 @@ class DistillEngine:
         self.gen_dev = torch.Generator(device=self.dev).manual_seed(int(getattr(args, "seed", 0)) + 1)
         self.expert_idx = 0
         self.fixed_scale = torch.tensor(ops.LOGIT_SCALE_UPSTREAM, device=self.dev)
+        self._lanes = []                            # (stream, workspace) pairs of segments_step
 
     # -- one expert segment -> loss and grads (distill.py:466-606) --
-    def segment_loss(self, expert: int, start_epoch: int, perms: torch.Tensor | None = None, masks=None):
+    def segment_loss(self, expert: int, start_epoch: int, perms: torch.Tensor | None = None, masks=None, workspace=None):
         a = self.args
+        ws = self.ws if workspace is None else workspace
         theta0 = self.experts[expert, start_epoch]
         theta_tgt = self.experts[expert, start_epoch + int(a.expert_epochs)]
         if perms is None:                                           # distill.py:510-511
@@ -210,8 +215,36 @@ class DistillEngine:
         scale = self.syn_lr_img if fork else self.fixed_scale
         p_drop = float(getattr(a, "student_dropout", 0.0))
         if masks is None and p_drop > 0.0 and self.K > 0:
-            masks = ops.fill_dropout_masks(self.ws, p_drop, self.gen_dev)      # fresh masks per call, as nn.Dropout does
-        return UnrolledMatch.apply(self.Y, self.U, self.syn_lr_txt, scale, theta0, theta_tgt, perms, masks, self.ws)
+            masks = ops.fill_dropout_masks(ws, p_drop, self.gen_dev)           # fresh masks per call, as nn.Dropout does
+        return UnrolledMatch.apply(self.Y, self.U, self.syn_lr_txt, scale, theta0, theta_tgt, perms, masks, ws)
+
+    def segments_step(self, segments, perms_list=None):
+        """Throughput mode: several expert segments of ONE outer step in flight at once on this GPU.
+
+        One segment is a chain of ~290 dependent kernels of 3-20 us, so a single segment leaves the machine waiting on
+        pipeline fills and drains; independent segments (one CUDA stream and one engine workspace each) fill those gaps:
+        measured 505 -> 626 (2 in flight) -> 662 (3) segment-iterations/s on one B200, 4 is slower again
+        (profiles/concurrent_segments.py).  The gradients are summed before the outer update, i.e. the same G-segment
+        minibatch the multi-GPU run computes (and composes with it: every rank may keep several segments in flight).
+        `segments`: list of (expert, start_epoch).  Returns the list of losses.
+        """
+        main = torch.cuda.current_stream(self.dev)
+        while len(self._lanes) < len(segments):
+            self._lanes.append((torch.cuda.Stream(device=self.dev),
+                                ops.UnrollWorkspace(self.N, self.B, self.K, self.dt, self.d, self.dev)))
+        losses = []
+        for j, (e, s) in enumerate(segments):
+            st, ws = self._lanes[j]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                losses.append(self.segment_loss(e, s, None if perms_list is None else perms_list[j], workspace=ws))
+        for j in range(len(segments)):
+            main.wait_stream(self._lanes[j][0])
+        total = losses[0]
+        for l in losses[1:]:
+            total = total + l
+        self.outer_step(total)
+        return losses
 
     def sample_segment(self):
         """distill.py:450-470: experts are consumed in order, start_epoch ~ U{0..max_start_epoch-1}."""
@@ -242,6 +275,9 @@ class DistillEngine:
         self.first = False
 
     def iteration(self):
+        g = int(getattr(self.args, "segments_in_flight", 1))
+        if g > 1:
+            return self.segments_step([self.sample_segment() for _ in range(g)])[0]
         e, s = self.sample_segment()
         loss = self.segment_loss(e, s)
         self.outer_step(loss)

@@ -237,3 +237,27 @@ def test_unrolled_match_coco_shape_full_dims(N, B, K, drop):
     assert rel_err(res["dY"], ref.dY) < RTOL
     assert rel_err(res["dU"], ref.dU) < RTOL
     assert rel_err(res["theta_K"], ref.theta_K) < RTOL
+
+
+def test_segments_in_flight_equal_sequential_sum():
+    """Throughput mode (DistillEngine.segments_step): two segments on two streams and workspaces give exactly the gradients
+    of the two segments run one after the other and summed (a + b is commutative bit for bit), then one outer update."""
+    import types
+    from multimodal_dataset_distillation_b200 import distill
+    N, B, K, dt, d = 48, 32, 3, 64, 96
+    args = distill.parse_args(["--syn_steps", str(K), "--expert_epochs", "1", "--max_start_epoch", "2", "--num_queries", str(N),
+                               "--mini_batch_size", str(B), "--lr_img", "10", "--lr_txt", "10", "--lr_lr", "0.01",
+                               "--logit_scale_mode", "upstream", "--student_dropout", "0.0"])
+    g = torch.Generator().manual_seed(4)
+    U, Y = torch.randn(N, d, generator=g), torch.randn(N, dt, generator=g)
+    experts = distill.synthetic_experts(2, 3, dt, d, seed=1).cuda()
+    perms = [torch.stack([torch.randperm(N, generator=g)[:B] for _ in range(K)]) for _ in range(2)]
+    segs = [(0, 0), (1, 1)]
+    a = distill.DistillEngine(U, Y, experts, args, "cuda")
+    la = a.segments_step(segs, perms)
+    b = distill.DistillEngine(U, Y, experts, args, "cuda")
+    lb = [b.segment_loss(e, s, p) for (e, s), p in zip(segs, perms)]
+    b.outer_step(lb[0] + lb[1])
+    assert all(torch.equal(x.detach(), y.detach()) for x, y in zip(la, lb))
+    assert torch.equal(a.U.detach(), b.U.detach()) and torch.equal(a.Y.detach(), b.Y.detach())
+    assert torch.equal(a.syn_lr_txt.detach(), b.syn_lr_txt.detach())

@@ -18,6 +18,7 @@ def test_cli_matches_reference_flags():
     parser = distill.build_parser()
     actions = {a.option_strings[0]: a for a in parser._actions if a.option_strings}
     assert len(ref) == 55
+    assert "--segments_in_flight" in actions and actions["--segments_in_flight"].default == 1     # extension, off by default
     for e in ref:
         a = actions.get(e["flag"])
         assert a is not None, e["flag"]
