@@ -61,7 +61,7 @@ def itm_eval(scores_i2t, scores_t2i, txt2img, img2txt, return_ranks: bool = Fals
 
 def text_head_flat_param(text_projection) -> torch.Tensor:
     """Flat parameter vector of a ProjectionHead-like module in ReparamModule order (reparam_module.py:28-51)."""
-    if hasattr(text_projection, "flat_param"):
+    if isinstance(getattr(text_projection, "flat_param", None), torch.Tensor):      # ReparamModule-wrapped head
         return text_projection.flat_param.detach()
     mod = text_projection
     return torch.cat([p.detach().reshape(-1) for p in (mod.projection.weight, mod.projection.bias, mod.fc.weight,

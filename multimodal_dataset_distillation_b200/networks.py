@@ -31,7 +31,7 @@ class ProjectionHead(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.layer_norm = nn.LayerNorm(projection_dim)
 
-    def flat_param(self) -> torch.Tensor:
+    def flat_parameters(self) -> torch.Tensor:
         """Parameters in ReparamModule order (reparam_module.py:28-51), differentiable w.r.t. each of them."""
         return torch.cat([p.reshape(-1) for p in (self.projection.weight, self.projection.bias, self.fc.weight,
                                                   self.fc.bias, self.layer_norm.weight, self.layer_norm.bias)])
@@ -48,7 +48,7 @@ class ProjectionHead(nn.Module):
         d = self.fc.out_features
         if mask is None:
             mask = self.dropout_mask(x.shape[0], x.device)
-        return ops.proj_head_forward(self.flat_param().detach(), x.float(), d, mask)
+        return ops.proj_head_forward(self.flat_parameters().detach(), x.float(), d, mask)
 
 
 class _ClipLoss(torch.autograd.Function):
@@ -105,7 +105,7 @@ class CLIPModel_full(nn.Module):
         else:
             raise TypeError("captions must be precomputed text embeddings (a tensor) when no text_encoder is attached")
         mask = self.text_projection.dropout_mask(text_features.shape[0], image_features.device)
-        loss, top1 = clip_contrastive_loss(self.text_projection.flat_param(), text_features, image_features,
+        loss, top1 = clip_contrastive_loss(self.text_projection.flat_parameters(), text_features, image_features,
                                            self.logit_scale, mask)
         acc = top1.sum().item() / 2                               # networks.py:884-886
         return loss, acc

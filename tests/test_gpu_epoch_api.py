@@ -128,3 +128,34 @@ def test_evaluate_synset_signature_and_result():
     ref = RR.itm_eval_ref(S, np.ascontiguousarray(S.T), loader.dataset.txt2img, loader.dataset.img2txt)
     for k in RR.RESULT_KEYS:
         assert abs(res[k] - ref[k]) <= 100.0 / n_img + 1e-9, k
+
+
+def test_evaluate_synset_with_kernel_backed_clip_model_tracks_torch_training():
+    """networks.CLIPModel_full (vldd_clip_loss under autograd) trained by evaluate_synset follows the same trajectory as
+    the plain-torch model with identical initial weights: same per-epoch training accuracy, parameters within fp32
+    tolerance after the SGD steps, same retrieval result."""
+    import copy
+    import types
+    from multimodal_dataset_distillation_b200 import epoch, networks
+    torch.manual_seed(1)
+    dt, d, din, n_img, caps = 16, 32, 24, 40, 5
+    ref_net = FakeCLIP(dt, d, din)
+    ref_net.text_projection.dropout.p = 0.0                       # deterministic: no dropout draws to align
+    enc = copy.deepcopy(ref_net.image_encoder)
+    net = networks.CLIPModel_full(types.SimpleNamespace(distill=True), image_encoder=enc, image_embedding=d, text_embedding=dt)
+    net.text_projection.dropout.p = 0.0
+    net.text_projection.load_state_dict(ref_net.text_projection.state_dict())     # same module tree -> same keys
+    images_train, labels_train = torch.randn(16, din), torch.randn(16, dt)
+    feats, bert = torch.randn(n_img, din), torch.randn(n_img * caps, dt)
+    out = []
+    for model in (ref_net, net):
+        torch.manual_seed(7)                                      # same DataLoader shuffles
+        args = types.SimpleNamespace(device="cuda", lr_net=0.05, epoch_eval_train=2, batch_train=8, distill=False)
+        out.append(epoch.evaluate_synset(0, model, images_train, labels_train, _loader(feats, n_img, caps), args, bert))
+    (_, accs_ref, res_ref), (_, accs_got, res_got) = out
+    assert accs_got == accs_ref
+    for (n1, p1), (n2, p2) in zip(sorted(ref_net.text_projection.named_parameters()), sorted(net.text_projection.named_parameters())):
+        assert n1 == n2 and float((p1 - p2).abs().max()) <= 1e-4 * float(p1.abs().max()) + 1e-6, n1
+    assert float((ref_net.image_encoder.weight - net.image_encoder.weight).abs().max()) <= 1e-4
+    for k in RR.RESULT_KEYS:
+        assert abs(res_got[k] - res_ref[k]) <= 100.0 / n_img + 1e-9, k

@@ -128,7 +128,7 @@ def test_networks_mirror_layout_and_errors(golden):
     head = networks.ProjectionHead(768, 2304)
     rp = ReparamModule(networks.ProjectionHead(768, 2304))
     assert [f"{mn}.{n}" for mn, n in rp._param_infos] == golden["reparam"]["names"]
-    flat = head.flat_param()
+    flat = head.flat_parameters()
     assert flat.numel() == golden["reparam"]["param_numel"] == ops.head_numel(768, 2304)
     off = 0
     for p in head.parameters():                                   # parameters() order == flat order
