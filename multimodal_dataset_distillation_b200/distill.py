@@ -361,7 +361,7 @@ def main(args):
     for it in range(int(args.Iteration) + 1):
         loss = eng.iteration()
         if it % 10 == 0:
-            v = float(loss)
+            v = float(loss.detach())
             if math.isnan(v):                                                # distill.py:599-600
                 break
             print("%s iter = %04d, loss = %.4f" % (datetime.datetime.now().strftime("[%Y-%m-%d %H:%M:%S]"), it, v))

@@ -261,3 +261,37 @@ def test_segments_in_flight_equal_sequential_sum():
     assert all(torch.equal(x.detach(), y.detach()) for x, y in zip(la, lb))
     assert torch.equal(a.U.detach(), b.U.detach()) and torch.equal(a.Y.detach(), b.Y.detach())
     assert torch.equal(a.syn_lr_txt.detach(), b.syn_lr_txt.detach())
+
+
+def test_distill_main_from_reference_format_files(tmp_path, capsys):
+    """distill.main end to end from files laid out like the reference's: txt_replay_buffer_{n}.pt = list[expert] of
+    list[snapshot] of list[param tensors] (buffer.py:64-68, 104-112) and an .npz of frozen image / text embeddings."""
+    from multimodal_dataset_distillation_b200 import distill
+    dt, d, M = 24, 40, 64
+    g = torch.Generator().manual_seed(3)
+    shapes = [(d, dt), (d,), (d, d), (d,), (d,), (d,)]                      # ReparamModule order of ProjectionHead
+    for n in range(2):
+        experts = []
+        for _ in range(2):
+            snap = [torch.randn(*s, generator=g) * 0.1 for s in shapes]
+            traj = [snap]
+            for _ in range(3):
+                traj.append([p + 0.01 * torch.randn(p.shape, generator=g) for p in traj[-1]])
+            experts.append(traj)
+        torch.save(experts, tmp_path / f"txt_replay_buffer_{n}.pt")
+    np.savez(tmp_path / "embeds.npz", image_embed=torch.randn(M, d, generator=g).numpy(),
+             text_embed=torch.randn(M, dt, generator=g).numpy())
+    flat = distill.load_expert_buffers(str(tmp_path), "txt")
+    assert tuple(flat.shape) == (4, 4, d * dt + d + d * d + 3 * d) and flat.is_cuda
+    args = distill.parse_args(["--buffer_path", str(tmp_path), "--embed_path", str(tmp_path / "embeds.npz"), "--num_queries", "16",
+                               "--mini_batch_size", "16", "--syn_steps", "3", "--expert_epochs", "1", "--max_start_epoch", "2",
+                               "--Iteration", "12", "--lr_img", "1", "--lr_txt", "1", "--lr_lr", "0.001"])
+    eng = distill.main(args)
+    out = capsys.readouterr().out
+    assert "iter = 0000" in out and "iter = 0010" in out
+    assert torch.isfinite(eng.Y).all() and torch.isfinite(eng.U).all()
+    assert eng.experts.shape[0] == 2 and eng.expert_idx == 13 % 2           # --max_files 1 (distill.py:630): experts of file 0, consumed in order
+    # the fork's logit scale is the learnable syn_lr_img: it has received gradient and moved (distill.py:548)
+    assert float(eng.syn_lr_img) != float(args.lr_teacher_img)
+    with pytest.raises(AssertionError):
+        distill.load_expert_buffers(str(tmp_path / "nothing_here"), "txt")
