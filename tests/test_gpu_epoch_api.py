@@ -159,3 +159,26 @@ def test_evaluate_synset_with_kernel_backed_clip_model_tracks_torch_training():
     assert float((ref_net.image_encoder.weight - net.image_encoder.weight).abs().max()) <= 1e-4
     for k in RR.RESULT_KEYS:
         assert abs(res_got[k] - res_ref[k]) <= 100.0 / n_img + 1e-9, k
+
+
+def test_epoch_with_amp_scaler_runs_the_kernel_backed_model():
+    """Fork signature epoch(e, dataloader, net, optimizer_img, optimizer_txt, args, scaler) (epoch.py:59-98): autocast +
+    GradScaler around the kernel-backed CLIPModel_full; the scaled loss reaches our backward as `gout`, parameters move,
+    the returned averages are finite."""
+    import types
+    from multimodal_dataset_distillation_b200 import epoch, networks
+    torch.manual_seed(2)
+    dt, d, din = 16, 32, 24
+    net = networks.CLIPModel_full(types.SimpleNamespace(distill=True), image_encoder=nn.Linear(din, d), image_embedding=d,
+                                  text_embedding=dt).cuda()
+    before = net.text_projection.fc.weight.detach().clone()
+    enc_before = net.image_encoder.weight.detach().clone()
+    args = types.SimpleNamespace(device="cuda", distill=True)
+    opt_i = torch.optim.SGD(net.image_encoder.parameters(), lr=0.05)
+    opt_t = torch.optim.SGD(net.text_projection.parameters(), lr=0.05)
+    ds = torch.utils.data.TensorDataset(torch.randn(32, din), torch.randn(32, dt))
+    loader = torch.utils.data.DataLoader(ds, batch_size=8)
+    loss_avg, acc_avg = epoch.epoch(0, loader, net, opt_i, opt_t, args, scaler=torch.amp.GradScaler("cuda"))
+    assert np.isfinite(loss_avg) and 0.0 <= acc_avg <= 8.0
+    assert not torch.equal(before, net.text_projection.fc.weight.detach())
+    assert not torch.equal(enc_before, net.image_encoder.weight.detach())
