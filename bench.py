@@ -123,9 +123,9 @@ def algorithmic_bytes_per_iteration(K, P):
     return 4 * P * (2 * K + 3 + 4 * K)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-# `ncu --set full` capture (profiles/ncu_r01_tc_gemm_partial_f2.txt; same shape inside bench.py: profiles/ncu_r01_bench_tc_gemm_kernels.txt).
-DOMINANT_KERNEL_NCU_TRAFFIC_BYTES = 22178816 + 0     # read + write (the 7.4 MB of partial slabs stay in L2)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+# capture of that launch inside one distill iteration (profiles/ncu_r01e_f2_summary.txt).
+DOMINANT_KERNEL_NCU_TRAFFIC_BYTES = 22204928 + 0     # read + write (the 7.4 MB of partial slabs stay in L2)
 
 
 def bench_dominant_kernel(dev, experts, reps=20):
