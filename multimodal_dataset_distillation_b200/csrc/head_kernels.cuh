@@ -58,16 +58,19 @@ __device__ __forceinline__ float4 sum_slabs4(const float* __restrict__ part, int
   return v;
 }
 // Sum with four interleaved accumulators (slab s goes to accumulator s % 4, the tail beyond the last multiple of four
-// to accumulator 0; result (a0 + a1) + (a2 + a3)), loads issued twelve at a time: for the 36-slab logits GEMM.
+// to accumulator 0; result (a0 + a1) + (a2 + a3)), loads issued kChunk at a time: for the 36-slab logits GEMM, whose
+// row kernels have one element per thread and nothing else to overlap the loads with -- one L2 round trip instead of nine.
+template <int kChunk = 36>
 __device__ __forceinline__ float sum_slabs_ilp(const float* __restrict__ part, int splits, size_t stride, size_t idx) {
+  static_assert(kChunk % 4 == 0, "chunks keep the slab -> accumulator mapping");
   float a[4] = {0.f, 0.f, 0.f, 0.f};
   const int n4 = splits & ~3;
-  for (int s0 = 0; s0 < splits; s0 += 12) {
-    float t[12];
+  for (int s0 = 0; s0 < splits; s0 += kChunk) {
+    float t[kChunk];
 #pragma unroll
-    for (int u = 0; u < 12; ++u) t[u] = (s0 + u < splits) ? part[(size_t)(s0 + u) * stride + idx] : 0.f;
+    for (int u = 0; u < kChunk; ++u) t[u] = (s0 + u < splits) ? part[(size_t)(s0 + u) * stride + idx] : 0.f;
 #pragma unroll
-    for (int u = 0; u < 12; ++u) {
+    for (int u = 0; u < kChunk; ++u) {
       if (s0 + u < n4) a[u & 3] += t[u];
       else a[0] += t[u];                        // tail slabs (and the zeros past `splits`)
     }
