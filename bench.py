@@ -110,7 +110,7 @@ def bench_args():
 
 def kernel_launches_per_iteration(K):
     # this library's kernels only (torch's mask / bookkeeping kernels are not counted); checked against the ncu launch
-    # list profiles/launches_r01e.csv (288 at K = 8):
+    # list profiles/launches_r01g.csv (288 at K = 8):
     #   forward step: 7 GEMMs (p, f, S, dyn, dh, dW2, dW1) + 8 row / element-wise kernels
     #   reverse step: 9 GEMMs + 11 row / element-wise / scatter kernels
     #   per call: row normalise, gather, matching loss fwd + bwd, normalise bwd; outer update: 3 momentum-SGD launches
@@ -312,8 +312,8 @@ def run_ours(opt):
                          "frac": dk_achieved / pk["hbm"], "traffic": DOMINANT_KERNEL_NCU_TRAFFIC_BYTES,
                          "peak_source": pk["src"],
                          "kernel": "vldd::tc::tc_gemm_kernel<K-major,K-major,3xTF32,EpiPartial> launched as f = h W2^T "
-                                   "(M=100, N=K=2304, split-K %d): the GEMM family is ~59%% of the iteration's kernel time "
-                                   "(profiles/launches_r01d_summary.txt)" % dk["splits"],
+                                   "(M=100, N=K=2304, split-K %d): the GEMM family is ~62%% of the iteration's kernel time "
+                                   "(profiles/launches_r01g_summary.txt)" % dk["splits"],
                          "algorithmic_bytes_per_launch": dk["abytes"], "avg_launch_us": dk["avg_us"],
                          "median_launch_us": dk["median_us"], "launches_timed": dk["launches"],
                          "tensor_tflops_3xtf32_equiv": 3 * dk["flops"] / (dk["avg_us"] * 1e-6) / 1e12,
