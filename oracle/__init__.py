@@ -7,6 +7,10 @@ It exists to check the CUDA path.  Only ``tests/``, ``__graft_entry__.smoke()`` 
 under ``multimodal_dataset_distillation_b200/`` imports it, and the product path
 raises if the CUDA library is missing -- there is no CPU fallback.
 
+Contents: ``retrieval_ref.py`` (numpy), ``distill_ref.py`` (torch CPU, fp64 capable) and ``c/itm_eval_ref.c``, a plain-C
+restatement of itm_eval's integer part (ranks with the index tie-break, recall@1/5/10) built by ``c/Makefile`` into
+``_ref/libitm_ref.so`` -- an independent cross-check of the numpy one (``retrieval_ref.itm_eval_c``).
+
 Parity pinning: the reference ships NO tests, golden vectors or fixtures for this
 path ("parity unpinned" upstream).  The oracle is therefore
 pinned against outputs of the reference itself, run in the build container:

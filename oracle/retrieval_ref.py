@@ -190,3 +190,44 @@ def cosine_matrix(query: np.ndarray, bank: np.ndarray) -> np.ndarray:
         n[n == 0.0] = 1.0
         return x / n
     return unit(query) @ unit(bank).T
+
+
+# ---- plain-C restatement of the integer part (oracle/c/itm_eval_ref.c), an independent cross-check of the numpy one -----
+def c_oracle():
+    """ctypes handle of oracle/_ref/libitm_ref.so (built by `make -C oracle/c`, which __graft_entry__.build() runs)."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "_ref", "libitm_ref.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-s", "-C", os.path.join(here, "c")], check=True)
+    lib = ctypes.CDLL(so)
+    P = ctypes.c_void_p
+    lib.itm_ranks_rows.argtypes = [P, ctypes.c_int, ctypes.c_int, P, P, P]
+    lib.itm_ranks_rows.restype = None
+    lib.itm_result.argtypes = [P, ctypes.c_int, P, ctypes.c_int, P]
+    lib.itm_result.restype = None
+    return lib
+
+
+def itm_eval_c(scores_i2t, scores_t2i, txt2img, img2txt, return_ranks=False):
+    """itm_eval through the C restatement: same inputs as the reference (numpy matrices + the dataset's dict maps)."""
+    lib = c_oracle()
+    s1 = np.ascontiguousarray(scores_i2t, dtype=np.float32)
+    s2 = np.ascontiguousarray(scores_t2i, dtype=np.float32)
+    I, T = s1.shape
+    ptr = np.zeros(I + 1, dtype=np.int32)
+    lists = [np.atleast_1d(np.asarray(img2txt[i], dtype=np.int32)) for i in range(I)]
+    ptr[1:] = np.cumsum([len(l) for l in lists])
+    idx = np.concatenate(lists).astype(np.int32)
+    t2i = np.asarray([txt2img[t] for t in range(T)], dtype=np.int32)
+    r1, r2 = np.empty(I, dtype=np.int32), np.empty(T, dtype=np.int32)
+    a = lambda x: x.ctypes.data
+    lib.itm_ranks_rows(a(s1), I, T, a(ptr), a(idx), a(r1))
+    one = np.arange(T + 1, dtype=np.int32)
+    lib.itm_ranks_rows(a(s2), T, I, a(one), a(t2i), a(r2))
+    out = np.zeros(9, dtype=np.float64)
+    lib.itm_result(a(r1), I, a(r2), T, a(out))
+    res = {k: float(v) for k, v in zip(RESULT_KEYS, out)}
+    return (res, r1, r2) if return_ranks else res

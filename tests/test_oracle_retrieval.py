@@ -99,3 +99,32 @@ def test_topk_fill_keeps_exactly_k_and_is_idempotent():
     a = RR.ranks_i2t(S, img2txt)
     b = RR.ranks_i2t(F, img2txt)
     assert np.array_equal(a < 10, b < 10) and np.array_equal(a[a < 128], b[a < 128])
+
+
+def test_c_oracle_agrees_with_numpy_oracle_and_reference_goldens(golden):
+    """oracle/c/itm_eval_ref.c (plain C, built into oracle/_ref/) against the numpy restatement on every golden case, and
+    against the reference's own itm_eval numbers on the tie-free ones."""
+    for case in golden["retrieval"]:
+        if case["I"] >= 1000 and case["fill"]:
+            continue
+        S, St, (txt2img, img2txt) = _case_inputs(case)
+        res, r_i, r_t = RR.itm_eval_c(S, St, txt2img, img2txt, return_ranks=True)
+        assert np.array_equal(r_i, RR.ranks_i2t(S, img2txt)) and np.array_equal(r_t, RR.ranks_t2i(St, txt2img))
+        ref = RR.recall_dict(r_i, r_t)
+        assert tuple(res.keys()) == RR.RESULT_KEYS and all(abs(res[k] - ref[k]) < 1e-12 for k in res)
+        if not case["quant"] and not case["fill"]:
+            for k, v in case["fork"].items():
+                assert abs(res[k] - v) < 1e-9, (case["name"], k)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(1, 12), st.integers(1, 4), st.integers(0, 2 ** 31 - 1), st.sampled_from([0, 2, 8]))
+def test_c_oracle_random_ties(n_img, caps, seed, quant):
+    rng = np.random.default_rng(seed)
+    S = rng.standard_normal((n_img, n_img * caps)).astype(np.float32)
+    if quant:
+        S = (np.round(S * quant) / quant).astype(np.float32)          # heavy ties: index tie-break must agree
+    St = np.ascontiguousarray(S.T)
+    txt2img, img2txt = RR.flickr_maps(n_img, caps)
+    res, r_i, r_t = RR.itm_eval_c(S, St, txt2img, img2txt, return_ranks=True)
+    assert np.array_equal(r_i, RR.ranks_i2t(S, img2txt)) and np.array_equal(r_t, RR.ranks_t2i(St, txt2img))
