@@ -60,7 +60,10 @@ __device__ __forceinline__ float4 sum_slabs4(const float* __restrict__ part, int
 // Sum with four interleaved accumulators (slab s goes to accumulator s % 4, the tail beyond the last multiple of four
 // to accumulator 0; result (a0 + a1) + (a2 + a3)), loads issued kChunk at a time: for the 36-slab logits GEMM, whose
 // row kernels have one element per thread and nothing else to overlap the loads with -- one L2 round trip instead of nine.
-template <int kChunk = 36>
+#ifndef VLDD_NCE_CHUNK
+#define VLDD_NCE_CHUNK 36
+#endif
+template <int kChunk = VLDD_NCE_CHUNK>
 __device__ __forceinline__ float sum_slabs_ilp(const float* __restrict__ part, int splits, size_t stride, size_t idx) {
   static_assert(kChunk % 4 == 0, "chunks keep the slab -> accumulator mapping");
   float a[4] = {0.f, 0.f, 0.f, 0.f};
