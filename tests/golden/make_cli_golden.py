@@ -1,6 +1,7 @@
-"""Extract the reference CLI (flag, type, default, action, choices) from /root/reference/distill.py:625-679 with ast.
+"""Extract the reference CLIs (flag, type, default, action, choices) with ast: /root/reference/distill.py:625-679 ->
+tests/golden/cli.json, /root/reference/buffer.py:119-160 -> tests/golden/cli_buffer.json.
 
-    python tests/golden/make_cli_golden.py      # build container only; writes tests/golden/cli.json
+    python tests/golden/make_cli_golden.py      # build container only
 """
 import ast
 import json
@@ -17,7 +18,7 @@ def lit(node):
         return "<non-literal>"
 
 
-def main():
+def main(SRC=SRC, out="cli.json", source="distill.py:625-679"):
     tree = ast.parse(open(SRC).read())
     flags = []
     for node in ast.walk(tree):
@@ -33,10 +34,11 @@ def main():
                     entry[kw.arg] = lit(kw.value)
             flags.append(entry)
     flags.sort(key=lambda e: e["line"])
-    with open(os.path.join(HERE, "cli.json"), "w") as f:
-        json.dump({"source": "distill.py:625-679", "flags": flags}, f, indent=1)
-    print(len(flags), "flags")
+    with open(os.path.join(HERE, out), "w") as f:
+        json.dump({"source": source, "flags": flags}, f, indent=1)
+    print(out, len(flags), "flags")
 
 
 if __name__ == "__main__":
     main()
+    main("/root/reference/buffer.py", "cli_buffer.json", "buffer.py:119-160")

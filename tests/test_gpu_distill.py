@@ -295,3 +295,40 @@ def test_distill_main_from_reference_format_files(tmp_path, capsys):
     assert float(eng.syn_lr_img) != float(args.lr_teacher_img)
     with pytest.raises(AssertionError):
         distill.load_expert_buffers(str(tmp_path / "nothing_here"), "txt")
+
+
+def test_buffer_writes_reference_format_and_distill_reads_it(tmp_path, capsys):
+    """buffer.main (text-head experts on frozen embeddings, kernel-backed loss) -> txt_replay_buffer_{n}.pt in the
+    reference layout -> distill.load_expert_buffers / distill.main consume it; the teacher's loss goes down."""
+    from multimodal_dataset_distillation_b200 import buffer, distill
+    dt, d, M = 24, 40, 256
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(M, d, generator=g)
+    txt = img[:, :dt] * 0.8 + 0.3 * torch.randn(M, dt, generator=g)
+    ti = torch.randn(20, d, generator=g)
+    tt = ti.repeat_interleave(5, 0)[:, :dt] * 0.8 + 0.3 * torch.randn(100, dt, generator=g)
+    np.savez(tmp_path / "embeds.npz", image_embed=img.numpy(), text_embed=txt.numpy(), test_image_embed=ti.numpy(),
+             test_text_embed=tt.numpy())
+    args = buffer.build_parser().parse_args(["--buffer_path", str(tmp_path / "buffers"), "--embed_path", str(tmp_path / "embeds.npz"),
+                                             "--num_experts", "2", "--train_epochs", "4", "--batch_train", "64",
+                                             "--lr_teacher_txt", "0.1", "--image_encoder", "nfnet", "--decay"])
+    files = buffer.main(args)
+    out = capsys.readouterr().out
+    assert len(files) == 2 and all(os.path.basename(f) == f"txt_replay_buffer_{i}.pt" for i, f in enumerate(files))
+    assert files[0].startswith(os.path.join(str(tmp_path / "buffers"), "flickr", "nfnet", "bert")) and "R@Mean" in out
+    traj = torch.load(files[0])
+    assert isinstance(traj, list) and len(traj) == 1 and len(traj[0]) == 5            # 1 expert, initial + 4 epoch snapshots
+    assert [tuple(p.shape) for p in traj[0][0]] == [(d, dt), (d,), (d, d), (d,), (d,), (d,)] and not traj[0][0][0].is_cuda
+    flat = distill.load_expert_buffers(os.path.dirname(files[0]), "txt", max_files=2)
+    assert tuple(flat.shape) == (2, 5, d * dt + d + d * d + 3 * d)
+    assert not torch.equal(flat[0, 0], flat[0, 4]) and not torch.equal(flat[0, 0], flat[1, 0])
+    # the teacher learns: InfoNCE of the last snapshot on the training pairs is below the first one's
+    from multimodal_dataset_distillation_b200 import ops
+    l0 = float(ops.clip_loss(flat[0, 0], txt[:64].cuda(), img[:64].cuda())["loss"])
+    l4 = float(ops.clip_loss(flat[0, 4], txt[:64].cuda(), img[:64].cuda())["loss"])
+    assert l4 < l0
+    dargs = distill.parse_args(["--buffer_path", os.path.dirname(files[0]), "--embed_path", str(tmp_path / "embeds.npz"),
+                                "--num_queries", "32", "--mini_batch_size", "32", "--syn_steps", "2", "--expert_epochs", "1",
+                                "--max_start_epoch", "3", "--Iteration", "3", "--max_files", "2", "--lr_img", "1", "--lr_txt", "1"])
+    eng = distill.main(dargs)
+    assert eng.experts.shape[0] == 2 and torch.isfinite(eng.Y).all()

@@ -156,3 +156,25 @@ def test_networks_mirror_layout_and_errors(golden):
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             distill.nearest_neighbor(["a", "b"], np.zeros((1, 4), np.float32), np.zeros((2, 4), np.float32))
+
+
+def test_buffer_cli_matches_reference_flags():
+    """Every flag of buffer.py:119-160 exists with the same type and default (tests/golden/cli_buffer.json, extracted with ast)."""
+    from multimodal_dataset_distillation_b200 import buffer
+    with open(os.path.join(GOLDEN_DIR, "cli_buffer.json")) as f:
+        ref = json.load(f)["flags"]
+    actions = {a.option_strings[0]: a for a in buffer.build_parser()._actions if a.option_strings}
+    assert len(ref) == 35
+    for e in ref:
+        a = actions.get(e["flag"])
+        assert a is not None, e["flag"]
+        if e.get("action") == "store_true":
+            assert a.default is False and a.nargs == 0
+        if "default" in e and e["default"] != "<non-literal>":
+            assert a.default == e["default"], e["flag"]
+        if "type" in e and e["type"] in ("int", "float", "str", "bool"):
+            assert a.type is {"int": int, "float": float, "str": str, "bool": bool}[e["type"]], e["flag"]
+        if "choices" in e:
+            assert set(e["choices"]) <= set(a.choices), e["flag"]
+    args = buffer.build_parser().parse_args(["--dataset", "coco", "--image_encoder", "nfnet"])
+    assert buffer.save_dir_of(args) == os.path.join("./buffers", "coco", "nfnet", "bert")       # buffer.py:27-31
