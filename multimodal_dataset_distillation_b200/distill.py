@@ -20,6 +20,7 @@ import datetime
 import glob
 import math
 import os
+import types
 
 import numpy as np
 import torch
@@ -340,6 +341,46 @@ def synthetic_experts(n_experts: int, n_snapshots: int, dt: int, d: int, seed: i
     return torch.stack(out)
 
 
+class _EmbeddingLoader(list):
+    """Test "dataloader" over precomputed image-encoder embeddings: yields (features, ids) batches and carries the
+    dataset maps that epoch_test / itm_eval read (flickr30k_dataset.py:110-118)."""
+
+
+def _load_test_split(args, dev):
+    """Optional test embeddings next to the training ones: test_image_embed [I,d], test_text_embed [T,dt] (T = C * I)."""
+    if getattr(args, "embed_path", None) is None or getattr(args, "synthetic", False):
+        return None
+    z = np.load(args.embed_path)
+    if "test_image_embed" not in z.files:
+        return None
+    ti, tt = torch.from_numpy(z["test_image_embed"]).float(), torch.from_numpy(z["test_text_embed"]).float()
+    caps = tt.shape[0] // ti.shape[0]
+    loader = _EmbeddingLoader((ti[i:i + 256], torch.arange(i, min(i + 256, ti.shape[0]))) for i in range(0, ti.shape[0], 256))
+    loader.dataset = types.SimpleNamespace(txt2img={t: t // caps for t in range(tt.shape[0])},
+                                           img2txt={i: list(range(caps * i, caps * i + caps)) for i in range(ti.shape[0])})
+    return dict(loader=loader, bert=tt)
+
+
+def evaluate_synthetic_set(eng: "DistillEngine", test, args):
+    """distill.py:293-330: `num_eval` fresh models trained on the current synthetic set (evaluate_synset, lr_net = the
+    learned syn_lr_img), each retrieval-evaluated on the test split; returns the list of result dicts.  Mode A: the
+    synthetic "images" are image-encoder embeddings, so the evaluated model's image tower is the identity."""
+    from . import epoch as epoch_mod, networks
+    results = []
+    for it_eval in range(int(args.num_eval)):
+        net_eval = networks.CLIPModel_full(args, image_encoder=torch.nn.Identity(), image_embedding=eng.d, text_embedding=eng.dt)
+        ev = types.SimpleNamespace(device=str(eng.dev), lr_net=float(eng.syn_lr_img.detach()), epoch_eval_train=int(args.epoch_eval_train),
+                                   batch_train=int(args.batch_train), distill=True)
+        _, _acc, val = epoch_mod.evaluate_synset(it_eval, net_eval, eng.U.detach().clone(), eng.Y.detach().clone(), test["loader"],
+                                                 ev, test["bert"])
+        print("Evaluate_%02d: Img R@1 = %.4f, Img R@5 = %.4f, Img R@10 = %.4f, Img R@Mean = %.4f, Txt R@1 = %.4f, Txt R@5 = %.4f, "
+              "Txt R@10 = %.4f, Txt R@Mean = %.4f, R@Mean = %.4f" % (it_eval, val["img_r1"], val["img_r5"], val["img_r10"],
+                                                                     val["img_r_mean"], val["txt_r1"], val["txt_r5"], val["txt_r10"],
+                                                                     val["txt_r_mean"], val["r_mean"]))
+        results.append(val)
+    return results
+
+
 def main(args):
     if not torch.cuda.is_available():
         raise RuntimeError("distill needs a CUDA device (sm_100a); there is no CPU path")
@@ -358,7 +399,12 @@ def main(args):
         img, txt = torch.from_numpy(z["image_embed"][sel]), torch.from_numpy(z["text_embed"][sel])
         experts = load_expert_buffers(args.buffer_path, "txt", args.max_files, dev)
     eng = DistillEngine(img, txt, experts, args, dev)
+    test = _load_test_split(args, dev)
+    eval_it_pool = list(range(0, int(args.Iteration) + 1, max(int(args.eval_it), 1))) if test is not None else []   # distill.py:285
+    eng.eval_history = []
     for it in range(int(args.Iteration) + 1):
+        if it in eval_it_pool:                                               # distill.py:293-330
+            eng.eval_history.append((it, evaluate_synthetic_set(eng, test, args)))
         loss = eng.iteration()
         if it % 10 == 0:
             v = float(loss.detach())

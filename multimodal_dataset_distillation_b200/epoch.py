@@ -150,6 +150,16 @@ def epoch(e, dataloader, net, optimizer_img, optimizer_txt, args, scaler=None):
     return loss_avg / max(num_exp, 1), acc_avg / max(num_exp, 1)
 
 
+class _NullOptimizer:
+    """Stands in for the image optimiser when the image tower has no parameters."""
+
+    def zero_grad(self, *a, **k):
+        pass
+
+    def step(self, *a, **k):
+        pass
+
+
 def evaluate_synset(it_eval, net, images_train, labels_train, testloader, args, bert_test_embed, return_loss=False):
     """Train `net` on the synthetic set, then retrieval-evaluate it (epoch_original.py:164-195 / epoch.py:348-397)."""
     net = net.to(args.device)
@@ -158,7 +168,8 @@ def evaluate_synset(it_eval, net, images_train, labels_train, testloader, args, 
     args.distill = True                                           # fork epoch.py:357
     lr = float(args.lr_net)
     Epoch = int(args.epoch_eval_train)
-    optimizer_img = torch.optim.SGD(net.image_encoder.parameters(), lr=lr, momentum=0.9, weight_decay=0.0005)
+    img_params = list(net.image_encoder.parameters())              # empty when the image tower is frozen embeddings (identity)
+    optimizer_img = (torch.optim.SGD(img_params, lr=lr, momentum=0.9, weight_decay=0.0005) if img_params else _NullOptimizer())
     optimizer_txt = torch.optim.SGD(net.text_projection.parameters(), lr=lr, momentum=0.9, weight_decay=0.0005)
     dst_train = torch.utils.data.TensorDataset(images_train, labels_train)
     trainloader = torch.utils.data.DataLoader(dst_train, batch_size=args.batch_train, shuffle=True, num_workers=0)

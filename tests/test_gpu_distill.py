@@ -329,6 +329,11 @@ def test_buffer_writes_reference_format_and_distill_reads_it(tmp_path, capsys):
     assert l4 < l0
     dargs = distill.parse_args(["--buffer_path", os.path.dirname(files[0]), "--embed_path", str(tmp_path / "embeds.npz"),
                                 "--num_queries", "32", "--mini_batch_size", "32", "--syn_steps", "2", "--expert_epochs", "1",
-                                "--max_start_epoch", "3", "--Iteration", "3", "--max_files", "2", "--lr_img", "1", "--lr_txt", "1"])
+                                "--max_start_epoch", "3", "--Iteration", "3", "--max_files", "2", "--lr_img", "1", "--lr_txt", "1",
+                                "--eval_it", "2", "--num_eval", "2", "--epoch_eval_train", "3", "--batch_train", "16"])
     eng = distill.main(dargs)
     assert eng.experts.shape[0] == 2 and torch.isfinite(eng.Y).all()
+    # evaluation block (distill.py:293-330): iterations 0 and 2, two fresh models each, the nine reference keys
+    assert [it for it, _ in eng.eval_history] == [0, 2] and all(len(r) == 2 for _, r in eng.eval_history)
+    assert list(eng.eval_history[0][1][0].keys()) == list(ops.RESULT_KEYS)
+    assert "Evaluate_01: Img R@1" in capsys.readouterr().out
