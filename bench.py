@@ -110,11 +110,12 @@ def bench_args():
 
 def kernel_launches_per_iteration(K):
     # this library's kernels only (torch's mask / bookkeeping kernels are not counted); checked against the ncu launch
-    # list profiles/launches_r01g.csv (288 at K = 8):
+    # list profiles/launches_r01g.csv (288 at K = 8, plus the one-thread index-check kernel added since):
     #   forward step: 7 GEMMs (p, f, S, dyn, dh, dW2, dW1) + 8 row / element-wise kernels
     #   reverse step: 9 GEMMs + 11 row / element-wise / scatter kernels
-    #   per call: row normalise, gather, matching loss fwd + bwd, normalise bwd; outer update: 3 momentum-SGD launches
-    return 15 * K + 20 * K + 5 + 3
+    #   per call: row normalise, gather, matching loss fwd + bwd, normalise bwd, index-check poison; outer update: 3
+    #   momentum-SGD launches
+    return 15 * K + 20 * K + 6 + 3
 
 
 def algorithmic_bytes_per_iteration(K, P):

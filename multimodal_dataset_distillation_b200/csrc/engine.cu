@@ -65,6 +65,7 @@ struct Work {
   float *pa, *pb, *pc, *pe;            // GEMM partial slabs / raw outputs (pc, pe: side-stream branches)
   float *pd, *hd, *rhatd, *ynd, *dzd, *drd, *dfd, *dpd, *t, *nzd, *Sd, *Gd, *rho, *kap, *rowA, *rowB;
   float *neg_one;                      // device constant -1 (first-order API)
+  int* bad_index;                      // set by the gather kernel when a minibatch index is out of range
   void* ml_scratch;
   size_t bytes;
 };
@@ -109,6 +110,7 @@ void carve(Work& w, const Dims& m, void* base) {
   w.t = b.f(m.B); w.nzd = b.f(m.B); w.rho = b.f(m.B); w.kap = b.f(m.B); w.rowA = b.f(m.B); w.rowB = b.f(m.B);
   w.Sd = b.f(BB); w.Gd = b.f(BB);
   w.neg_one = b.f(4);
+  w.bad_index = reinterpret_cast<int*>(b.f(4));
   w.ml_scratch = b.f((size_t)match_loss_scratch_bytes() / sizeof(float) + 8);
   w.bytes = b.off;
 }
@@ -421,7 +423,7 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   L.s1_busy = true;
   CHECK_RC((gemm_store<true, false>(gemm_ops2(w.Gd, Bp, s.yn, d, B, s.G, Bp, w.ynd, d, B, B, d), w.pc, d, 1.0f, L.s1)));
   prof_mark("gemm_store<true,false> A=w.Gd", L.s1);
-  launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pc, 1, Bd, perm, d, lr, scale, w.dXn);
+  launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pc, 1, Bd, perm, d, lr, scale, w.dXn, m.N);
   prof_mark("scatter_add_rows_kernel", L.s1);
   if (!fused_nce) {        // the dlr / dscale accumulation is off the critical path: side stream, ordered step to step
     launch_k(nce_t_finish_kernel, 1, 128, 0, L.s1, w.rowA, w.rowB, B, lr, scale, dlr, dscale);
@@ -454,7 +456,7 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   int sp_y = 1;
   CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dpd, d, W1, dt, d, s.dp, d, V1, dt, d, B, dt), w.pe, &sp_y, L.s1)));
   prof_mark("gemm_partial<true,false> A=w.dpd", L.s1);
-  launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pe, sp_y, (size_t)B * dt, perm, dt, lr, nullptr, dY);
+  launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pe, sp_y, (size_t)B * dt, perm, dt, lr, nullptr, dY, m.N);
   prof_mark("scatter_add_rows_kernel", L.s1);
   // small parameters of a_k by column sums: also on the side stream, next to the main stream's W1 GEMM
   launch_k(colsum_tangent_update_kernel, ceil_div(d, 16), 256, 0, L.s1, 
@@ -498,6 +500,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   Lanes L;
   CHECK_RC(lanes_init(L, st));
   VLDD_CUDA(cudaMemsetAsync(w.ml_scratch, 0, 16, st));
+  VLDD_CUDA(cudaMemsetAsync(w.bad_index, 0, sizeof(int), st));
   VLDD_CUDA(cudaMemsetAsync(out5 + 3, 0, 2 * sizeof(float), st));
   VLDD_CUDA(cudaMemsetAsync(dY, 0, (size_t)N * dt * sizeof(float), st));
   VLDD_CUDA(cudaMemsetAsync(w.dXn, 0, (size_t)N * d * sizeof(float), st));
@@ -509,7 +512,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   if (K > 0) {
     const size_t step_stride = K > 1 ? (size_t)(w.sv[1].Yb - w.sv[0].Yb) : 0;
     launch_k(gather_all_kernel, dim3(B, K, 2), 256, 0, st, Y, (const float*)w.Xn, perms, B, dt, d, w.sv[0].Yb, w.sv[0].Xb,
-             step_stride);
+             step_stride, N, w.bad_index);
     MARK("gather_all");
   }
   // forward unroll
@@ -536,6 +539,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   }
   launch_k(row_normalise_bwd_kernel, N, 256, 0, st, w.Xn, w.un, w.dXn, nullptr, d, dU);
   MARK("row_normalise_bwd");
+  if (K > 0) launch_k(poison_kernel, 1, 32, 0, st, (const int*)w.bad_index, out5);
   prof_report();
   return check_launch("unrolled_match");
 }

@@ -214,15 +214,25 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 }
 
 // All K steps at once: Yb[k][b,:] = Y[perms[k][b],:] and Xb[k][b,:] = Xn[perms[k][b],:]   (grid = (B, K, 2))
+// An index outside [0, N) (the reference would raise IndexError, distill.py:512-513) is clamped so that no memory outside
+// the operands is touched, and recorded in *bad_index: the call then reports NaN losses (poison_kernel) instead of silently
+// training on the wrong rows.
+__device__ __forceinline__ size_t checked_row(int64_t idx, int N, int* bad_index) {
+  if (idx < 0 || idx >= N) {
+    if (bad_index != nullptr) atomicExch(bad_index, 1);
+    return idx < 0 ? 0 : (size_t)(N - 1);
+  }
+  return (size_t)idx;
+}
 __global__ void __launch_bounds__(256) gather_all_kernel(const float* __restrict__ Y, const float* __restrict__ Xn,
                                                          const int64_t* __restrict__ perms, int B, int dt, int d,
                                                          float* __restrict__ Yb0, float* __restrict__ Xb0,
-                                                         size_t step_stride) {
+                                                         size_t step_stride, int N, int* __restrict__ bad_index) {
   pdl_enter();
   const int b = blockIdx.x, k = blockIdx.y;
   const bool isx = blockIdx.z == 1;
   const int cols = isx ? d : dt;
-  const size_t row = (size_t)perms[(size_t)k * B + b];
+  const size_t row = checked_row(perms[(size_t)k * B + b], N, bad_index);
   const float* src = (isx ? Xn : Y) + row * cols;
   float* dst = (isx ? Xb0 : Yb0) + (size_t)k * step_stride + (size_t)b * cols;
   if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
@@ -239,10 +249,10 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
                                                                const int64_t* __restrict__ idx, int cols,
                                                                const float* __restrict__ lr,
                                                                const float* __restrict__ scale,
-                                                               float* __restrict__ dst) {
+                                                               float* __restrict__ dst, int N) {
   pdl_enter();
   const float coef = -(*lr) * (scale ? *scale : 1.0f);
-  const size_t s = (size_t)blockIdx.x * cols, t = (size_t)idx[blockIdx.x] * cols;
+  const size_t s = (size_t)blockIdx.x * cols, t = checked_row(idx[blockIdx.x], N, nullptr) * cols;
   if ((cols & 3) == 0 && (stride & 3) == 0 &&
       ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
     for (int j = threadIdx.x; j < (cols >> 2); j += blockDim.x) {
@@ -254,6 +264,12 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
   } else {
     for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[t + j] += coef * sum_slabs(part, splits, stride, s + j);
   }
+}
+
+// out5[0..4] := NaN when an index was out of range (see checked_row); one thread, end of the call
+__global__ void poison_kernel(const int* __restrict__ bad_index, float* __restrict__ out5) {
+  pdl_enter();
+  if (threadIdx.x < 5 && *bad_index != 0) out5[threadIdx.x] = __int_as_float(0x7fc00000);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -337,3 +337,20 @@ def test_buffer_writes_reference_format_and_distill_reads_it(tmp_path, capsys):
     assert [it for it, _ in eng.eval_history] == [0, 2] and all(len(r) == 2 for _, r in eng.eval_history)
     assert list(eng.eval_history[0][1][0].keys()) == list(ops.RESULT_KEYS)
     assert "Evaluate_01: Img R@1" in capsys.readouterr().out
+
+
+def test_out_of_range_minibatch_index_poisons_the_loss():
+    """The reference raises IndexError on a bad minibatch index (distill.py:512-513).  Here no memory outside the operands is
+    touched (the index is clamped) and the call reports NaN losses -- the NaN guard of distill.py:599-600 then stops the run."""
+    from multimodal_dataset_distillation_b200 import ops
+    pr = R.make_problem(N=16, B=8, K=2, dt=24, d=40, seed=0)
+    c = to_cuda(pr)
+    good = ops.unrolled_match(c["theta0"], c["theta_tgt"], c["Y"], c["U"], c["lr"], c["scale"], c["perms"], None)
+    assert torch.isfinite(good["out5"]).all()
+    for bad_value in (16, -1, 10 ** 12):
+        perms = c["perms"].clone()
+        perms[1, 3] = bad_value
+        res = ops.unrolled_match(c["theta0"], c["theta_tgt"], c["Y"], c["U"], c["lr"], c["scale"], perms, None)
+        assert torch.isnan(res["out5"]).all()
+    again = ops.unrolled_match(c["theta0"], c["theta_tgt"], c["Y"], c["U"], c["lr"], c["scale"], c["perms"], None)
+    assert torch.equal(again["out5"], good["out5"]) and torch.equal(again["dY"], good["dY"])     # the flag does not stick
