@@ -116,6 +116,11 @@ def maps_to_arrays(txt2img, img2txt, n_img: int, n_txt: int):
     for i, l in enumerate(lists):
         ptr[i + 1] = ptr[i] + len(l)
     idx = np.concatenate(lists).astype(np.int32) if lists else np.zeros(0, dtype=np.int32)
+    # the kernels index the score matrices with these: refuse maps that point outside them (numpy would raise IndexError)
+    if n_txt and (t2i.min() < 0 or t2i.max() >= n_img):
+        raise IndexError(f"txt2img refers to image {int(t2i.max() if t2i.max() >= n_img else t2i.min())}, but there are {n_img} images")
+    if idx.size and (idx.min() < 0 or idx.max() >= n_txt):
+        raise IndexError(f"img2txt refers to caption {int(idx.max() if idx.max() >= n_txt else idx.min())}, but there are {n_txt} captions")
     return t2i, ptr, idx
 
 

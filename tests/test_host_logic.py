@@ -178,3 +178,13 @@ def test_buffer_cli_matches_reference_flags():
             assert set(e["choices"]) <= set(a.choices), e["flag"]
     args = buffer.build_parser().parse_args(["--dataset", "coco", "--image_encoder", "nfnet"])
     assert buffer.save_dir_of(args) == os.path.join("./buffers", "coco", "nfnet", "bert")       # buffer.py:27-31
+
+
+def test_maps_to_arrays_rejects_out_of_range_ground_truth():
+    from multimodal_dataset_distillation_b200 import ops
+    t2i, ptr, idx = ops.maps_to_arrays({0: 0, 1: 0, 2: 1}, {0: [0, 1], 1: [2]}, 2, 3)
+    assert t2i.tolist() == [0, 0, 1] and ptr.tolist() == [0, 2, 3] and idx.tolist() == [0, 1, 2]
+    with pytest.raises(IndexError):
+        ops.maps_to_arrays({0: 0, 1: 2, 2: 1}, {0: [0, 1], 1: [2]}, 2, 3)          # image 2 of 2
+    with pytest.raises(IndexError):
+        ops.maps_to_arrays({0: 0, 1: 0, 2: 1}, {0: [0, 3], 1: [2]}, 2, 3)          # caption 3 of 3
