@@ -169,6 +169,208 @@ def bench_dominant_kernel(dev, experts, reps=20):
                 flops=2 * M * N * K, launches=reps * group)
 
 
+def gpu_eager_baseline(dev, max_seconds=20.0, max_iters=10):
+    """The reference's own mechanism on the SAME B200 through PyTorch eager (BASELINE.md section 3 "B3", SURVEY 8d: the
+    honest bar): oracle restatement of distill.py:509-606 -- autograd.grad(create_graph=True) per step, backward()
+    through the unroll -- with every tensor on the GPU, fp32 matmuls (torch default: TF32 off)."""
+    from oracle import distill_ref as R
+    pr = R.make_problem(N=CFG["N"], B=CFG["B"], K=CFG["K"], dt=CFG["dt"], d=CFG["d"], seed=0, dropout=True)
+    pr = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in pr.items()}
+    for _ in range(2):
+        R.unrolled_match_autograd(**pr)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n, t0 = 0, time.perf_counter()
+    e0.record()
+    while n < max_iters and (time.perf_counter() - t0) < max_seconds:
+        R.unrolled_match_autograd(**pr)
+        torch.cuda.synchronize()
+        n += 1
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": 1e3 / ms, "unit": "iters/s", "ms_per_step": ms, "iterations": n, "kind": "port",
+            "what": "PyTorch eager on this GPU: oracle/distill_ref.py::unrolled_match_autograd (torch %s, fp32, "
+                    "allow_tf32=%s), same Flickr-shaped workload, inputs resident" % (torch.__version__,
+                                                                                      torch.backends.cuda.matmul.allow_tf32)}
+
+
+def _time_rotating(fn, n_variants, reps=5):
+    """Average us per call of fn(i) over `reps` rounds of `n_variants` calls, each on different buffers (> L2 in total)."""
+    for i in range(n_variants):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for r in range(reps):
+        for i in range(n_variants):
+            fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / (reps * n_variants)
+
+
+def bench_streaming_kernels(dev, experts):
+    """Achieved HBM GB/s of the streaming kernels (north_star: "achieved HBM GB/s for the streaming kernels ... against
+    B200 peak"; distill.py:582-598, 611-613; epoch.py:219-244), each launched back to back on rotating buffers whose
+    total exceeds the 126 MB L2 (12 resident snapshots of 28 MB + 6 scratch vectors), CUDA events on the launch stream."""
+    import ctypes as C
+    from multimodal_dataset_distillation_b200 import ops
+    from multimodal_dataset_distillation_b200._lib import lib, check
+    pk = peaks()
+    flat = experts.reshape(-1, experts.shape[-1])
+    S, P = flat.shape
+    outs = [torch.empty(P, device=dev) for _ in range(6)]
+    bufs = [torch.zeros(P, device=dev) for _ in range(6)]
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    res = {}
+
+    def entry(name, us, nbytes, per_elem, site):
+        gbs = nbytes / (us * 1e-6) / 1e9
+        res[name] = {"avg_launch_us": us, "algorithmic_bytes_per_launch": nbytes, "bytes_per_element": per_elem,
+                     "achieved_gbs": gbs, "frac": gbs / pk["hbm"], "reference_site": site}
+
+    lr = torch.full((1,), 0.1, device=dev)
+    us = _time_rotating(lambda i: check(lib().vldd_flat_sgd_step(ptr(flat[i % S]), ptr(flat[(i + 1) % S]), ptr(lr), ptr(outs[i % 6]), P, st()), "sgd"), 12)
+    entry("flat_sgd_step", us, 12 * P, 12, "distill.py:582-583")
+    out3 = torch.empty(3, device=dev)
+    scratch = torch.zeros(lib().vldd_match_loss_scratch_bytes(), dtype=torch.uint8, device=dev)
+    us = _time_rotating(lambda i: check(lib().vldd_match_loss_fwd(ptr(flat[i % S]), ptr(flat[(i + 1) % S]), ptr(flat[(i + 2) % S]), P, ptr(out3), ptr(scratch), st()), "ml"), 12)
+    entry("match_loss_fwd", us, 12 * P, 12, "distill.py:588-598")
+    us = _time_rotating(lambda i: check(lib().vldd_match_loss_bwd(ptr(flat[i % S]), ptr(flat[(i + 1) % S]), ptr(out3), None, ptr(outs[i % 6]), P, st()), "mlb"), 12)
+    entry("match_loss_bwd", us, 12 * P, 12, "distill.py:606 (d/d theta_K of the ratio)")
+    if hasattr(lib(), "vldd_match_final"):
+        den = torch.ones(1, device=dev)
+        us = _time_rotating(lambda i: check(lib().vldd_match_final(ptr(flat[i % S]), ptr(flat[(i + 1) % S]), ptr(den), P, ptr(out3), ptr(outs[i % 6]), ptr(scratch), st()), "mlf"), 12)
+        entry("match_final (num + adjoint in one pass)", us, 12 * P, 12, "distill.py:588-598 + 606")
+    us = _time_rotating(lambda i: check(lib().vldd_momentum_sgd(ptr(outs[i % 6]), ptr(flat[i % S]), ptr(bufs[i % 6]), 1e-9, 0.5, 0, P, st()), "mom"), 12)
+    entry("momentum_sgd", us, 20 * P, 20, "distill.py:233-241, 611-613")
+    # rank kernels on a score matrix larger than L2 (COCO eval shape: 5000 x 25000 fp32 = 500 MB, read once per direction)
+    I, Cc = 5000, 5
+    T = I * Cc
+    Smat = torch.randn(I, T, device=dev)
+    t2i = (torch.arange(T, device=dev, dtype=torch.int32) // Cc).contiguous()
+    gptr = (torch.arange(I + 1, device=dev, dtype=torch.int32) * Cc).contiguous()
+    gidx = torch.arange(T, device=dev, dtype=torch.int32)
+    us = _time_rotating(lambda i: ops.ranks_from_scores(Smat, None, t2i, gptr, gidx), 1, reps=5)
+    entry("ranks_rows", us, 4 * I * T, 4, "epoch.py:227-233 (image->text)")
+    us = _time_rotating(lambda i: ops.ranks_cols(Smat, t2i), 1, reps=5)
+    entry("ranks_cols", us, 4 * I * T, 4, "epoch.py:236-241 (text->image, read column-wise from the same matrix)")
+    return res
+
+
+def gpu_retrieval_set(I, Cc, D, dev, seed=0):
+    """Synthetic retrieval set generated on the device (identical on every rank: same seed, same GPU model):
+    SURVEY 8d config 1 recipe -- N(0,1) embeddings, captions pulled 0.15 towards their image, rows normalised."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    img = torch.randn(I, D, generator=g, device=dev)
+    txt = torch.randn(I * Cc, D, generator=g, device=dev) + 0.15 * img.repeat_interleave(Cc, dim=0)
+    img = img / img.norm(dim=1, keepdim=True)
+    txt = txt / txt.norm(dim=1, keepdim=True)
+    T = I * Cc
+    t2i = (torch.arange(T, device=dev, dtype=torch.int32) // Cc).contiguous()
+    gptr = (torch.arange(I + 1, device=dev, dtype=torch.int32) * Cc).contiguous()
+    gidx = torch.arange(T, device=dev, dtype=torch.int32)
+    return img.contiguous(), txt.contiguous(), t2i, gptr, gidx
+
+
+def bench_retrieval_large(dev, world, rank, reps=3):
+    """configs[3]/[4]: 5000 x 25000 and 25000 x 125000 (D = 768).  One GPU: vldd_sim_rank_fused.  N > 1: captions sharded
+    per rank (dist.sharded_ranks: one [I, T/N] score GEMM per rank, two 8 B/image all-gathers + one int32 all-reduce),
+    ranks asserted equal to rank 0's single-GPU result; time = max over ranks."""
+    import torch.distributed as dist
+    from multimodal_dataset_distillation_b200 import ops, dist as D
+    pk = peaks()
+    out = []
+    for I in (5000, 25000):
+        Cc, Dm = 5, 768
+        T = I * Cc
+        img, txt, t2i, gptr, gidx = gpu_retrieval_set(I, Cc, Dm, dev, seed=I)
+        def single():
+            return ops.sim_rank_fused(img, txt, t2i, gptr, gidx, 14.285714)
+        entry = {"workload": f"{I} images x {T} captions, {Dm}-d", "pairs": I * T}
+        if world == 1:
+            single()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                r1, r2 = single()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            entry.update(path="vldd_sim_rank_fused (one GPU, no score matrix in HBM)")
+        else:
+            lo, hi = D.shard_bounds(T, world, rank)
+            txt_s, t2i_s = txt[lo:hi].contiguous(), t2i[lo:hi].contiguous()
+            def sharded():
+                return D.sharded_ranks(img, txt_s, lo, t2i_s, gptr, gidx, 14.285714)
+            sharded()
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                ri, rt = sharded()
+            e1.record()
+            dist.barrier(); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+            # parity: the sharded ranks equal the single-GPU ranks (rank 0 computes those)
+            sizes = [D.shard_bounds(T, world, r)[1] - D.shard_bounds(T, world, r)[0] for r in range(world)]
+            parts = [torch.empty(n, dtype=torch.int32, device=dev) for n in sizes]
+            dist.all_gather(parts, rt.contiguous())
+            ok = None
+            if rank == 0:
+                r1, r2 = single()
+                ok = bool(torch.equal(r1, ri)) and bool(torch.equal(r2, torch.cat(parts)))
+                assert ok, "sharded ranks differ from the single-GPU ranks"
+            entry.update(path=f"dist.sharded_ranks: captions sharded {world}-way, images replicated",
+                         collectives="2 x all_gather of 8 B/image (best ground-truth candidate per shard) + 1 x int32 "
+                                     "all_reduce of I counts (NCCL over NVLink); latency-bound, the GEMM dominates",
+                         ranks_equal_single_gpu=ok)
+            del txt_s, t2i_s
+        tflops = 2.0 * I * T * Dm / (ms / 1e3) / 1e12
+        entry.update(ms=ms, value=I * T / (ms / 1e3), unit="pairs/s",
+                     roofline={"bound": "tensor", "achieved": tflops, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tflops / pk["tf"],
+                               "note": "useful 2*I*T*D flops counted once for both directions against sustained dense bf16"})
+        out.append(entry)
+        del img, txt
+        torch.cuda.empty_cache()
+    return out
+
+
+def allreduce_parity_check(eng, dev, world, rank):
+    """N > 1: the all-reduced (dU, dY, dlr, dscale) of N segments (one per rank) equals the sum a single GPU gets by
+    looping the same N segments (SURVEY section 4 test plan).  Dropout off so that every rank's call is reproducible."""
+    import torch.distributed as dist
+    from multimodal_dataset_distillation_b200 import ops, dist as D
+    K, B, N = CFG["K"], CFG["B"], CFG["N"]
+
+    def segment(r):
+        ex = make_experts(100 + r)[0].to(dev)                     # expert 0 of rank r's trajectories
+        g = torch.Generator().manual_seed(1000 + r)
+        perms = torch.stack([torch.randperm(N, generator=g)[:B] for _ in range(K)]).to(dev)
+        res = ops.unrolled_match(ex[0], ex[1], eng.Y.detach(), eng.U.detach(), eng.syn_lr_txt.detach(), eng.fixed_scale, perms, None)
+        return [res["dU"].clone(), res["dY"].clone(), res["out5"][3:5].clone()]
+
+    mine = segment(rank)
+    D.allreduce_packed(mine)
+    err = None
+    if rank == 0:
+        tot = None
+        for r in range(world):
+            part = segment(r)
+            tot = part if tot is None else [a + b for a, b in zip(tot, part)]
+        err = max(float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)) for a, b in zip(mine, tot))
+        assert err < 1e-5, f"all-reduced gradients differ from the single-GPU sum: {err}"
+    dist.barrier()
+    return {"segments": world, "max_rel_err_vs_single_gpu_sum": err,
+            "what": "NCCL all-reduce of packed [dU | dY | dlr, dscale] from one segment per rank vs rank 0 looping the same "
+                    "segments and summing (fp32; summation order differs)"}
+
+
 def workload_config(world):
     return {"workload": "configs[2]: full distill inner loop, Flickr30K-shaped (N=B=100 pairs, syn_steps=8, "
                         "expert_epochs=1, max_start_epoch=2, text_projection 768->2304 in train mode (fresh "
@@ -392,6 +594,7 @@ def bench_retrieval(dev, opt):
 def cpu_baseline_distill(max_seconds=20.0, max_iters=8):
     """Oracle (torch CPU restatement of distill.py:509-606, autograd double backward) on the host cores."""
     from oracle import distill_ref as R
+    torch.set_num_threads(host_threads())
     pr = R.make_problem(N=CFG["N"], B=CFG["B"], K=CFG["K"], dt=CFG["dt"], d=CFG["d"], seed=0, dropout=True)
     R.unrolled_match_autograd(**pr)                       # warm-up (thread pools, allocator)
     n, t0 = 0, time.perf_counter()
@@ -404,14 +607,26 @@ def cpu_baseline_distill(max_seconds=20.0, max_iters=8):
                       f"torch {torch.__version__} CPU, {torch.get_num_threads()} threads of {os.cpu_count()} cpus)"}
 
 
+def host_threads():
+    """Threads for the CPU arms.  torchrun exports OMP_NUM_THREADS=1 to every rank, which would make the N > 1 reference
+    run single-threaded; the reference arm runs on rank 0 alone, so it gets the whole box either way: one thread per
+    physical core (torch's own default when nothing is forced: half the logical CPUs)."""
+    n = os.cpu_count() or 2
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    return max(1, n // 2)
+
+
 def run_reference(opt):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
+    torch.set_num_threads(host_threads())
     from oracle import distill_ref as R
     pr = R.make_problem(N=CFG["N"], B=CFG["B"], K=CFG["K"], dt=CFG["dt"], d=CFG["d"], seed=0, dropout=True)
-    steps = min(opt.steps, 10)
-    warm = min(opt.warmup, 2)
+    steps, warm = opt.steps, opt.warmup
     for _ in range(max(warm, 1)):
         R.unrolled_match_autograd(**pr)
     t0 = time.perf_counter()
@@ -419,8 +634,9 @@ def run_reference(opt):
         R.unrolled_match_autograd(**pr)
     dt = time.perf_counter() - t0
     v = steps / dt
-    sample = (f"{steps} full iterations (bounded from --steps {opt.steps}) of the Flickr-shaped workload on the host CPU: "
-              f"oracle restatement of distill.py:509-606 with torch autograd double backward")
+    sample = (f"{steps} full iterations (one step = one whole iteration, ~0.15 s) of the Flickr-shaped workload on the host CPU, "
+              f"{torch.get_num_threads()} threads of {os.cpu_count()} logical cpus: oracle restatement of distill.py:509-606 "
+              f"with torch autograd double backward")
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": opt.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",

@@ -176,6 +176,10 @@ size_t vldd_bench_skinny_gemm_workspace_bytes(int M, int N, int K);
 int vldd_bench_skinny_gemm(const float* A, const float* W, int M, int N, int K, float* partial, size_t partial_bytes,
                            int* splits_out, void* stream);
 
+/* Kernels of this library launched by the process so far (a replayed CUDA graph counts its kernel nodes on every
+ * replay).  Measurement aid: bench.py reports the difference across its timed region as `gpu_launches`. */
+unsigned long long vldd_kernel_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ _P = C.c_void_p
 _SIGS = {
     "vldd_version": (C.c_int, []),
     "vldd_last_error": (C.c_char_p, []),
+    "vldd_kernel_launch_count": (C.c_ulonglong, []),
     "vldd_flat_sgd_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     "vldd_match_loss_scratch_bytes": (C.c_size_t, []),
     "vldd_match_loss_fwd": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
@@ -71,9 +72,9 @@ def lib() -> C.CDLL:
     """Load (building if needed) the shared library.  Raises if it cannot be produced."""
     global _LIB
     if _LIB is None:
-        path = _build.LIB_PATH
-        if not os.path.exists(path):
-            path = _build.build_library()
+        # always go through build_library: it compares the digest of csrc/ + include/ with the one the .so was built
+        # from and rebuilds on a mismatch, so a stale library is never loaded silently (cheap: hashes ~30 files)
+        path = _build.build_library(force=False)
         handle = C.CDLL(path)
         for name, (res, args) in _SIGS.items():
             fn = getattr(handle, name)          # AttributeError if the .so is stale / missing a symbol

@@ -71,6 +71,7 @@ extern "C" {
 
 int vldd_version(void) { return 100; }
 const char* vldd_last_error(void) { return g_err; }
+unsigned long long vldd_kernel_launch_count(void) { return launch_counter().load(); }
 
 int vldd_flat_sgd_step(const float* theta, const float* grad, const float* lr, float* out, int64_t n, void* stream) {
   VLDD_REQUIRE(n >= 0 && (n == 0 || (theta && grad && lr && out)), "flat_sgd_step: null pointer or negative n");

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #define VLDD_OK 0
 #ifndef VLDD_ERR_ARG
 #define VLDD_ERR_ARG (-1)
@@ -33,7 +35,19 @@ int check_launch(const char* what);
     }                                                                          \
   } while (0)
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kMaxSMs = 256;   // sizing bound for per-block scratch (B200: 148)
+// SM count of the current device, queried once per device ordinal (grids are sized in multiples of it)
+inline int num_sms() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0 || n > kMaxSMs) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
 // Every kernel of the library starts with pdl_wait(): it blocks until the preceding kernel in the stream has
@@ -45,6 +59,14 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_launch_dependents(); }
 
 bool pdl_enabled();   // VLDD_PDL=0 disables the launch attribute (capi.cu)
+
+// Number of kernels of this library that have been (or, while a CUDA graph is being captured, will be per replay)
+// launched by the process: launch_k() counts, the engine adds a graph's node count on every replay.  bench.py reports
+// the difference across its timed region as `gpu_launches` (vldd_kernel_launch_count).
+inline std::atomic<unsigned long long>& launch_counter() {
+  static std::atomic<unsigned long long> c{0};
+  return c;
+}
 
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -59,6 +81,7 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors surface through cudaGetLastError (check_launch)
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
 }
 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

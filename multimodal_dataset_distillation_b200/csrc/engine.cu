@@ -155,7 +155,7 @@ inline int ew_grid(size_t n);
 inline int ew_grid4(size_t n, int d) { return (d & 3) == 0 ? ew_grid(n / 4) : ew_grid(n); }
 inline int ew_grid(size_t n) {
   size_t g = (n + 255) / 256;
-  const size_t cap = (size_t)kNumSMs * 8;
+  const size_t cap = (size_t)num_sms() * 8;
   return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
@@ -550,7 +550,7 @@ struct GraphKey {
   int dims[5];
   bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
-struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t last_use; };
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t last_use; unsigned long long kernels; };
 std::mutex g_graph_mu;
 std::vector<GraphEntry> g_graphs;
 uint64_t g_graph_clock = 0;
@@ -594,17 +594,20 @@ int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, 
   memcpy(key.dims, dims, sizeof(dims));
   std::lock_guard<std::mutex> lock(g_graph_mu);
   cudaGraphExec_t exec = nullptr;
+  unsigned long long graph_kernels = 0;
   for (auto& e : g_graphs)
-    if (e.key == key) { exec = e.exec; e.last_use = ++g_graph_clock; break; }
+    if (e.key == key) { exec = e.exec; e.last_use = ++g_graph_clock; graph_kernels = e.kernels; break; }
   if (exec == nullptr) {
     DeviceState* ds = nullptr;
     CHECK_RC(current_device_state(&ds));
     if (ds->capture == nullptr) VLDD_CUDA(cudaStreamCreateWithFlags(&ds->capture, cudaStreamNonBlocking));
     cudaStream_t g_capture_stream = ds->capture;
     VLDD_CUDA(cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal));
+    const unsigned long long before = launch_counter().load();
     const int rc = unrolled_match_body(m, w, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K, g_capture_stream);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce_end = cudaStreamEndCapture(g_capture_stream, &graph);
+    graph_kernels = launch_counter().exchange(before) - before;   // recorded, not run: counted per replay below
     if (rc != VLDD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce_end != cudaSuccess || graph == nullptr) {
       set_error("CUDA graph capture failed: %s", cudaGetErrorString(ce_end));
@@ -620,9 +623,10 @@ int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, 
       cudaGraphExecDestroy(g_graphs[victim].exec);
       g_graphs.erase(g_graphs.begin() + victim);
     }
-    g_graphs.push_back(GraphEntry{key, exec, ++g_graph_clock});
+    g_graphs.push_back(GraphEntry{key, exec, ++g_graph_clock, graph_kernels});
   }
   VLDD_CUDA(cudaGraphLaunch(exec, st));
+  launch_counter().fetch_add(graph_kernels, std::memory_order_relaxed);
   return VLDD_OK;
 }
 

@@ -233,7 +233,7 @@ int recall_counts(const int32_t* ranks, int n, int32_t* counts3, cudaStream_t st
   if (e != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); return VLDD_ERR_CUDA; }
   if (n <= 0) return VLDD_OK;
   int grid = ceil_div(n, 256);
-  if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+  if (grid > num_sms() * 4) grid = num_sms() * 4;
   launch_k(recall_counts_kernel, grid, 256, 0, st, ranks, n, counts3);
   return check_launch("recall_counts");
 }

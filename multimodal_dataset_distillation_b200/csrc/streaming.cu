@@ -13,7 +13,7 @@ constexpr int kStreamBlocksPerSM = 8;
 
 static inline int stream_grid(int64_t n_vec) {
   int64_t want = ceil_div64(n_vec, kStreamThreads);
-  int64_t cap = (int64_t)kNumSMs * kStreamBlocksPerSM;
+  int64_t cap = (int64_t)num_sms() * kStreamBlocksPerSM;
   return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
@@ -164,7 +164,7 @@ int flat_sgd_step(const float* theta, const float* grad, const float* lr, float*
   return check_launch("flat_sgd_step");
 }
 
-int64_t match_loss_scratch_bytes() { return (int64_t)(2 * kNumSMs * kStreamBlocksPerSM) * sizeof(double) + 16; }
+int64_t match_loss_scratch_bytes() { return (int64_t)(2 * kMaxSMs * kStreamBlocksPerSM) * sizeof(double) + 16; }
 
 int match_loss_fwd(const float* thK, const float* tgt, const float* th0, int64_t n, float* out3, void* scratch,
                    cudaStream_t st) {

@@ -28,21 +28,32 @@ namespace tc {
 constexpr int BM = 128, BK = 32;                    // BK floats = 128 bytes = one swizzle row; BN is a template parameter
 constexpr int UMMA_K = 8;                           // tf32
 constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB per operand per stage
-constexpr int NUM_THREADS = 320;                    // producer, MMA, 4 splitter warps, 4 epilogue warps
+constexpr int kBaseThreads = 192;                   // producer, MMA, 4 splitter warps; + 32 per epilogue warp (4 or 8 of them)
 
 // Stage layout (kSplit == 3):  K-major A  -> [A | B | B_lo]            48 KB x 4 stages; A_hi / A_lo live in TMEM
 //                              MN-major A -> [A | B | A_lo | B_lo]     64 KB x 3 stages
 //               (kSplit == 1):              [A | B]                    32 KB x 6 stages
-template <int kSplit, bool A_TMEM, int kStagesT = 0, int BN = 128>
+template <int kSplit, bool A_TMEM, int kStagesT = 0, int BN = 128, int kEpiWarps = 4>
 struct Cfg {
+  static_assert(kEpiWarps == 4 || kEpiWarps == 8, "one or two epilogue warps per TMEM lane quadrant");
+  static constexpr int kThreads = kBaseThreads + 32 * kEpiWarps;
   static constexpr int kTileB = BN * BK * 4;                              // B tile bytes (12 KB at BN = 96)
   static constexpr int kStageBytes = kSplit == 3 ? (A_TMEM ? TILE_BYTES + 2 * kTileB : 2 * TILE_BYTES + 2 * kTileB)
                                                  : TILE_BYTES + kTileB;
-  static constexpr int kStages = kStagesT > 0 ? kStagesT : (kSplit == 3 ? (A_TMEM ? 4 : 3) : 6);
-  static constexpr int kEpiBytes = 4 * 32 * 36 * 4;                       // private transpose patches of the epilogue warps
+  // Pipeline depth.  One stage's round trip (TMA issue -> data landed ~0.8-1.0 us, operand split ~0.25 us, its 12 MMAs
+  // ~0.4 us, commit -> producer) is ~1.8 us, so with d stages a k-block costs max(MMA time, 1.8 us / d): narrower N tiles
+  // buy depth (shared memory: 48 / 40 / 32 KB per stage at BN = 128 / 96 / 64; tensor memory: 64 columns of A per stage).
+  static constexpr int kStagesDefault = (kSplit == 3 ? (A_TMEM ? (BN <= 64 ? 6 : (BN <= 96 ? 5 : 4)) : 3) : 6) - (kEpiWarps == 8 ? 1 : 0);
+  static constexpr int kStages = kStagesT > 0 ? kStagesT : kStagesDefault;
+  static constexpr int kEpiBytes = kEpiWarps * 32 * 36 * 4;               // private transpose patches of the epilogue warps
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = (kSplit == 3 && A_TMEM) ? 512 : 256;   // 2 accumulators x 128 + kStages x (32 hi + 32 lo)
-  static constexpr uint32_t kTmemA = 256;
+  static constexpr int kAccStride = BN;                                   // accumulator a lives in TMEM columns [a*BN, a*BN + BN)
+  static constexpr uint32_t kTmemA = 2 * BN;                              // first column of the staged A operand (hi | lo per stage)
+  static constexpr int kTmemNeed = (kSplit == 3 && A_TMEM) ? 2 * BN + kStages * 64 : 2 * BN;
+  static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
+  static_assert(kTmemNeed <= 512, "tensor memory: 2 accumulators + 64 columns of A per stage must fit 512 columns");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory per CTA");
+  static_assert(3 * kStages * 8 + 4 * 8 + 8 <= 256, "barrier block");
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -69,6 +80,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+}
+// One lane of the (fully converged) warp: tcgen05.mma / TMA / commit are issued from uniform registers, and ptxas only
+// keeps their operands there when the surrounding control flow is warp-uniform.  Under `if (lane == 0)` it emitted a
+// divergence "waterfall" around every UTCHMMA (ELECT, 4 x R2UR.BROADCAST, UTCHMMA, BRA.U.ANY: ~90 cycles per MMA, more
+// than the 64 cycles the tensor core needs for 128x128x8), which made every k-block cost 0.58 us whatever the tile width.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -250,13 +276,13 @@ struct Maps {
 // Work item w (one per (m-tile, n-tile, k-split)) -> CTA blockIdx.x, blockIdx.x + gridDim.x, ... (persistent loop).
 struct WorkItem { int m0, n0, z, kb_begin, n_kb; };
 
-template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128, int kEpiWarps = 4>
+__global__ void __launch_bounds__(kBaseThreads + 32 * kEpiWarps, 1)
 tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, int splits, Epi epi,
                const int* __restrict__ work_list, const int* __restrict__ work_count, int old_mask) {
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= 128, "N tile: 64, 96 or 128 (32-column epilogue chunks, MN-major boxes)");
   constexpr bool A_TMEM = kSplit == 3;                 // hi/lo of the A tile are staged in tensor memory (either major)
-  using C = Cfg<kSplit, A_TMEM, kStagesT, BN>;
+  using C = Cfg<kSplit, A_TMEM, kStagesT, BN, kEpiWarps>;
   constexpr int TILE_B = C::kTileB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -300,7 +326,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 32 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -334,7 +360,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   // Drain columns [c_begin, c_end) of accumulator `acc` for work item `it`: TMEM lane quadrant is fixed by warp index % 4.
   // Each thread drains 32 columns of its own row (tcgen05.ld 32x32b.x32), the warp transposes the 32x32 block through a
   // private shared-memory patch and then touches global memory as 4 rows x 128 contiguous bytes per instruction.
-  auto drain = [&](const WorkItem& it, int acc, uint32_t parity, int c_begin, int c_end, float* stage, bool release) {
+  auto drain = [&](const WorkItem& it, int acc, uint32_t parity, int c_begin, int c_end, int c_step, float* stage, bool release) {
     const int quad = warp & 3;
     constexpr int LDS = 36;                                    // padded row stride (floats): conflict-free float4 access
     const int rsub = lane >> 3, q4 = (lane & 7) * 4;
@@ -373,16 +399,16 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
       if (my_m < M) { row_thr = epi.row_thr[my_m]; row_thr_idx = epi.row_thr_idx[my_m]; }
     }
 #pragma unroll 1
-    for (int c = c_begin; c < c_end; c += 32) {
+    for (int c = c_begin; c < c_end; c += c_step) {
       float v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 128 + c);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * C::kAccStride + c);
       if (it.n_kb > 0) {
         tmem_ld_32x32(taddr, v);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      if (release && c + 32 >= c_end) {          // accumulator fully read: hand the TMEM buffer back to the MMA warp
+      if (release && c + c_step >= c_end) {      // this warp's last chunk is read: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
       }
@@ -408,7 +434,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         float4 cur[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = sv[i];
-        if (c + 32 < c_end) load_src(c + 32);
+        if (c + c_step < c_end) load_src(c + c_step);
         const int nb = n0 + c + q4;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -465,54 +491,56 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   };
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      auto issue = [&](const WorkItem& it, int i, int s, bool load_a, bool load_b) {
-        const int kb = it.kb_begin + i;
-        const bool seg1 = kb >= nkb0;
-        const int k = (seg1 ? kb - nkb0 : kb) * BK;
-        const CUtensorMap* ma = seg1 ? &maps.a1 : &maps.a0;
-        const CUtensorMap* mb = seg1 ? &maps.b1 : &maps.b0;
-        uint8_t* sa = smem + s * C::kStageBytes + OFF_A;
-        uint8_t* sb = smem + s * C::kStageBytes + OFF_B;
-        if (load_a) { if (A_KMAJOR) tma_load_2d(sa, ma, &full[s], k, it.m0); else tma_load_3d(sa, ma, &full[s], 0, k, it.m0 / 32); }
-        if (load_b) { if (B_KMAJOR) tma_load_2d(sb, mb, &full[s], k, it.n0); else tma_load_3d(sb, mb, &full[s], 0, k, it.n0 / 32); }
-      };
-      // early loads of the operands that do not depend on the programmatic predecessor (first item, first kStages k-blocks)
-      int pre = 0;
-      const bool a_old = (old_mask & 1) != 0, b_old = (old_mask & 2) != 0;
-      if (old_mask != 0 && work_list == nullptr && work_count == nullptr && (int)blockIdx.x < total_work) {
-        const WorkItem it0 = decode(blockIdx.x);
-        pre = min(C::kStages, it0.n_kb);
-        for (int i = 0; i < pre; ++i) {
+    // ===== TMA producer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
+    auto issue = [&](const WorkItem& it, int i, int s, bool load_a, bool load_b) {
+      const int kb = it.kb_begin + i;
+      const bool seg1 = kb >= nkb0;
+      const int k = (seg1 ? kb - nkb0 : kb) * BK;
+      const CUtensorMap* ma = seg1 ? &maps.a1 : &maps.a0;
+      const CUtensorMap* mb = seg1 ? &maps.b1 : &maps.b0;
+      uint8_t* sa = smem + s * C::kStageBytes + OFF_A;
+      uint8_t* sb = smem + s * C::kStageBytes + OFF_B;
+      if (load_a) { if (A_KMAJOR) tma_load_2d(sa, ma, &full[s], k, it.m0); else tma_load_3d(sa, ma, &full[s], 0, k, it.m0 / 32); }
+      if (load_b) { if (B_KMAJOR) tma_load_2d(sb, mb, &full[s], k, it.n0); else tma_load_3d(sb, mb, &full[s], 0, k, it.n0 / 32); }
+    };
+    // early loads of the operands that do not depend on the programmatic predecessor (first item, first kStages k-blocks)
+    int pre = 0;
+    const bool a_old = (old_mask & 1) != 0, b_old = (old_mask & 2) != 0;
+    if (old_mask != 0 && work_list == nullptr && work_count == nullptr && (int)blockIdx.x < total_work) {
+      const WorkItem it0 = decode(blockIdx.x);
+      pre = min(C::kStages, it0.n_kb);
+      for (int i = 0; i < pre; ++i) {
+        if (elect_one()) {
           mbar_expect_tx(&full[i], TILE_BYTES + TILE_B);        // both tiles of the stage; the rest follows after the wait
           issue(it0, i, i, a_old, b_old);
         }
+        __syncwarp();
       }
-      pdl_enter();
-      if (work_count != nullptr) total_work = *work_count;
-      int g = 0;                                                    // k-blocks issued so far (across work items)
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const WorkItem it = decode(w);
-        for (int i = 0; i < it.n_kb; ++i, ++g) {
-          const int s = g % C::kStages, round = g / C::kStages;
-          if (g < pre) {
-            issue(it, i, s, !a_old, !b_old);
-          } else {
-            if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+    }
+    pdl_enter();
+    if (work_count != nullptr) total_work = *work_count;
+    int g = 0;                                                    // k-blocks issued so far (across work items)
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const WorkItem it = decode(w);
+      for (int i = 0; i < it.n_kb; ++i, ++g) {
+        const int s = g % C::kStages, round = g / C::kStages;
+        if (g < pre) {
+          if (elect_one()) issue(it, i, s, !a_old, !b_old);
+        } else {
+          if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+          if (elect_one()) {
             mbar_expect_tx(&full[s], TILE_BYTES + TILE_B);
             issue(it, i, s, true, true);
           }
-          if (g == 0) TL(3);
         }
+        __syncwarp();
+        if (g == 0) TL(3);
       }
-      TL(4);
-    } else {
-      pdl_enter();
     }
+    TL(4);
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
+    {
       constexpr uint32_t idesc = instr_desc_tf32(A_TMEM ? false : !A_KMAJOR, !B_KMAJOR, BM, BN);   // TMEM A is row-per-lane
       // K-major  (SWIZZLE_128B):         8-row groups 1024 B apart (SBO), k-step of 8 floats = +32 B inside the row
       // MN-major (SWIZZLE_128B_BASE32B): 32-wide MN chunks 4096 B apart (LBO), 4-k-row groups 512 B apart (SBO),
@@ -528,10 +556,10 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
       int g = 0, local = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
         const WorkItem it = decode(w);
-        const int acc = local & 1;                                  // accumulator buffer: TMEM columns [128*acc, +128)
+        const int acc = local & 1;                                  // accumulator buffer: TMEM columns [BN*acc, +BN)
         if (local >= 2) mbar_wait(&tmem_empty[acc], ((local >> 1) - 1) & 1);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + acc * 128;
+        const uint32_t tacc = tmem_base + acc * C::kAccStride;
         uint32_t accumulate = 0;
         for (int i = 0; i < it.n_kb; ++i, ++g) {
           const int s = g % C::kStages, round = g / C::kStages;
@@ -541,31 +569,36 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
           const uint32_t st = smem_u32(smem + s * C::kStageBytes);
           const uint32_t sa = st + OFF_A, sb = st + OFF_B, sal = st + OFF_ALO, sbl = st + OFF_BLO;
           const uint32_t ta_hi = tmem_base + C::kTmemA + s * 64, ta_lo = ta_hi + 32;   // TMEM columns of this stage's A
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t db = smem_desc(sb + k * b_step, b_lbo, b_sbo, b_lt);
-            if (kSplit == 3) {
-              const uint64_t dbl = smem_desc(sbl + k * b_step, b_lbo, b_sbo, b_lt);
-              if (A_TMEM) {
-                umma_tf32_ts(tacc, ta_lo + k * UMMA_K, db, idesc, accumulate);
-                umma_tf32_ts(tacc, ta_hi + k * UMMA_K, dbl, idesc, 1);
-                umma_tf32_ts(tacc, ta_hi + k * UMMA_K, db, idesc, 1);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t db = smem_desc(sb + k * b_step, b_lbo, b_sbo, b_lt);
+              if (kSplit == 3) {
+                const uint64_t dbl = smem_desc(sbl + k * b_step, b_lbo, b_sbo, b_lt);
+                if (A_TMEM) {
+                  umma_tf32_ts(tacc, ta_lo + k * UMMA_K, db, idesc, accumulate);
+                  umma_tf32_ts(tacc, ta_hi + k * UMMA_K, dbl, idesc, 1);
+                  umma_tf32_ts(tacc, ta_hi + k * UMMA_K, db, idesc, 1);
+                } else {
+                  const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt);
+                  const uint64_t dal = smem_desc(sal + k * a_step, a_lbo, a_sbo, a_lt);
+                  umma_tf32(tacc, dal, db, idesc, accumulate);
+                  umma_tf32(tacc, da, dbl, idesc, 1);
+                  umma_tf32(tacc, da, db, idesc, 1);
+                }
               } else {
                 const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt);
-                const uint64_t dal = smem_desc(sal + k * a_step, a_lbo, a_sbo, a_lt);
-                umma_tf32(tacc, dal, db, idesc, accumulate);
-                umma_tf32(tacc, da, dbl, idesc, 1);
-                umma_tf32(tacc, da, db, idesc, 1);
+                umma_tf32(tacc, da, db, idesc, accumulate);
               }
-            } else {
-              const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt);
-              umma_tf32(tacc, da, db, idesc, accumulate);
+              accumulate = 1;
             }
-            accumulate = 1;
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
+          accumulate = 1;
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
+        __syncwarp();
       }
       TL(4);
     }
@@ -644,23 +677,32 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
       TL(5);
     }
   } else {
-    // ===== epilogue warps (6..9): drain accumulator `acc` of work item i while the other roles run item i+1 =====
+    // ===== epilogue warps (6..): drain accumulator `acc` of work item i while the other roles run item i+1 =====
+    // TMEM lane quadrant = warp % 4.  With 8 epilogue warps two warps share a quadrant and take alternate 32-column chunks:
+    // twice the loads of the axpy epilogue's `src` operand in flight (that stream, not the MMAs, bounds the weight-gradient
+    // GEMMs: 16 KB in flight per SM against ~0.6 us of L2 latency is 4 TB/s over the chip).
+    constexpr int kGroups = kEpiWarps / 4;
+    const int grp = (warp - 6) >> 2;
     int local = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++local) {
       const WorkItem it = decode(w);
       const bool last = w + (int)gridDim.x >= total_work;
-      // the CTA's last item has nothing to overlap with: the (by then idle) splitter warps take the upper two chunks
-      drain(it, local & 1, (local >> 1) & 1, 0, (last && kSplit == 3) ? kHalfN : BN, epi_stage + (warp - 6) * 32 * 36, !last);
+      if (kGroups == 1) {
+        // the CTA's last item has nothing to overlap with: the (by then idle) splitter warps take the upper two chunks
+        drain(it, local & 1, (local >> 1) & 1, 0, (last && kSplit == 3) ? kHalfN : BN, 32, epi_stage + (warp - 6) * 32 * 36, !last);
+      } else {
+        drain(it, local & 1, (local >> 1) & 1, 32 * grp, BN, 32 * kGroups, epi_stage + (warp - 6) * 32 * 36, true);
+      }
       if (local == 0) TL(6);
     }
     TL(7);
   }
-  if (kSplit == 3 && warp >= 2 && warp < 6 && total_work > (int)blockIdx.x) {
+  if (kEpiWarps == 4 && kSplit == 3 && warp >= 2 && warp < 6 && total_work > (int)blockIdx.x) {
     const int n_items = (total_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int local = n_items - 1;
     const WorkItem it = decode((int)blockIdx.x + local * (int)gridDim.x);
     // pipeline stage 0 is free once tmem_full of the last item has fired (drain waits for it before touching it)
-    drain(it, local & 1, (local >> 1) & 1, kHalfN, BN, reinterpret_cast<float*>(smem) + (warp - 2) * 32 * 36, false);
+    drain(it, local & 1, (local >> 1) & 1, kHalfN, BN, 32, reinterpret_cast<float*>(smem) + (warp - 2) * 32 * 36, false);
   }
   tc_fence_before();
   __syncthreads();

@@ -96,16 +96,19 @@ inline bool gemm_ok(const GemmOperands& g) {
   return true;
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128>
+template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128, int kEpiWarps = 4>
 inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st, const int* work_list = nullptr,
                   const int* work_count = nullptr, int old_mask = 0) {
-  using C = Cfg<kSplit, kSplit == 3, kStagesT, BN>;
-  auto kern = tc_gemm_kernel<A_KMAJOR, B_KMAJOR, kSplit, Epi, kStagesT, BN>;
-  static bool configured = false;
-  if (!configured) {
+  using C = Cfg<kSplit, kSplit == 3, kStagesT, BN, kEpiWarps>;
+  auto kern = tc_gemm_kernel<A_KMAJOR, B_KMAJOR, kSplit, Epi, kStagesT, BN, kEpiWarps>;
+  // the attribute is per device (a process may drive several GPUs): one flag per device ordinal and template instance
+  static bool configured[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("tc::launch: bad device ordinal"); return VLDD_ERR_CUDA; }
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", C::kSmemBytes, cudaGetErrorString(e)); return VLDD_ERR_CUDA; }
-    configured = true;
+    configured[dev] = true;
   }
   Maps maps;
   int rc = get_map(g.A0, g.M, g.K0, g.lda0, A_KMAJOR, &maps.a0);
@@ -122,17 +125,17 @@ inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st, c
     maps.b1 = maps.b0;
   }
   const int work = ceil_div(g.N, BN) * ceil_div(g.M, BM) * splits;
-  dim3 grid(work < kNumSMs ? work : kNumSMs);                         // persistent: one CTA per SM at most
-  launch_k(kern, grid, NUM_THREADS, C::kSmemBytes, st, maps, g.M, g.N, g.K0, g.K1, splits, epi, work_list, work_count, old_mask);
+  dim3 grid(work < num_sms() ? work : num_sms());                         // persistent: one CTA per SM at most
+  launch_k(kern, grid, C::kThreads, C::kSmemBytes, st, maps, g.M, g.N, g.K0, g.K1, splits, epi, work_list, work_count, old_mask);
   return VLDD_OK;
 }
 
 // number of K splits so that tiles x splits fills ONE wave of the 148 SMs without spilling into a second one (the
 // kernel runs one CTA per SM: 18 tiles x 9 splits = 162 CTAs would cost two waves), each split keeping >= 2 k-blocks
-inline int pick_splits(int M, int N, int Ktot) {
-  const int tiles = ceil_div(M, BM) * ceil_div(N, 128);
+inline int pick_splits(int M, int N, int Ktot, int bn = 128) {
+  const int tiles = ceil_div(M, BM) * ceil_div(N, bn);
   const int nkb = ceil_div(Ktot, BK);
-  int s = kNumSMs / tiles;
+  int s = num_sms() / tiles;
   const int max_s = nkb / 2 > 0 ? nkb / 2 : 1;
   if (s > max_s) s = max_s;
   return s < 1 ? 1 : s;

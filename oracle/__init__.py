@@ -9,7 +9,7 @@ raises if the CUDA library is missing -- there is no CPU fallback.
 
 Contents: ``retrieval_ref.py`` (numpy), ``distill_ref.py`` (torch CPU, fp64 capable) and ``c/itm_eval_ref.c``, a plain-C
 restatement of itm_eval's integer part (ranks with the index tie-break, recall@1/5/10) built by ``c/Makefile`` into
-``_ref/libitm_ref.so`` -- an independent cross-check of the numpy one (``retrieval_ref.itm_eval_c``).
+``_build/libitm_port.so`` (the builder's own port, not the reference compiled) -- an independent cross-check of the numpy one (``retrieval_ref.itm_eval_c``).
 
 Parity pinning: the reference ships NO tests, golden vectors or fixtures for this
 path ("parity unpinned" upstream).  The oracle is therefore

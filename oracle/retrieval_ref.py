@@ -194,12 +194,12 @@ def cosine_matrix(query: np.ndarray, bank: np.ndarray) -> np.ndarray:
 
 # ---- plain-C restatement of the integer part (oracle/c/itm_eval_ref.c), an independent cross-check of the numpy one -----
 def c_oracle():
-    """ctypes handle of oracle/_ref/libitm_ref.so (built by `make -C oracle/c`, which __graft_entry__.build() runs)."""
+    """ctypes handle of oracle/_build/libitm_port.so (built by `make -C oracle/c`, which __graft_entry__.build() runs)."""
     import ctypes
     import os
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
-    so = os.path.join(here, "_ref", "libitm_ref.so")
+    so = os.path.join(here, "_build", "libitm_port.so")
     if not os.path.exists(so):
         subprocess.run(["make", "-s", "-C", os.path.join(here, "c")], check=True)
     lib = ctypes.CDLL(so)

@@ -102,7 +102,7 @@ def test_topk_fill_keeps_exactly_k_and_is_idempotent():
 
 
 def test_c_oracle_agrees_with_numpy_oracle_and_reference_goldens(golden):
-    """oracle/c/itm_eval_ref.c (plain C, built into oracle/_ref/) against the numpy restatement on every golden case, and
+    """oracle/c/itm_eval_ref.c (plain C, built into oracle/_build/) against the numpy restatement on every golden case, and
     against the reference's own itm_eval numbers on the tie-free ones."""
     for case in golden["retrieval"]:
         if case["I"] >= 1000 and case["fill"]:
