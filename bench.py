@@ -108,25 +108,22 @@ def bench_args():
                                "--student_dropout", "0.1"])
 
 
-def kernel_launches_per_iteration(K):
-    # this library's kernels only (torch's mask / bookkeeping kernels are not counted); checked against the ncu launch
-    # list profiles/launches_r01g.csv (288 at K = 8, plus the one-thread index-check kernel added since):
-    #   forward step: 7 GEMMs (p, f, S, dyn, dh, dW2, dW1) + 8 row / element-wise kernels
-    #   reverse step: 9 GEMMs + 11 row / element-wise / scatter kernels
-    #   per call: row normalise, gather, matching loss fwd + bwd, normalise bwd, index-check poison; outer update: 3
-    #   momentum-SGD launches
-    return 15 * K + 20 * K + 6 + 3
-
-
 def algorithmic_bytes_per_iteration(K, P):
     # forward unroll reads theta_k and writes theta_{k+1} (2K passes), matching loss reads 3
     # vectors, reverse sweep reads theta_k, a_{k+1}, writes a_k plus one extra weight pass (4K)
     return 4 * P * (2 * K + 3 + 4 * K)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-# capture of that launch inside one distill iteration (profiles/ncu_r01e_f2_summary.txt).
-DOMINANT_KERNEL_NCU_TRAFFIC_BYTES = 22204928 + 0     # read + write (the 7.4 MB of partial slabs stay in L2)
+def dominant_kernel_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
+    capture of the CURRENT kernel (profiles/ncu_dominant.json, written by profiles/summarise_ncu.py from the .ncu-rep);
+    None when no capture of this round's kernel is committed."""
+    path = os.path.join(ROOT, "profiles", "ncu_dominant.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        d = json.load(f)
+    return d.get("dram_bytes_read", 0) + d.get("dram_bytes_write", 0), d
 
 
 def bench_dominant_kernel(dev, experts, reps=20):
@@ -405,9 +402,7 @@ def run_ours(opt):
 
     def step(i):
         e, s = i % CFG["experts"], (i // CFG["experts"]) % 2          # rotate segments: inputs (4 x 3 x 28 MB) exceed L2
-        loss = eng.segment_loss(e, s, perm_sets[i % 8])
-        eng.outer_step(loss)
-        return loss
+        return eng.step_fast(e, s, perm_sets[i % 8])                   # engine call (+ all-reduce) + fused update
 
     def sync():
         if world > 1:
@@ -421,11 +416,13 @@ def run_ours(opt):
     clk = ClockSampler(local)                       # sampled across both timed regions (device-resident and end-to-end)
     clk.__enter__()
     sync()
+    launches0 = lib().vldd_kernel_launch_count()
     ev0.record()
     for i in range(opt.steps):
         step(opt.warmup + i)
     ev1.record()
     sync()
+    gpu_launches = int(lib().vldd_kernel_launch_count() - launches0)     # counted by the library's launcher, not a formula
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -436,38 +433,45 @@ def run_ours(opt):
 
     # ---- end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ----
     # Expert trajectories stay in host memory as in the reference (distill.py:466-476 uploads the segment every
-    # iteration); distill.SegmentPrefetcher streams segment i+1 on a copy stream while segment i is processed.
+    # iteration).  "streamed": distill.SegmentPrefetcher copies segment i+1 on a copy stream while segment i is processed
+    # (every step moves 2 snapshots = 56.7 MB).  "cached": distill.SegmentCache keeps the most recently used snapshots in a
+    # device-side LRU and uploads only misses (the bench's 4 experts x 3 snapshots all fit, so steady state moves only
+    # the minibatch permutations).  Both read the loss back to the host every step.
     P = ops.head_numel(CFG["dt"], CFG["d"])
-    pre = distill.SegmentPrefetcher(experts_host, dev)
     perms_host = [p.cpu().pin_memory() for p in perm_sets]
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     seg = lambda i: (i % CFG["experts"], (i // CFG["experts"]) % 2)
-    pre.prefetch(*seg(0), 1)
 
-    def e2e_step(i):
-        sl = pre.get()
-        perms = perms_host[i % 8].to(dev, non_blocking=True)
-        masks = ops.fill_dropout_masks(eng.ws, 0.1, eng.gen_dev)
-        loss = distill.UnrolledMatch.apply(eng.Y, eng.U, eng.syn_lr_txt, eng.fixed_scale, sl["th0"], sl["tgt"], perms, masks, eng.ws)
-        pre.release(sl)
-        pre.prefetch(*seg(i + 1), 1)                                     # next segment's H2D overlaps this iteration
-        eng.outer_step(loss)
-        loss_host.copy_(loss.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()                        # the user reads the loss every iteration
-        return float(loss_host)
+    def run_e2e(pre):
+        pre.prefetch(*seg(0), 1)
 
-    for i in range(opt.warmup):
-        e2e_step(i)
-    sync()
-    t0 = time.perf_counter()
-    for i in range(opt.steps):
-        e2e_step(opt.warmup + i)
-    sync()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * opt.steps / float(te)
+        def e2e_step(i):
+            sl = pre.get()
+            eng.ws.perms.copy_(perms_host[i % 8], non_blocking=True)         # H2D straight into the engine's argument buffer
+            loss = eng.step_fast(perms=eng.ws.perms, theta0=sl["th0"], theta_tgt=sl["tgt"])
+            pre.release(sl)
+            pre.prefetch(*seg(i + 1), 1)                                     # next segment's H2D overlaps this iteration
+            loss_host.copy_(loss.reshape(()), non_blocking=True)
+            torch.cuda.current_stream().synchronize()                        # the user reads the loss every iteration
+            return float(loss_host)
+
+        for i in range(max(opt.warmup, 8)):                                  # one full rotation of the 8 segments
+            e2e_step(i)
+        sync()
+        bytes0 = getattr(pre, "h2d_bytes", None)
+        t0 = time.perf_counter()
+        for i in range(opt.steps):
+            e2e_step(max(opt.warmup, 8) + i)
+        sync()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        copied = None if bytes0 is None else (pre.h2d_bytes - bytes0) / opt.steps
+        return world * opt.steps / float(te), copied
+
+    e2e_value, _ = run_e2e(distill.SegmentPrefetcher(experts_host, dev))
+    e2e_cached, cached_bytes = run_e2e(distill.SegmentCache(experts_host, dev, capacity=16))
     clk.__exit__(None, None, None)
     h2d = 2 * P * 4 + K * B * 8
     d2h = 4
@@ -508,11 +512,16 @@ def run_ours(opt):
             "config": workload_config(world),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "segment (theta_start, theta_target, perms) copied from pinned host memory every step "
-                            "(prefetched one iteration ahead on a copy stream); loss read back every step"},
-            "gpu_launches": kernel_launches_per_iteration(K) * opt.steps,
+                    "note": "streamed: segment (theta_start, theta_target, perms) copied from pinned host memory every step "
+                            "(prefetched one iteration ahead on a copy stream); loss read back every step",
+                    "cached": {"value": e2e_cached, "unit": "iters/s", "h2d_bytes_per_step": (cached_bytes or 0) + K * B * 8,
+                               "d2h_bytes_per_step": d2h,
+                               "note": "same host-resident trajectories behind distill.SegmentCache (device-side LRU of uploaded "
+                                       "snapshots, 16 slots): only misses are copied; the bench's 12 snapshots all fit"}},
+            "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": dk_achieved, "peak": pk["hbm"], "unit": "GB/s",
-                         "frac": dk_achieved / pk["hbm"], "traffic": DOMINANT_KERNEL_NCU_TRAFFIC_BYTES,
+                         "frac": dk_achieved / pk["hbm"], "traffic": dominant_kernel_traffic()[0],
+                         "traffic_source": (dominant_kernel_traffic()[1] or {}).get("source"),
                          "peak_source": pk["src"],
                          "kernel": "vldd::tc::tc_gemm_kernel<K-major,K-major,3xTF32,EpiPartial> launched as f = h W2^T "
                                    "(M=100, N=K=2304, split-K %d): the GEMM family is ~62%% of the iteration's kernel time "
@@ -526,8 +535,18 @@ def run_ours(opt):
         }
         if conc is not None:
             out["concurrent_segments"] = conc
+        out["kernels"] = bench_streaming_kernels(dev, experts)
         out["retrieval"] = bench_retrieval(dev, opt)
+        out["gpu_eager_baseline"] = gpu_eager_baseline(dev)
         out["cpu_baseline"] = cpu_baseline_distill(max_seconds=20.0)
+    # every rank takes part in the sharded retrieval sweep and the all-reduce parity check
+    if world > 1:
+        parity = allreduce_parity_check(eng, dev, world, rank)
+    large = bench_retrieval_large(dev, world, rank)
+    if rank == 0:
+        out["retrieval"]["large"] = large
+        if world > 1:
+            out["parity_check"] = parity
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -160,13 +160,39 @@ int vldd_nearest_rows(const float* query, const float* bank, int n_query, int n_
  *              theta_{k+1} = theta_k - lr g (583);
  *   loss = |theta_K - theta_tgt|^2 / |theta_0 - theta_tgt|^2 (588-598);  backward to Y, U, lr, scale (606).
  * perms: int64 [K,B] (unique indices per row);  masks: [K,B,d] pre-scaled dropout masks or NULL.
+ * dropout_p > 0 (needs masks != NULL and rng_state): the engine DRAWS the K masks itself into `masks` at the head of its
+ * launch graph (networks.py:636,643 nn.Dropout(p), students in train mode distill.py:446-447) -- Philox4x32-10 keyed by
+ * rng_state[0] (seed) with rng_state[1] (draws so far, advanced by one per call) in the counter -- and the reverse sweep
+ * reads the same buffer, i.e. replays the same masks.  dropout_p == 0: `masks` is used as given (parity mode).
  * Outputs: out5 = {num, den, loss, dloss/dlr, dloss/dscale}; ce[K] per-step contrastive losses (nullable);
  * dY[N,dt]; dU[N,d]; theta_K[P] (nullable). */
 size_t vldd_unrolled_match_workspace_bytes(int N, int B, int K, int dt, int d);
 int vldd_unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, const float* U, const float* lr,
-                        const float* scale, const int64_t* perms, const float* masks, int N, int B, int K, int dt, int d,
-                        float* out5, float* ce, float* dY, float* dU, float* theta_K, void* workspace,
-                        size_t workspace_bytes, void* stream);
+                        const float* scale, const int64_t* perms, float* masks, float dropout_p,
+                        unsigned long long* rng_state, int N, int B, int K, int dt, int d, float* out5, float* ce, float* dY,
+                        float* dU, float* theta_K, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Numerator and adjoint of the matching loss in one pass (distill.py:588-598 + the first step of 606):
+ *   out3 = {num = |theta_K - theta_tgt|^2, *den, num / *den};  adjoint = 2 (theta_K - theta_tgt) / *den.
+ * `den` = |theta_0 - theta_tgt|^2 is a device scalar computed beforehand (the engine accumulates it while it stages the
+ * segment).  12 B / parameter; scratch as for vldd_match_loss_fwd (ticket word zero before the first use). */
+int vldd_match_final(const float* theta_K, const float* theta_tgt, const float* den, int64_t n, float* out3, float* adjoint,
+                     void* scratch, void* stream);
+
+/* The three torch.optim.SGD(momentum) steps of one outer iteration in ONE launch (distill.py:233-241, 603-613):
+ *   buf = first ? g : momentum * buf + g;  p -= lr * buf   for U ("image_syn", Mode A), Y (text_syn) and the two
+ * learnable student learning rates *syn_lr_img, *syn_lr_txt (device scalars, each nullable; momentum in buf_lr[0], buf_lr[1])
+ * with gradients *g_lr_img (nullable = 0; the fork's logit-scale path, distill.py:548) and *g_lr_txt.  Gradients are multiplied by grad_scale first (1 = sum over
+ * segments / ranks, 1/segments = mean).  If `loss` is given and *loss is not finite nothing is updated and *skipped = 1
+ * (the reference breaks before stepping, distill.py:599-600). */
+int vldd_outer_update(float* U, const float* gU, float* bufU, int64_t nU, float lr_img, float* Y, const float* gY, float* bufY,
+                      int64_t nY, float lr_txt, float* syn_lr_img, float* syn_lr_txt, const float* g_lr_img, const float* g_lr_txt,
+                      float* buf_lr, float lr_lr, float momentum, int first, float grad_scale, const float* loss, int* skipped,
+                      void* stream);
+
+/* Pre-scaled dropout masks (0 or 1/(1-p)) from the engine's generator: Philox4x32-10, key = rng_state[0], counter =
+ * (element index / 4, rng_state[1]); advance != 0 bumps rng_state[1] afterwards.  networks.py:629,636. */
+int vldd_dropout_masks(float* masks, int64_t n, float p, unsigned long long* rng_state, int advance, void* stream);
 
 /* ---- measurement hook ------------------------------------------------------------------------------ */
 /* One launch of the weight-streaming GEMM the engine issues for networks.py:642 (`fc`: f = h W2^T) inside the unroll:

@@ -51,8 +51,12 @@ _SIGS = {
     "vldd_bench_skinny_gemm_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "vldd_bench_skinny_gemm": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P]),
     "vldd_unrolled_match_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "vldd_unrolled_match": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                      _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vldd_unrolled_match": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_float, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vldd_match_final": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P]),
+    "vldd_outer_update": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, _P, _P, _P, C.c_int64, C.c_float, _P, _P, _P, _P, _P,
+                                    C.c_float, C.c_float, C.c_int, C.c_float, _P, _P, _P]),
+    "vldd_dropout_masks": (C.c_int, [_P, C.c_int64, C.c_float, _P, C.c_int, _P]),
 }
 
 

@@ -320,13 +320,37 @@ size_t vldd_unrolled_match_workspace_bytes(int N, int B, int K, int dt, int d) {
 }
 
 int vldd_unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, const float* U, const float* lr,
-                        const float* scale, const int64_t* perms, const float* masks, int N, int B, int K, int dt, int d,
-                        float* out5, float* ce, float* dY, float* dU, float* theta_K, void* workspace,
-                        size_t workspace_bytes, void* stream) {
+                        const float* scale, const int64_t* perms, float* masks, float dropout_p,
+                        unsigned long long* rng_state, int N, int B, int K, int dt, int d, float* out5, float* ce, float* dY,
+                        float* dU, float* theta_K, void* workspace, size_t workspace_bytes, void* stream) {
   VLDD_REQUIRE(theta0 && theta_tgt && Y && U && lr && scale && (K == 0 || perms) && out5 && dY && dU,
                "unrolled_match: null pointer");
-  return unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks, N, B, K, dt, d, out5, ce, dY, dU, theta_K,
-                        workspace, workspace_bytes, S(stream));
+  return unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks, dropout_p, rng_state, N, B, K, dt, d, out5, ce, dY,
+                        dU, theta_K, workspace, workspace_bytes, S(stream));
+}
+
+int vldd_match_final(const float* theta_K, const float* theta_tgt, const float* den, int64_t n, float* out3, float* adjoint,
+                     void* scratch, void* stream) {
+  VLDD_REQUIRE(n > 0 && theta_K && theta_tgt && den && out3 && adjoint && scratch, "match_final: null pointer or n <= 0");
+  const int rc = match_final_pass(theta_K, theta_tgt, den, n, adjoint, scratch, S(stream));
+  return rc ? rc : match_final_finish(den, n, out3, scratch, S(stream));
+}
+
+int vldd_outer_update(float* U, const float* gU, float* bufU, int64_t nU, float lr_img, float* Y, const float* gY, float* bufY,
+                      int64_t nY, float lr_txt, float* syn_lr_img, float* syn_lr_txt, const float* g_lr_img, const float* g_lr_txt,
+                      float* buf_lr, float lr_lr, float momentum, int first, float grad_scale, const float* loss, int* skipped,
+                      void* stream) {
+  VLDD_REQUIRE(nU >= 0 && nY >= 0 && (nU == 0 || (U && gU && bufU)) && (nY == 0 || (Y && gY && bufY)),
+               "outer_update: null pointer or negative size");
+  VLDD_REQUIRE((syn_lr_img == nullptr && syn_lr_txt == nullptr) || buf_lr != nullptr,
+               "outer_update: the student learning rates need their momentum buffer buf_lr[2]");
+  return outer_update(U, gU, bufU, nU, lr_img, Y, gY, bufY, nY, lr_txt, syn_lr_img, syn_lr_txt, g_lr_img, g_lr_txt, buf_lr, lr_lr,
+                      momentum, first, grad_scale, loss, skipped, S(stream));
+}
+
+int vldd_dropout_masks(float* masks, int64_t n, float p, unsigned long long* rng_state, int advance, void* stream) {
+  VLDD_REQUIRE(n >= 0 && (n == 0 || masks) && rng_state && p >= 0.f && p < 1.f, "dropout_masks: bad argument");
+  return dropout_masks(masks, n, p, rng_state, advance, S(stream));
 }
 
 }  // extern "C"

@@ -67,6 +67,8 @@ struct Work {
   float *neg_one;                      // device constant -1 (first-order API)
   int* bad_index;                      // set by the gather kernel when a minibatch index is out of range
   void* ml_scratch;
+  void* stage_scratch;                 // ticket + block partials of the staging kernel (runs outside the graph)
+  float* den;                          // |theta_0 - theta*|^2, produced while the segment is staged
   size_t bytes;
 };
 
@@ -112,6 +114,8 @@ void carve(Work& w, const Dims& m, void* base) {
   w.neg_one = b.f(4);
   w.bad_index = reinterpret_cast<int*>(b.f(4));
   w.ml_scratch = b.f((size_t)match_loss_scratch_bytes() / sizeof(float) + 8);
+  w.stage_scratch = b.f((size_t)match_loss_scratch_bytes() / sizeof(float) + 8);
+  w.den = b.f(4);
   w.bytes = b.off;
 }
 
@@ -493,8 +497,9 @@ size_t unrolled_match_workspace_bytes(int N, int B, int K, int dt, int d) {
 // (~300 kernels) is captured ONCE per such address set into a CUDA graph and replayed afterwards.
 // ---------------------------------------------------------------------------------------------------
 static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const float* U, const float* lr,
-                               const float* scale, const int64_t* perms, const float* masks, float* out5, float* ce,
-                               float* dY, float* dU, float* theta_K, cudaStream_t st) {
+                               const float* scale, const int64_t* perms, const float* masks, float dropout_p,
+                               unsigned long long* rng_state, float* out5, float* ce, float* dY, float* dU, float* theta_K,
+                               cudaStream_t st) {
   const int N = m.N, B = m.B, K = m.K, dt = m.dt, d = m.d;
   const size_t Bd = (size_t)B * d;
   Lanes L;
@@ -506,6 +511,14 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   VLDD_CUDA(cudaMemsetAsync(w.dXn, 0, (size_t)N * d * sizeof(float), st));
   CHECK_RC(zero_square_matrices(m, w, st));
   MARK("start");
+  // fresh dropout masks for the K student steps (networks.py:636,643), drawn by the engine itself on a side branch; the
+  // reverse sweep reads the same buffer, i.e. replays the same masks.  First use: the LayerNorm kernel of step 0.
+  if (masks != nullptr && dropout_p > 0.f && rng_state != nullptr && K > 0) {
+    CHECK_RC(lane_edge(st, L.s2));
+    L.s2_busy = true;
+    CHECK_RC(dropout_masks(const_cast<float*>(masks), (int64_t)K * (int64_t)Bd, dropout_p, rng_state, 1, L.s2));
+    prof_mark("dropout_masks", L.s2);
+  }
   launch_k(row_normalise_kernel, N, 256, 0, st, U, d, w.Xn, w.un);
   MARK("row_normalise");
   // minibatches of all K steps in one launch (distill.py:510-513)
@@ -524,9 +537,12 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   }
   CHECK_RC(lanes_join(L));
   const float* thK = w.traj + (size_t)K * m.P;
-  CHECK_RC(match_loss_fwd(thK, w.tgt, w.traj, m.P, out5, w.ml_scratch, st));
-  CHECK_RC(match_loss_bwd(thK, w.tgt, out5, nullptr, w.adj0, m.P, st));
-  MARK("match_loss fwd+bwd");
+  // numerator + adjoint a_K = 2 (theta_K - theta*) / den in one pass (den was accumulated while the segment was staged)
+  CHECK_RC(match_final_pass(thK, w.tgt, w.den, m.P, w.adj0, w.ml_scratch, st));
+  CHECK_RC(lane_edge(st, L.s2));                 // the finish (block partials -> out5[0..2]) rides on a side branch: nothing
+  L.s2_busy = true;                              // in the reverse sweep reads the numerator
+  CHECK_RC(match_final_finish(w.den, m.P, out5, w.ml_scratch, L.s2));
+  MARK("match_final");
   if (theta_K) VLDD_CUDA(cudaMemcpyAsync(theta_K, thK, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // reverse sweep
   float* a_cur = w.adj0;
@@ -537,6 +553,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
                           perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L));
     float* t = a_cur; a_cur = a_nxt; a_nxt = t;
   }
+  CHECK_RC(lanes_join(L));            // K == 0: no reverse step has joined the matching-loss finish yet
   launch_k(row_normalise_bwd_kernel, N, 256, 0, st, w.Xn, w.un, w.dXn, nullptr, d, dU);
   MARK("row_normalise_bwd");
   if (K > 0) launch_k(poison_kernel, 1, 32, 0, st, (const int*)w.bad_index, out5);
@@ -546,8 +563,9 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
 
 namespace {
 struct GraphKey {
-  const void* p[12];
+  const void* p[13];
   int dims[5];
+  float dropout_p;
   bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t last_use; unsigned long long kernels; };
@@ -567,9 +585,9 @@ bool graphs_enabled() {
 }  // namespace
 
 int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, const float* U, const float* lr,
-                   const float* scale, const int64_t* perms, const float* masks, int N, int B, int K, int dt, int d,
-                   float* out5, float* ce, float* dY, float* dU, float* theta_K, void* workspace,
-                   size_t workspace_bytes, cudaStream_t st) {
+                   const float* scale, const int64_t* perms, const float* masks, float dropout_p,
+                   unsigned long long* rng_state, int N, int B, int K, int dt, int d, float* out5, float* ce, float* dY,
+                   float* dU, float* theta_K, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   CHECK_RC(validate(N, B, K, dt, d));
   const Dims m = make_dims(N, B, K, dt, d);
   Work w;
@@ -578,20 +596,25 @@ int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, 
     set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
     return VLDD_ERR_WORKSPACE;
   }
-  // stage the segment into the workspace (outside the graph: these two source addresses change every iteration)
-  VLDD_CUDA(cudaMemcpyAsync(w.traj, theta0, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  VLDD_CUDA(cudaMemcpyAsync(w.tgt, theta_tgt, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  VLDD_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p=%f out of range [0,1)", dropout_p);
+  VLDD_REQUIRE(!(dropout_p > 0.f) || (masks != nullptr && rng_state != nullptr),
+               "dropout_p > 0 needs a [K,B,d] mask buffer and an rng state {seed, draws}");
+  // stage the segment into the workspace (outside the graph: these two source addresses change every iteration); the same
+  // pass accumulates the denominator |theta_0 - theta*|^2 of the matching loss
+  VLDD_CUDA(cudaMemsetAsync(w.stage_scratch, 0, 16, st));
+  CHECK_RC(stage_segment(theta0, theta_tgt, w.traj, w.tgt, m.P, w.den, w.stage_scratch, st));
   if (!graphs_enabled() || prof_enabled()) {
     std::lock_guard<std::mutex> lock(g_graph_mu);   // the side streams / event pool are process-wide
-    return unrolled_match_body(m, w, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K, st);
+    return unrolled_match_body(m, w, Y, U, lr, scale, perms, masks, dropout_p, rng_state, out5, ce, dY, dU, theta_K, st);
   }
 
   GraphKey key;
   memset(&key, 0, sizeof(key));
-  const void* ptrs[12] = {workspace, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K};
+  const void* ptrs[13] = {workspace, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K, rng_state};
   memcpy(key.p, ptrs, sizeof(ptrs));
   const int dims[5] = {N, B, K, dt, d};
   memcpy(key.dims, dims, sizeof(dims));
+  key.dropout_p = dropout_p;
   std::lock_guard<std::mutex> lock(g_graph_mu);
   cudaGraphExec_t exec = nullptr;
   unsigned long long graph_kernels = 0;
@@ -604,7 +627,8 @@ int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, 
     cudaStream_t g_capture_stream = ds->capture;
     VLDD_CUDA(cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal));
     const unsigned long long before = launch_counter().load();
-    const int rc = unrolled_match_body(m, w, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K, g_capture_stream);
+    const int rc = unrolled_match_body(m, w, Y, U, lr, scale, perms, masks, dropout_p, rng_state, out5, ce, dY, dU, theta_K,
+                                       g_capture_stream);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce_end = cudaStreamEndCapture(g_capture_stream, &graph);
     graph_kernels = launch_counter().exchange(before) - before;   // recorded, not run: counted per replay below

@@ -8,9 +8,9 @@ namespace vldd {
 
 size_t unrolled_match_workspace_bytes(int N, int B, int K, int dt, int d);
 int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, const float* U, const float* lr,
-                   const float* scale, const int64_t* perms, const float* masks, int N, int B, int K, int dt, int d,
-                   float* out5, float* ce, float* dY, float* dU, float* theta_K, void* workspace,
-                   size_t workspace_bytes, cudaStream_t st);
+                   const float* scale, const int64_t* perms, const float* masks, float dropout_p,
+                   unsigned long long* rng_state, int N, int B, int K, int dt, int d, float* out5, float* ce, float* dY,
+                   float* dU, float* theta_K, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t contrastive_step_workspace_bytes(int B, int dt, int d);
 int contrastive_step(const float* theta, const float* Y, const float* U, const float* scale, const float* mask, int B,
                      int dt, int d, float* loss, float* g_theta, float* dY, float* dU, float* dscale, void* workspace,

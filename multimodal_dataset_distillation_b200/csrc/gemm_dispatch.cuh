@@ -55,18 +55,33 @@ inline int simt_pick_splits(int M, int N, int Ktot) {
 }
 // upper bound of the split count either backend may choose (workspace sizing)
 inline int max_splits(int M, int N, int Ktot) {
-  const int a = simt_pick_splits(M, N, Ktot), b = tc::pick_splits(M, N, Ktot);
-  return a > b ? a : b;
+  const int a = simt_pick_splits(M, N, Ktot), b = tc::pick_splits(M, N, Ktot), c = tc::pick_splits(M, N, Ktot, 64);
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
+
+// Tile width of the split-K GEMMs (profiles/gemm_sweep_r02*.txt, B200, GEMM + slab consumer timed as a dependent pair).
+// The main loop is bound by the shared-memory port: per k-block the A tile crosses it twice (TMA write, splitter read) and the
+// B tile six times (TMA write, splitter read, B_lo write, three MMA reads) = 32 KB + 6 * BN * 128 B at 128 B/clk, i.e.
+// 0.50 us at BN = 128 and 0.32 us at BN = 64, and a 64-wide tile needs half the K splits to fill one wave, so its consumer
+// sums half as many slabs: p (K = 768) 10.1 -> 8.8 us, S 10.9 -> 9.8, dY 12.2 -> 11.0, f / dh (K = 2304) 13.2 -> 13.1.
+// Only the long-K, wide-N products (K >= 4608: f-tangent, dh-tangent) keep 128 columns (18.1 vs 19.1 us): with 36 k-blocks per
+// CTA the re-read of the activation tile by twice as many n-tiles outweighs the slabs.
+// (one M tile only: with many M tiles there is no split-K to save and the wider tile does more MMA work per byte of shared memory)
+inline bool narrow_tile(const GemmOperands& g) { return g.M <= tc::BM && !(g.K0 + g.K1 >= 4096 && g.N >= 1024); }
+inline int tc_partial_splits(const GemmOperands& g) { return tc::pick_splits(g.M, g.N, g.K0 + g.K1, narrow_tile(g) ? 64 : 128); }
 
 // partial slabs: part[z][M*N], returns the split count through *splits
 template <bool AK, bool BKm>
 inline int gemm_partial(const GemmOperands& g, float* part, int* splits, cudaStream_t st, int old_mask = 0) {
   const int Kt = g.K0 + g.K1;
   if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) {
-    *splits = tc::pick_splits(g.M, g.N, Kt);
-    if (tf32_single_pass())
+    if (tf32_single_pass()) {
+      *splits = tc::pick_splits(g.M, g.N, Kt);
       return tc::launch<AK, BKm, 1, tc::EpiPartial>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st, nullptr, nullptr, old_mask);
+    }
+    *splits = tc_partial_splits(g);
+    if (narrow_tile(g))
+      return tc::launch<AK, BKm, 3, tc::EpiPartial, VLDD_STAGES_PARTIAL, 64>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st, nullptr, nullptr, old_mask);
     return tc::launch<AK, BKm, 3, tc::EpiPartial, VLDD_STAGES_PARTIAL>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st, nullptr, nullptr, old_mask);
   }
   *splits = simt_pick_splits(g.M, g.N, Kt);
@@ -92,8 +107,15 @@ inline int gemm_axpy(const GemmOperands& g, const float* src, float* dst, int ld
   if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) {
     // 128 x 96 tiles when they divide N: 2304 x 2304 -> 432 work items = 2.92 per SM (three even rounds) instead of
     // 324 = 2.19 (28 CTAs run a third round while 120 idle)
-    if (g.N % 96 == 0 && ceil_div(g.M, tc::BM) * (g.N / 128) > num_sms())
+    // (8 epilogue warps -- two per TMEM lane quadrant -- keep twice the `src` loads in flight: 15.1 -> 13.8 us for K = 100;
+    //  with two K segments the 4-stage pipeline they leave room for costs what they gain: 18.6 vs 18.8 us)
+    if (g.N % 96 == 0 && ceil_div(g.M, tc::BM) * (g.N / 128) > num_sms()) {
+      if (g.K1 == 0)
+        return tc::launch<AK, BKm, 3, tc::EpiAxpyTC, VLDD_STAGES_AXPY, 96, 8>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st, nullptr, nullptr, old_mask);
       return tc::launch<AK, BKm, 3, tc::EpiAxpyTC, VLDD_STAGES_AXPY, 96>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st, nullptr, nullptr, old_mask);
+    }
+    if (g.N % 96 == 0 && g.K1 == 0)
+      return tc::launch<AK, BKm, 3, tc::EpiAxpyTC, VLDD_STAGES_AXPY, 96, 8>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st, nullptr, nullptr, old_mask);
     return tc::launch<AK, BKm, 3, tc::EpiAxpyTC, VLDD_STAGES_AXPY>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st, nullptr, nullptr, old_mask);
   }
   launch_gemm<AK, BKm>(g, 1, nullptr, EpiAxpy{src, dst, ld, lr}, st);

@@ -15,6 +15,15 @@ int match_loss_bwd(const float* thK, const float* tgt, const float* num_den, con
                    cudaStream_t st);
 int momentum_sgd(float* p, const float* g, float* buf, float lr, float momentum, int first, int64_t n,
                  cudaStream_t st);
+int stage_segment(const float* th0_src, const float* tgt_src, float* th0_dst, float* tgt_dst, int64_t n, float* den_out,
+                  void* scratch, cudaStream_t st);
+int match_final_pass(const float* thK, const float* tgt, const float* den, int64_t n, float* a, void* scratch, cudaStream_t st);
+int match_final_finish(const float* den, int64_t n, float* out3, void* scratch, cudaStream_t finish_st);
+int outer_update(float* U, const float* gU, float* bufU, int64_t nU, float lrU, float* Y, const float* gY, float* bufY,
+                 int64_t nY, float lrY, float* syn_lr_img, float* syn_lr_txt, const float* g_lr_img, const float* g_lr_txt,
+                 float* buf_lr, float lr_lr, float momentum, int first, float gscale, const float* loss, int* skipped,
+                 cudaStream_t st);
+int dropout_masks(float* masks, int64_t n, float p, unsigned long long* state, int advance, cudaStream_t st);
 
 // retrieval.cu
 int ranks_rows(const float* S, int64_t ld, int nrows, int ncols, const int32_t* gt_ptr, const int32_t* gt_idx,

@@ -101,6 +101,13 @@ def build_parser() -> argparse.ArgumentParser:
     A("--segments_in_flight", type=int, default=1,
       help="expert segments per outer step processed concurrently on this GPU (throughput mode, DistillEngine.segments_step); "
            "1 = the reference's one segment per iteration")
+    A("--grad_reduce", type=str, default="sum", choices=["sum", "mean"],
+      help="how the synthetic-data gradients of the segments of one outer step (segments_in_flight x world size) are combined "
+           "before the SGD step: sum (a G-segment step is G times the reference's single-segment step; scale lr_img / lr_txt / "
+           "lr_lr down accordingly) or mean (same step size as the reference, lower variance)")
+    A("--save_path", type=str, default=None,
+      help="directory for the distilled set (distilled_{it}.pt: U, Y, syn_lr_img, syn_lr_txt[, sentences]) at the evaluation "
+           "iterations and at exit; default {buffer_path}/distilled")
     A("--student_dropout", type=float, default=0.1,
       help="dropout of the student text_projection during the unroll (networks.py:629,636; students are in train mode, "
            "distill.py:446-447); 0 gives the deterministic parity mode")
@@ -180,7 +187,7 @@ class DistillEngine:
     """State of the distillation: synthetic pairs, learnable student lr(s), outer momentum-SGD, expert segments."""
 
     def __init__(self, image_embed: torch.Tensor, text_embed: torch.Tensor, experts: torch.Tensor, args,
-                 device="cuda", process_group=None):
+                 device="cuda", process_group=None, rank: int = 0, world: int = 1):
         self.args = args
         self.dev = torch.device(device)
         self.U = image_embed.to(self.dev, torch.float32).contiguous().requires_grad_(True)       # "image_syn" (Mode A)
@@ -193,15 +200,27 @@ class DistillEngine:
         self.K = int(args.syn_steps)
         self.B = min(int(args.mini_batch_size), self.N)
         self.ws = ops.UnrollWorkspace(self.N, self.B, self.K, self.dt, self.d, self.dev)
-        self.bufs = {n: torch.zeros_like(t) for n, t in (("U", self.U), ("Y", self.Y))}
-        self.buf_lr = torch.zeros(2, device=self.dev)
+        # momentum buffers of the outer SGD, one allocation laid out like UnrollWorkspace.pack: [U | Y | lr_img, lr_txt | pad]
+        n_u, n_y = self.N * self.d, self.N * self.dt
+        self.buf_pack = torch.zeros(n_u + n_y + 8, device=self.dev)
+        self.bufs = {"U": self.buf_pack[:n_u].view(self.N, self.d), "Y": self.buf_pack[n_u:n_u + n_y].view(self.N, self.dt)}
+        self.buf_lr = self.buf_pack[n_u + n_y:n_u + n_y + 2]
         self.first = True
         self.pg = process_group
-        self.gen = torch.Generator().manual_seed(int(getattr(args, "seed", 0)))
-        self.gen_dev = torch.Generator(device=self.dev).manual_seed(int(getattr(args, "seed", 0)) + 1)
-        self.expert_idx = 0
+        self._init_sampling(int(getattr(args, "seed", 0)), rank, world, int(experts.shape[0]))
+        self.rng_state = ops.make_rng_state(self.seed_base + 7919 * (self.rank + 1), self.dev)
         self.fixed_scale = torch.tensor(ops.LOGIT_SCALE_UPSTREAM, device=self.dev)
         self._lanes = []                            # (stream, workspace) pairs of segments_step
+
+    def _init_sampling(self, seed: int, rank: int, world: int, n_experts: int):
+        """Host-side sampling state (no device work).  Every rank must sample DIFFERENT segments, minibatches and dropout
+        masks -- with one seed everywhere the all-reduce would only multiply one gradient by the world size -- so the host
+        generator, the device Philox seed and the expert cursor are offset by the rank; the cursor then advances by the
+        world size, i.e. ranks walk disjoint residue classes of the expert list (distill.py:450-465 consumes them in order)."""
+        self.rank, self.world = int(rank), max(int(world), 1)
+        self.seed_base = int(seed) * 1000003
+        self.gen = torch.Generator().manual_seed(self.seed_base + self.rank)
+        self.expert_idx = self.rank % max(int(n_experts), 1)
 
     # -- one expert segment -> loss and grads (distill.py:466-606) --
     def segment_loss(self, expert: int, start_epoch: int, perms: torch.Tensor | None = None, masks=None, workspace=None):
@@ -209,15 +228,63 @@ class DistillEngine:
         ws = self.ws if workspace is None else workspace
         theta0 = self.experts[expert, start_epoch]
         theta_tgt = self.experts[expert, start_epoch + int(a.expert_epochs)]
-        if perms is None:                                           # distill.py:510-511
-            perms = torch.stack([torch.randperm(self.N, generator=self.gen)[: self.B] for _ in range(self.K)])
+        if perms is None:
+            perms = self.draw_perms()
         perms = perms.to(self.dev)
         fork = getattr(a, "logit_scale_mode", "fork") == "fork"
         scale = self.syn_lr_img if fork else self.fixed_scale
         p_drop = float(getattr(a, "student_dropout", 0.0))
         if masks is None and p_drop > 0.0 and self.K > 0:
-            masks = ops.fill_dropout_masks(ws, p_drop, self.gen_dev)           # fresh masks per call, as nn.Dropout does
+            masks = ops.fill_dropout_masks(ws, p_drop, self.rng_state)         # fresh masks per call, as nn.Dropout does
         return UnrolledMatch.apply(self.Y, self.U, self.syn_lr_txt, scale, theta0, theta_tgt, perms, masks, ws)
+
+    def draw_perms(self) -> torch.Tensor:
+        """distill.py:510-511: a fresh randperm(N)[:B] per student step, from this rank's host generator."""
+        return torch.stack([torch.randperm(self.N, generator=self.gen)[: self.B] for _ in range(self.K)])
+
+    def _grad_scale(self, segments_here: int = 1) -> float:
+        if getattr(self.args, "grad_reduce", "sum") != "mean":
+            return 1.0
+        world = self.world
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size(self.pg)
+        return 1.0 / float(segments_here * world)
+
+    def step_fast(self, expert: int | None = None, start_epoch: int | None = None, perms: torch.Tensor | None = None,
+                  theta0: torch.Tensor | None = None, theta_tgt: torch.Tensor | None = None):
+        """One whole outer iteration (distill.py:439-613) without autograd in the loop: ONE engine call (which also draws
+        the dropout masks), one all-reduce of the packed gradient buffer when a process group is up, ONE update kernel.
+        No torch kernel is launched.  Returns the loss as a view of the workspace (valid until the next call); a
+        non-finite loss leaves the synthetic set untouched and raises ``ws.skipped`` (distill.py:599-600).
+        theta0 / theta_tgt override the resident experts (host-streamed segments, SegmentPrefetcher)."""
+        a, ws = self.args, self.ws
+        if theta0 is None:
+            theta0 = self.experts[expert, start_epoch]
+            theta_tgt = self.experts[expert, start_epoch + int(a.expert_epochs)]
+        if perms is None:
+            perms = self.draw_perms().pin_memory().to(self.dev, non_blocking=True)
+        fork = getattr(a, "logit_scale_mode", "fork") == "fork"
+        scale = self.syn_lr_img if fork else self.fixed_scale
+        p_drop = float(getattr(a, "student_dropout", 0.0)) if self.K > 0 else 0.0
+        ops.unrolled_match(theta0, theta_tgt, self.Y.detach(), self.U.detach(), self.syn_lr_txt.detach(), scale.detach(), perms,
+                           None, ws, dropout_p=p_drop, rng_state=self.rng_state if p_drop > 0 else None, clone_results=False)
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            if torch.distributed.get_world_size(self.pg) > 1:
+                torch.distributed.all_reduce(ws.pack, group=self.pg)     # [dU | dY | out5]: 1.23 MB at Flickr shape
+        self.apply_update(ws)
+        return ws.out5[2]
+
+    def apply_update(self, ws, segments_here: int = 1):
+        """Fused momentum-SGD update of (U, Y, syn_lr_img, syn_lr_txt) from a workspace's packed gradients."""
+        a = self.args
+        n_u, n_y = self.N * self.d, self.N * self.dt
+        fork = getattr(a, "logit_scale_mode", "fork") == "fork"
+        ops.outer_update(self.U.detach(), ws.dU, self.buf_pack[:n_u], float(a.lr_img),
+                         self.Y.detach(), ws.dY, self.buf_pack[n_u:n_u + n_y], float(a.lr_txt),
+                         self.syn_lr_img.detach(), self.syn_lr_txt.detach(), ws.out5[4:5] if fork else None, ws.out5[3:4],
+                         self.buf_pack[n_u + n_y:n_u + n_y + 2], float(a.lr_lr), 0.5, self.first,
+                         self._grad_scale(segments_here), ws.out5[2:3], ws.skipped)
+        self.first = False
 
     def segments_step(self, segments, perms_list=None):
         """Throughput mode: several expert segments of ONE outer step in flight at once on this GPU.
@@ -250,7 +317,7 @@ class DistillEngine:
     def sample_segment(self):
         """distill.py:450-470: experts are consumed in order, start_epoch ~ U{0..max_start_epoch-1}."""
         e = self.expert_idx
-        self.expert_idx = (self.expert_idx + 1) % self.experts.shape[0]
+        self.expert_idx = (self.expert_idx + self.world) % self.experts.shape[0]     # ranks walk disjoint residue classes
         hi = min(int(self.args.max_start_epoch), self.experts.shape[1] - int(self.args.expert_epochs))
         s = int(torch.randint(0, max(hi, 1), (1,), generator=self.gen))
         return e, s
@@ -266,6 +333,9 @@ class DistillEngine:
             # one NCCL all-reduce of the packed [dU | dY | dlr_img, dlr_txt] buffer (1.23 MB at Flickr shape)
             dist_mod.allreduce_packed([self.U.grad, self.Y.grad, g_lr], group=self.pg)
         a = self.args
+        gs = self._grad_scale(max(int(getattr(a, "segments_in_flight", 1)), 1))
+        if gs != 1.0:                                                # --grad_reduce mean
+            self.U.grad.mul_(gs); self.Y.grad.mul_(gs); g_lr = g_lr * gs
         with torch.no_grad():
             ops.momentum_sgd_(self.U, self.U.grad, self.bufs["U"], float(a.lr_img), 0.5, self.first)
             ops.momentum_sgd_(self.Y, self.Y.grad, self.bufs["Y"], float(a.lr_txt), 0.5, self.first)
@@ -280,9 +350,7 @@ class DistillEngine:
         if g > 1:
             return self.segments_step([self.sample_segment() for _ in range(g)])[0]
         e, s = self.sample_segment()
-        loss = self.segment_loss(e, s)
-        self.outer_step(loss)
-        return loss
+        return self.step_fast(e, s)
 
 
 class SegmentPrefetcher:
@@ -323,6 +391,68 @@ class SegmentPrefetcher:
 
     def release(self, sl):
         sl["free"].record(torch.cuda.current_stream(self.dev))
+
+
+class SegmentCache:
+    """Host-resident expert trajectories with a device-side LRU of uploaded snapshots.
+
+    The reference uploads theta_start and theta_target from CPU lists every iteration (distill.py:466-476) although the
+    same (expert, epoch) snapshots come back again and again (experts are cycled, start epochs are drawn from a small range,
+    and one iteration's target snapshot is a later iteration's start).  When all trajectories fit in HBM keep them resident
+    (``load_expert_buffers``); when they do not, this cache keeps the most recently used `capacity` snapshots on the device,
+    uploads only misses -- on a copy stream, one iteration ahead, like SegmentPrefetcher -- and evicts least-recently-used
+    slots.  Same prefetch / get / release protocol as SegmentPrefetcher; ``h2d_bytes`` counts what was actually copied.
+    """
+
+    def __init__(self, experts_host: torch.Tensor, device="cuda", capacity: int = 64):
+        import collections
+        self.host = experts_host if experts_host.is_pinned() else experts_host.pin_memory()
+        self.dev = torch.device(device)
+        self.P = int(self.host.shape[-1])
+        self.capacity = max(int(capacity), 4)            # two snapshots in use + two being prefetched
+        self.slots = collections.OrderedDict()           # (expert, snapshot) -> dict(buf, ready, free); order = recency
+        self.spare = []
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.pending = None
+        self.h2d_bytes = 0
+        self.hits = self.misses = 0
+
+    def _slot_for(self, key):
+        sl = self.slots.get(key)
+        if sl is not None:
+            self.slots.move_to_end(key)
+            self.hits += 1
+            return sl
+        self.misses += 1
+        if len(self.slots) < self.capacity:
+            sl = dict(buf=torch.empty(self.P, device=self.dev), ready=torch.cuda.Event(), free=torch.cuda.Event())
+            sl["free"].record(torch.cuda.current_stream(self.dev))
+        else:
+            _, sl = self.slots.popitem(last=False)       # least recently used
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(sl["free"])      # the engine has staged this slot's previous content
+            sl["buf"].copy_(self.host[key[0], key[1]], non_blocking=True)
+            sl["ready"].record(self.copy_stream)
+        self.h2d_bytes += self.P * 4
+        self.slots[key] = sl
+        return sl
+
+    def prefetch(self, expert: int, start_epoch: int, expert_epochs: int):
+        a = self._slot_for((int(expert), int(start_epoch)))
+        b = self._slot_for((int(expert), int(start_epoch) + int(expert_epochs)))
+        self.pending = dict(th0=a["buf"], tgt=b["buf"], _slots=(a, b))
+
+    def get(self):
+        sl = self.pending
+        st = torch.cuda.current_stream(self.dev)
+        for x in sl["_slots"]:
+            st.wait_event(x["ready"])
+        return sl
+
+    def release(self, sl):
+        st = torch.cuda.current_stream(self.dev)
+        for x in sl["_slots"]:
+            x["free"].record(st)
 
 
 def synthetic_experts(n_experts: int, n_snapshots: int, dt: int, d: int, seed: int = 0, step: float = 0.01) -> torch.Tensor:
@@ -381,36 +511,77 @@ def evaluate_synthetic_set(eng: "DistillEngine", test, args):
     return results
 
 
+def save_distilled(eng: "DistillEngine", path: str, it: int, sentences=None) -> str:
+    """The distilled set as the reference keeps it around for evaluation / visualisation (distill.py:331-384): synthetic
+    image embeddings, synthetic text embeddings, the learned student learning rates, and the nearest training captions."""
+    os.makedirs(path, exist_ok=True)
+    out = os.path.join(path, f"distilled_{it}.pt")
+    blob = dict(iteration=it, U=eng.U.detach().cpu(), Y=eng.Y.detach().cpu(), syn_lr_img=float(eng.syn_lr_img.detach()),
+                syn_lr_txt=float(eng.syn_lr_txt.detach()))
+    if sentences is not None:
+        blob["sentences"] = sentences
+    torch.save(blob, out)
+    return out
+
+
 def main(args):
     if not torch.cuda.is_available():
         raise RuntimeError("distill needs a CUDA device (sm_100a); there is no CPU path")
-    args.device = "cuda"                                                     # distill.py:214
-    dev = torch.device("cuda")
+    # one process per GPU (torchrun): every rank runs a different expert segment per outer step against the same
+    # replicated synthetic set; gradients are all-reduced (NCCL) before the identical update on every rank
+    rank, world, local = dist_mod.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    args.device = str(dev)                                                   # distill.py:214
     N = int(args.num_queries)
+    train_text, sentences = None, None
     if args.synthetic or args.embed_path is None:
-        g = torch.Generator().manual_seed(args.seed)
+        g = torch.Generator().manual_seed(args.seed)                         # same seed on every rank: replicated synthetic set
         dt, d = 768, 2304
         img = torch.randn(N, d, generator=g)
         txt = torch.randn(N, dt, generator=g) * 0.5253 - 0.0094             # distill_original.py:147
-        experts = synthetic_experts(2, int(args.max_start_epoch) + int(args.expert_epochs) + 1, dt, d, args.seed).to(dev)
+        experts = synthetic_experts(max(2, world), int(args.max_start_epoch) + int(args.expert_epochs) + 1, dt, d, args.seed).to(dev)
     else:
-        z = np.load(args.embed_path)
+        z = np.load(args.embed_path, allow_pickle=True)
         sel = np.random.default_rng(args.seed).permutation(len(z["image_embed"]))[:N]   # distill.py:231 random real pairs
         img, txt = torch.from_numpy(z["image_embed"][sel]), torch.from_numpy(z["text_embed"][sel])
         experts = load_expert_buffers(args.buffer_path, "txt", args.max_files, dev)
-    eng = DistillEngine(img, txt, experts, args, dev)
+        if "sentences" in z.files:                                           # for the nearest-caption read-out (distill.py:374)
+            train_text, sentences = torch.from_numpy(z["text_embed"]).float(), [str(x) for x in z["sentences"]]
+    eng = DistillEngine(img, txt, experts, args, dev, rank=rank, world=world)
     test = _load_test_split(args, dev)
     eval_it_pool = list(range(0, int(args.Iteration) + 1, max(int(args.eval_it), 1))) if test is not None else []   # distill.py:285
+    save_path = args.save_path or os.path.join(str(args.buffer_path), "distilled")
     eng.eval_history = []
+    if rank == 0:
+        os.makedirs(save_path, exist_ok=True)                                # fail now, not after the last iteration
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    it = 0
     for it in range(int(args.Iteration) + 1):
         if it in eval_it_pool:                                               # distill.py:293-330
-            eng.eval_history.append((it, evaluate_synthetic_set(eng, test, args)))
+            if rank == 0:
+                eng.eval_history.append((it, evaluate_synthetic_set(eng, test, args)))
+                near = nearest_neighbor(sentences, eng.Y.detach(), train_text) if sentences is not None else None
+                save_distilled(eng, save_path, it, near)
+            if world > 1:
+                torch.distributed.barrier()
         loss = eng.iteration()
-        if it % 10 == 0:
-            v = float(loss.detach())
-            if math.isnan(v):                                                # distill.py:599-600
-                break
+        # distill.py:599-600: a NaN loss ends the run BEFORE the update is applied.  The update kernel itself refuses to step
+        # on a non-finite loss (device-side, every iteration); the host looks at the loss every iteration too -- one 4-byte
+        # read that the engine's ~2 ms of queued work hides.
+        loss_host.copy_(loss.detach().reshape(()), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        v = float(loss_host)
+        if math.isnan(v) or math.isinf(v):
+            if rank == 0:
+                print("%s iter = %04d, loss = %s: stopping, synthetic set left at the last finite iteration" % (
+                    datetime.datetime.now().strftime("[%Y-%m-%d %H:%M:%S]"), it, v))
+            break
+        if it % 10 == 0 and rank == 0:
             print("%s iter = %04d, loss = %.4f" % (datetime.datetime.now().strftime("[%Y-%m-%d %H:%M:%S]"), it, v))
+    if rank == 0:
+        near = nearest_neighbor(sentences, eng.Y.detach(), train_text) if sentences is not None else None
+        eng.saved_to = save_distilled(eng, save_path, it, near)
     return eng
 
 

@@ -384,31 +384,74 @@ class UnrollWorkspace:
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.perms = torch.empty(max(K, 1), B, dtype=torch.int64, device=device)
         self.masks = None
-        self.out5 = torch.empty(5, dtype=torch.float32, device=device)
+        # results live in ONE packed buffer [dU | dY | out5 | pad]: a multi-GPU run all-reduces it with a single collective and
+        # no concatenation (out5 = {num, den, loss, dloss/dlr, dloss/dscale} is summed along: harmless, the loss sum is reported)
+        n_u, n_y = N * d, N * dt
+        self.pack = torch.zeros(n_u + n_y + 8, dtype=torch.float32, device=device)
+        self.dU = self.pack[:n_u].view(N, d)
+        self.dY = self.pack[n_u:n_u + n_y].view(N, dt)
+        self.out5 = self.pack[n_u + n_y:n_u + n_y + 5]
         self.ce = torch.empty(max(K, 1), dtype=torch.float32, device=device)
-        self.dY = torch.empty(N, dt, dtype=torch.float32, device=device)
-        self.dU = torch.empty(N, d, dtype=torch.float32, device=device)
+        self.skipped = torch.zeros(1, dtype=torch.int32, device=device)     # raised by outer_update on a non-finite loss
         self.theta_K = None
         self.lr = torch.empty(1, dtype=torch.float32, device=device)
         self.scale = torch.empty(1, dtype=torch.float32, device=device)
 
 
-def fill_dropout_masks(workspace: "UnrollWorkspace", p: float, generator: torch.Generator | None = None) -> torch.Tensor:
-    """Fresh pre-scaled dropout masks (0 or 1/(1-p)) for the K student steps, drawn in place in the workspace.
+def fill_dropout_masks(workspace: "UnrollWorkspace", p: float, rng_state: torch.Tensor) -> torch.Tensor:
+    """Fresh pre-scaled dropout masks (0 or 1/(1-p)) for the K student steps, drawn in place in the workspace by the
+    library's own Philox kernel (no torch kernel involved); advances `rng_state`.
 
     The reference's students run in train mode (distill.py:446-447), so every forward of text_projection draws a new
-    nn.Dropout(0.1) mask (networks.py:636,643); the engine replays the SAME masks in its reverse sweep.
+    nn.Dropout(0.1) mask (networks.py:636,643); the engine replays the SAME masks in its reverse sweep.  The unroll
+    engine normally draws them itself (``unrolled_match(dropout_p=..., rng_state=...)``); this is the stand-alone form.
     """
     N, B, K, dt, d = workspace.key
     if workspace.masks is None:
         workspace.masks = torch.empty(max(K, 1), B, d, dtype=torch.float32, device=workspace.buf.device)
-    workspace.masks.bernoulli_(1.0 - p, generator=generator).mul_(1.0 / (1.0 - p))
-    return workspace.masks
+    return dropout_masks(None, p, rng_state, advance=True, out=workspace.masks)
+
+
+def make_rng_state(seed: int, device) -> torch.Tensor:
+    """{seed, draws so far} of the engine's Philox generator as two uint64 in device memory (viewed as int64 by torch)."""
+    return torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+
+
+def dropout_masks(shape, p: float, rng_state: torch.Tensor, advance: bool = True, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Pre-scaled dropout masks (0 or 1/(1-p)) from the engine's own generator (vldd_dropout_masks)."""
+    st = _req(rng_state, "rng_state", torch.int64)
+    out = torch.empty(shape, dtype=torch.float32, device=st.device) if out is None else _req(out, "out")
+    check(lib().vldd_dropout_masks(_ptr(out), out.numel(), float(p), _ptr(st), int(bool(advance)), _stream()), "dropout_masks")
+    return out
+
+
+def outer_update(U, gU, bufU, lr_img: float, Y, gY, bufY, lr_txt: float, syn_lr_img, syn_lr_txt, g_lr_img, g_lr_txt, buf_lr,
+                 lr_lr: float, momentum: float, first: bool, grad_scale: float = 1.0, loss=None, skipped=None) -> None:
+    """The three SGD(momentum) steps of one outer iteration in one launch (distill.py:233-241, 603-613), in place.
+
+    syn_lr_img / syn_lr_txt: one-element device tensors updated through buf_lr[0] / buf_lr[1]; g_lr_img may be None (the
+    logit scale is not tied to syn_lr_img: distill_original.py:430).  A non-finite `loss` skips the update and sets `skipped`.
+    """
+    for t, n in ((U, "U"), (gU, "gU"), (bufU, "bufU"), (Y, "Y"), (gY, "gY"), (bufY, "bufY"), (buf_lr, "buf_lr")):
+        _req(t, n)
+        if not t.is_contiguous():
+            raise ValueError(f"{n} must be contiguous for the in-place update")
+    check(lib().vldd_outer_update(_ptr(U), _ptr(gU), _ptr(bufU), U.numel(), float(lr_img), _ptr(Y), _ptr(gY), _ptr(bufY),
+                                  Y.numel(), float(lr_txt), _ptr(syn_lr_img), _ptr(syn_lr_txt), _ptr(g_lr_img), _ptr(g_lr_txt),
+                                  _ptr(buf_lr), float(lr_lr), float(momentum), int(bool(first)), float(grad_scale), _ptr(loss),
+                                  _ptr(skipped), _stream()), "outer_update")
 
 
 def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, workspace: UnrollWorkspace | None = None,
-                   want_theta_K: bool = False):
-    """distill.py:509-606 for one expert segment.  Returns dict(out5=[num,den,loss,dlr,dscale], ce, dY, dU[, theta_K])."""
+                   want_theta_K: bool = False, dropout_p: float = 0.0, rng_state: torch.Tensor | None = None,
+                   clone_results: bool = True):
+    """distill.py:509-606 for one expert segment.  Returns dict(out5=[num,den,loss,dlr,dscale], ce, dY, dU[, theta_K]).
+
+    dropout_p > 0 with an `rng_state` (make_rng_state): the engine draws fresh masks itself inside its launch graph
+    (train-mode students, distill.py:446-447); they can be read back from ``workspace.masks``.  `masks` given: used as is.
+    clone_results=False returns views of the workspace's result buffers (valid until the next call on that workspace)
+    and reads one-element device tensors `lr` / `scale` in place: no torch kernel is launched for the call.
+    """
     theta0, theta_tgt = _req(_flat(theta0), "theta0"), _req(_flat(theta_tgt), "theta_tgt")
     Y, U = _req(Y, "Y"), _req(U, "U")
     perms = _req(perms, "perms", torch.int64)
@@ -423,12 +466,25 @@ def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, worksp
     if workspace is None or workspace.key != (N, B, K, dt, d):
         workspace = UnrollWorkspace(N, B, K, dt, d, dev)
     ws = workspace
-    ws.lr.copy_(_scalar(lr, dev, "lr"))
-    ws.scale.copy_(_scalar(scale, dev, "scale"))
-    if K > 0:
-        ws.perms.copy_(perms)
+    lr_t, sc_t = _scalar(lr, dev, "lr"), _scalar(scale, dev, "scale")
+    if clone_results:                       # general API: private copies, so the caller may change lr / scale afterwards
+        ws.lr.copy_(lr_t)
+        ws.scale.copy_(sc_t)
+        lr_t, sc_t = ws.lr, ws.scale
+    if K > 0 and perms.data_ptr() != ws.perms.data_ptr():
+        ws.perms.copy_(perms, non_blocking=True)
     m_ptr = None
-    if masks is not None:
+    rng = None
+    if dropout_p > 0.0 and K > 0:
+        if masks is not None:
+            raise ValueError("give either explicit masks or dropout_p, not both")
+        if rng_state is None:
+            raise ValueError("dropout_p > 0 needs an rng_state (ops.make_rng_state)")
+        rng = _req(rng_state, "rng_state", torch.int64)
+        if ws.masks is None:
+            ws.masks = torch.empty(K, B, d, dtype=torch.float32, device=dev)
+        m_ptr = ws.masks
+    elif masks is not None:
         masks = _req(masks, "masks")
         if tuple(masks.shape) != (K, B, d):
             raise ValueError(f"masks must be [{K},{B},{d}]")
@@ -440,9 +496,15 @@ def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, worksp
     if want_theta_K and ws.theta_K is None:
         ws.theta_K = torch.empty_like(theta0)
     thK = ws.theta_K if want_theta_K else None
-    check(lib().vldd_unrolled_match(_ptr(theta0), _ptr(theta_tgt), _ptr(Y), _ptr(U), _ptr(ws.lr), _ptr(ws.scale),
-                                    _ptr(ws.perms), _ptr(m_ptr), N, B, K, dt, d, _ptr(ws.out5), _ptr(ws.ce), _ptr(ws.dY),
-                                    _ptr(ws.dU), _ptr(thK), _ptr(ws.buf), ws.buf.numel(), _stream()), "unrolled_match")
+    check(lib().vldd_unrolled_match(_ptr(theta0), _ptr(theta_tgt), _ptr(Y), _ptr(U), _ptr(lr_t), _ptr(sc_t),
+                                    _ptr(ws.perms), _ptr(m_ptr), float(dropout_p if rng is not None else 0.0), _ptr(rng),
+                                    N, B, K, dt, d, _ptr(ws.out5), _ptr(ws.ce), _ptr(ws.dY), _ptr(ws.dU), _ptr(thK),
+                                    _ptr(ws.buf), ws.buf.numel(), _stream()), "unrolled_match")
+    if not clone_results:
+        res = dict(out5=ws.out5, ce=ws.ce[:K], dY=ws.dY, dU=ws.dU, workspace=ws)
+        if want_theta_K:
+            res["theta_K"] = thK
+        return res
     # results are copied out of the persistent buffers (1.2 MB at Flickr shape) so that they survive the next call
     res = dict(out5=ws.out5.clone(), ce=ws.ce[:K].clone(), dY=ws.dY.clone(), dU=ws.dU.clone(), workspace=ws)
     if want_theta_K:

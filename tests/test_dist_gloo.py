@@ -128,15 +128,29 @@ def test_merge_candidates_tie_rule():
     assert bs.tolist()[:2] == [1.0, 7.0] and bi.tolist() == [2, 8, -1, 3]
 
 
-def test_distill_segments_sum_equals_allreduce():
-    """G ranks x 1 segment + all-reduce(SUM) == one process looping the same G segments and summing (oracle, fp64)."""
-    from oracle import distill_ref as R
-    prs = [R.make_problem(N=10, B=10, K=2, dt=6, d=8, seed=s, dtype=torch.float64, lr=0.3, scale=2.0, tgt_eps=0.05) for s in (0, 1)]
-    for p in prs[1:]:
-        p["Y"], p["U"] = prs[0]["Y"], prs[0]["U"]          # same replicated synthetic set, different expert segments
-    outs = [R.unrolled_match_manual(**p) for p in prs]
-    total = sum(o.dY for o in outs)
-    packed = [torch.cat([o.dU.reshape(-1), o.dY.reshape(-1), torch.stack([o.dscale, o.dlr])]) for o in outs]
-    summed = packed[0] + packed[1]
-    n_u = outs[0].dU.numel()
-    assert torch.allclose(summed[n_u:n_u + total.numel()].view_as(total), total)
+def test_ranks_sample_disjoint_segments_and_different_minibatches():
+    """distill.main under torchrun: rank r starts at expert r and strides by the world size, and draws its own minibatch
+    permutations and start epochs; the same (seed, rank) reproduces.  (The collective itself is driven with the real
+    engine in tests/test_gpu_dist_engine.py; this is the host-side sampling state only, no device needed.)"""
+    import types
+    from multimodal_dataset_distillation_b200 import distill
+
+    def sampler(rank, world, seed=3, n_experts=8):
+        e = object.__new__(distill.DistillEngine)
+        e.args = types.SimpleNamespace(max_start_epoch=4, expert_epochs=1)
+        e.experts = torch.empty(n_experts, 6, 1)
+        e.N, e.B, e.K = 20, 12, 3
+        e._init_sampling(seed, rank, world, n_experts)
+        return e
+
+    a, b, a2 = sampler(0, 2), sampler(1, 2), sampler(0, 2)
+    sa = [a.sample_segment() for _ in range(6)]
+    sb = [b.sample_segment() for _ in range(6)]
+    assert [e for e, _ in sa] == [0, 2, 4, 6, 0, 2] and [e for e, _ in sb] == [1, 3, 5, 7, 1, 3]
+    assert all(0 <= s < 4 for _, s in sa + sb) and [s for _, s in sa] != [s for _, s in sb]
+    pa, pb = a.draw_perms(), b.draw_perms()
+    assert tuple(pa.shape) == (3, 12) and not torch.equal(pa, pb)
+    assert all(len(set(row.tolist())) == 12 for row in pa)                  # randperm(N)[:B]: unique indices per step
+    assert [a2.sample_segment() for _ in range(6)] == sa and torch.equal(a2.draw_perms(), pa)
+    one = sampler(0, 1)
+    assert [one.sample_segment()[0] for _ in range(4)] == [0, 1, 2, 3]      # world 1: the reference's in-order walk
