@@ -228,19 +228,20 @@ def bench_streaming_kernels(dev, experts):
         res[name] = {"avg_launch_us": us, "algorithmic_bytes_per_launch": nbytes, "bytes_per_element": per_elem,
                      "achieved_gbs": gbs, "frac": gbs / pk["hbm"], "reference_site": site}
 
+    # operand sets are disjoint from launch to launch: a buffer comes back only after > 300 MB of other traffic (L2 = 126 MB)
     lr = torch.full((1,), 0.1, device=dev)
-    us = _time_rotating(lambda i: check(lib().vldd_flat_sgd_step(ptr(flat[i % S]), ptr(flat[(i + 1) % S]), ptr(lr), ptr(outs[i % 6]), P, st()), "sgd"), 12)
+    us = _time_rotating(lambda i: check(lib().vldd_flat_sgd_step(ptr(flat[(2 * i) % S]), ptr(flat[(2 * i + 1) % S]), ptr(lr), ptr(outs[i % 6]), P, st()), "sgd"), 6)
     entry("flat_sgd_step", us, 12 * P, 12, "distill.py:582-583")
     out3 = torch.empty(3, device=dev)
     scratch = torch.zeros(lib().vldd_match_loss_scratch_bytes(), dtype=torch.uint8, device=dev)
-    us = _time_rotating(lambda i: check(lib().vldd_match_loss_fwd(ptr(flat[i % S]), ptr(flat[(i + 1) % S]), ptr(flat[(i + 2) % S]), P, ptr(out3), ptr(scratch), st()), "ml"), 12)
-    entry("match_loss_fwd", us, 12 * P, 12, "distill.py:588-598")
-    us = _time_rotating(lambda i: check(lib().vldd_match_loss_bwd(ptr(flat[i % S]), ptr(flat[(i + 1) % S]), ptr(out3), None, ptr(outs[i % 6]), P, st()), "mlb"), 12)
-    entry("match_loss_bwd", us, 12 * P, 12, "distill.py:606 (d/d theta_K of the ratio)")
-    if hasattr(lib(), "vldd_match_final"):
-        den = torch.ones(1, device=dev)
-        us = _time_rotating(lambda i: check(lib().vldd_match_final(ptr(flat[i % S]), ptr(flat[(i + 1) % S]), ptr(den), P, ptr(out3), ptr(outs[i % 6]), ptr(scratch), st()), "mlf"), 12)
-        entry("match_final (num + adjoint in one pass)", us, 12 * P, 12, "distill.py:588-598 + 606")
+    us = _time_rotating(lambda i: check(lib().vldd_match_loss_fwd(ptr(flat[(3 * i) % S]), ptr(flat[(3 * i + 1) % S]), ptr(flat[(3 * i + 2) % S]), P, ptr(out3), ptr(scratch), st()), "ml"), 4)
+    entry("match_loss_fwd", us, 12 * P, 12, "distill.py:588-598 (stand-alone form: 3 reads, ticketed finish inside the kernel)")
+    us = _time_rotating(lambda i: check(lib().vldd_match_loss_bwd(ptr(flat[(2 * i) % S]), ptr(flat[(2 * i + 1) % S]), ptr(out3), None, ptr(outs[i % 6]), P, st()), "mlb"), 6)
+    entry("match_loss_bwd", us, 12 * P, 12, "distill.py:606 (d/d theta_K of the ratio; stand-alone form)")
+    den = torch.ones(1, device=dev)
+    us = _time_rotating(lambda i: check(lib().vldd_match_final(ptr(flat[(2 * i) % S]), ptr(flat[(2 * i + 1) % S]), ptr(den), P, None, ptr(outs[i % 6]), ptr(scratch), st()), "mlf"), 6)
+    entry("match_final_pass", us, 12 * P, 12, "distill.py:588-598 + 606: what the engine runs -- numerator partials + adjoint in one pass "
+          "(2 reads + 1 write); the denominator comes from the staging pass, the partials are added by the call's last kernel")
     us = _time_rotating(lambda i: check(lib().vldd_momentum_sgd(ptr(outs[i % 6]), ptr(flat[i % S]), ptr(bufs[i % 6]), 1e-9, 0.5, 0, P, st()), "mom"), 12)
     entry("momentum_sgd", us, 20 * P, 20, "distill.py:233-241, 611-613")
     # rank kernels on a score matrix larger than L2 (COCO eval shape: 5000 x 25000 fp32 = 500 MB, read once per direction)
@@ -470,6 +471,14 @@ def run_ours(opt):
         copied = None if bytes0 is None else (pre.h2d_bytes - bytes0) / opt.steps
         return world * opt.steps / float(te), copied
 
+    if opt.profile:
+        clk.__exit__(None, None, None)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": opt.steps, "warmup": opt.warmup,
+                "ms_per_step": ms_per_step, "gpu_launches": gpu_launches, "clocks": clk.summary(),
+                "profile_only": "--profile: the other legs of the bench line were skipped"} if rank == 0 else None
     e2e_value, _ = run_e2e(distill.SegmentPrefetcher(experts_host, dev))
     e2e_cached, cached_bytes = run_e2e(distill.SegmentCache(experts_host, dev, capacity=16))
     clk.__exit__(None, None, None)
@@ -670,11 +679,24 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile", action="store_true",
+                    help="developer aid for ncu: only the device-resident distill loop (value / ms_per_step / gpu_launches), none "
+                         "of the other legs (end to end, per-kernel, retrieval, baselines); the JSON line says so")
     opt = ap.parse_args()
     opt.warmup = max(opt.warmup, 3) if opt.impl == "ours" else opt.warmup
-    out = run_reference(opt) if opt.impl == "reference" else run_ours(opt)
+    # stdout must carry exactly ONE JSON line: libraries write banners to file descriptor 1 behind Python's back (NCCL prints
+    # "NCCL version ..." when its first communicator comes up), so everything but the final line goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = run_reference(opt) if opt.impl == "reference" else run_ours(opt)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

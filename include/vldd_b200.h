@@ -175,7 +175,9 @@ int vldd_unrolled_match(const float* theta0, const float* theta_tgt, const float
 /* Numerator and adjoint of the matching loss in one pass (distill.py:588-598 + the first step of 606):
  *   out3 = {num = |theta_K - theta_tgt|^2, *den, num / *den};  adjoint = 2 (theta_K - theta_tgt) / *den.
  * `den` = |theta_0 - theta_tgt|^2 is a device scalar computed beforehand (the engine accumulates it while it stages the
- * segment).  12 B / parameter; scratch as for vldd_match_loss_fwd (ticket word zero before the first use). */
+ * segment).  12 B / parameter; scratch: vldd_match_loss_scratch_bytes().  Two launches: the streaming pass (adjoint + fp64
+ * block partials of the numerator) and a one-block finish that adds the partials in index order; out3 == NULL skips the
+ * finish (the unroll engine folds it into the last kernel of its launch graph instead). */
 int vldd_match_final(const float* theta_K, const float* theta_tgt, const float* den, int64_t n, float* out3, float* adjoint,
                      void* scratch, void* stream);
 

@@ -331,9 +331,10 @@ int vldd_unrolled_match(const float* theta0, const float* theta_tgt, const float
 
 int vldd_match_final(const float* theta_K, const float* theta_tgt, const float* den, int64_t n, float* out3, float* adjoint,
                      void* scratch, void* stream) {
-  VLDD_REQUIRE(n > 0 && theta_K && theta_tgt && den && out3 && adjoint && scratch, "match_final: null pointer or n <= 0");
+  VLDD_REQUIRE(n > 0 && theta_K && theta_tgt && den && adjoint && scratch, "match_final: null pointer or n <= 0");
   const int rc = match_final_pass(theta_K, theta_tgt, den, n, adjoint, scratch, S(stream));
-  return rc ? rc : match_final_finish(den, n, out3, scratch, S(stream));
+  if (rc || out3 == nullptr) return rc;         // out3 == NULL: the streaming pass alone (block partials stay in `scratch`)
+  return match_final_finish(den, n, out3, scratch, S(stream));
 }
 
 int vldd_outer_update(float* U, const float* gU, float* bufU, int64_t nU, float lr_img, float* Y, const float* gY, float* bufY,

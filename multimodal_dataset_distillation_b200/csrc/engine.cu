@@ -538,10 +538,9 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   CHECK_RC(lanes_join(L));
   const float* thK = w.traj + (size_t)K * m.P;
   // numerator + adjoint a_K = 2 (theta_K - theta*) / den in one pass (den was accumulated while the segment was staged)
+  // (the pass leaves fp64 block partials of the numerator; nothing in the reverse sweep reads it, so the call's last kernel
+  //  -- finalize_kernel below -- adds them up together with the index check: no serial tail in the streaming pass)
   CHECK_RC(match_final_pass(thK, w.tgt, w.den, m.P, w.adj0, w.ml_scratch, st));
-  CHECK_RC(lane_edge(st, L.s2));                 // the finish (block partials -> out5[0..2]) rides on a side branch: nothing
-  L.s2_busy = true;                              // in the reverse sweep reads the numerator
-  CHECK_RC(match_final_finish(w.den, m.P, out5, w.ml_scratch, L.s2));
   MARK("match_final");
   if (theta_K) VLDD_CUDA(cudaMemcpyAsync(theta_K, thK, m.P * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // reverse sweep
@@ -553,10 +552,10 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
                           perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L));
     float* t = a_cur; a_cur = a_nxt; a_nxt = t;
   }
-  CHECK_RC(lanes_join(L));            // K == 0: no reverse step has joined the matching-loss finish yet
   launch_k(row_normalise_bwd_kernel, N, 256, 0, st, w.Xn, w.un, w.dXn, nullptr, d, dU);
   MARK("row_normalise_bwd");
-  if (K > 0) launch_k(poison_kernel, 1, 32, 0, st, (const int*)w.bad_index, out5);
+  launch_k(finalize_kernel, 1, 256, 0, st, match_final_parts(w.ml_scratch), match_final_n_parts(m.P), (const float*)w.den,
+           (const int*)w.bad_index, out5);
   prof_report();
   return check_launch("unrolled_match");
 }

@@ -244,7 +244,12 @@ __global__ void __launch_bounds__(256) gather_all_kernel(const float* __restrict
 }
 
 // dst[idx[b],:] += coef * sum_slabs(part)[b,:]   with coef = -(*lr) * (scale ? *scale : 1)
-// (indices inside one step are unique -- randperm -- so no atomics are needed)
+// The reference's minibatch indices are unique within a step (randperm, distill.py:510-511), but the C ABI takes arbitrary
+// caller permutations: the accumulation is a 128-bit reduction at the L2 (red.global.add.v4.f32), so duplicate rows add up
+// correctly instead of racing.  With unique indices every element receives one add per step: bit-reproducible as before.
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ part, int splits, size_t stride,
                                                                const int64_t* __restrict__ idx, int cols,
                                                                const float* __restrict__ lr,
@@ -257,19 +262,31 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
       ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
     for (int j = threadIdx.x; j < (cols >> 2); j += blockDim.x) {
       const float4 v = sum_slabs4(part, splits, stride, s + 4 * j);
-      float4 o = *reinterpret_cast<float4*>(dst + t + 4 * j);
-      o.x += coef * v.x; o.y += coef * v.y; o.z += coef * v.z; o.w += coef * v.w;
-      *reinterpret_cast<float4*>(dst + t + 4 * j) = o;
+      red_add4(dst + t + 4 * j, make_float4(coef * v.x, coef * v.y, coef * v.z, coef * v.w));
     }
   } else {
-    for (int j = threadIdx.x; j < cols; j += blockDim.x) dst[t + j] += coef * sum_slabs(part, splits, stride, s + j);
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) atomicAdd(dst + t + j, coef * sum_slabs(part, splits, stride, s + j));
   }
 }
 
-// out5[0..4] := NaN when an index was out of range (see checked_row); one thread, end of the call
-__global__ void poison_kernel(const int* __restrict__ bad_index, float* __restrict__ out5) {
+// Last kernel of the call: out5[0..2] = {num, den, num / den} from the fp64 block partials the matching-loss pass left
+// (added in index order: deterministic), then out5[0..4] := NaN when a minibatch index was out of range (see checked_row).
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ parts, int n_parts, const float* __restrict__ den_p,
+                                                       const int* __restrict__ bad_index, float* __restrict__ out5) {
   pdl_enter();
-  if (threadIdx.x < 5 && *bad_index != 0) out5[threadIdx.x] = __int_as_float(0x7fc00000);
+  __shared__ double scratch[34];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n_parts; i += blockDim.x) s += parts[i];
+  s = block_sum<double>(s, scratch);
+  const bool bad = bad_index != nullptr && *bad_index != 0;
+  if (threadIdx.x == 0) {
+    const float den = *den_p;
+    out5[0] = (float)s;
+    out5[1] = den;
+    out5[2] = (float)(s / (double)den);
+  }
+  __syncthreads();
+  if (threadIdx.x < 5 && bad) out5[threadIdx.x] = __int_as_float(0x7fc00000);
 }
 
 // ------------------------------------------------------------------------------------------------

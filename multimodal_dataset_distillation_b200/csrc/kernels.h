@@ -19,6 +19,8 @@ int stage_segment(const float* th0_src, const float* tgt_src, float* th0_dst, fl
                   void* scratch, cudaStream_t st);
 int match_final_pass(const float* thK, const float* tgt, const float* den, int64_t n, float* a, void* scratch, cudaStream_t st);
 int match_final_finish(const float* den, int64_t n, float* out3, void* scratch, cudaStream_t finish_st);
+const double* match_final_parts(const void* scratch);   // block partials left by match_final_pass ...
+int match_final_n_parts(int64_t n);                     // ... and how many there are
 int outer_update(float* U, const float* gU, float* bufU, int64_t nU, float lrU, float* Y, const float* gY, float* bufY,
                  int64_t nY, float lrY, float* syn_lr_img, float* syn_lr_txt, const float* g_lr_img, const float* g_lr_txt,
                  float* buf_lr, float lr_lr, float momentum, int first, float gscale, const float* loss, int* skipped,

@@ -257,15 +257,15 @@ __global__ void __launch_bounds__(kStreamThreads) match_final_kernel(const float
       const float4 d1 = make_float4(x1.x - t1.x, x1.y - t1.y, x1.z - t1.z, x1.w - t1.w);
       num = fmaf(d0.x, d0.x, num); num = fmaf(d0.y, d0.y, num); num = fmaf(d0.z, d0.z, num); num = fmaf(d0.w, d0.w, num);
       num = fmaf(d1.x, d1.x, num); num = fmaf(d1.y, d1.y, num); num = fmaf(d1.z, d1.z, num); num = fmaf(d1.w, d1.w, num);
-      // the adjoint is read again at once by the first reverse step: leave it in L2 (plain store, no streaming hint)
-      *reinterpret_cast<float4*>(a + 4 * i) = make_float4(c * d0.x, c * d0.y, c * d0.z, c * d0.w);
-      *reinterpret_cast<float4*>(a + 4 * (i + stride)) = make_float4(c * d1.x, c * d1.y, c * d1.z, c * d1.w);
+      // (L1::no_allocate store: +4 % in dev/stream_bench_test; the line still lands in L2, where the first reverse step finds it)
+      stg_stream4(a + 4 * i, make_float4(c * d0.x, c * d0.y, c * d0.z, c * d0.w));
+      stg_stream4(a + 4 * (i + stride), make_float4(c * d1.x, c * d1.y, c * d1.z, c * d1.w));
     }
     for (; i < n4; i += stride) {
       const float4 x0 = ldg_stream4(thK + 4 * i), t0 = ldg_stream4(tgt + 4 * i);
       const float4 d0 = make_float4(x0.x - t0.x, x0.y - t0.y, x0.z - t0.z, x0.w - t0.w);
       num = fmaf(d0.x, d0.x, num); num = fmaf(d0.y, d0.y, num); num = fmaf(d0.z, d0.z, num); num = fmaf(d0.w, d0.w, num);
-      *reinterpret_cast<float4*>(a + 4 * i) = make_float4(c * d0.x, c * d0.y, c * d0.z, c * d0.w);
+      stg_stream4(a + 4 * i, make_float4(c * d0.x, c * d0.y, c * d0.z, c * d0.w));
     }
     for (int64_t j = (n4 << 2) + tid; j < n; j += stride) {
       const float d = thK[j] - tgt[j];
@@ -426,6 +426,8 @@ int match_final_pass(const float* thK, const float* tgt, const float* den, int64
   launch_k(match_final_kernel, stream_grid(n / 8 + 1), kStreamThreads, 0, st, thK, tgt, den, n, vec, parts, a);
   return check_launch("match_final_pass");
 }
+const double* match_final_parts(const void* scratch) { return reinterpret_cast<const double*>(reinterpret_cast<const char*>(scratch) + 16); }
+int match_final_n_parts(int64_t n) { return stream_grid(n / 8 + 1); }
 int match_final_finish(const float* den, int64_t n, float* out3, void* scratch, cudaStream_t finish_st) {
   const double* parts = reinterpret_cast<const double*>(reinterpret_cast<char*>(scratch) + 16);
   launch_k(match_finish_kernel, 1, 256, 0, finish_st, parts, stream_grid(n / 8 + 1), den, out3);
