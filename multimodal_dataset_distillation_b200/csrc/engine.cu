@@ -14,6 +14,7 @@
 #include "gemm_dispatch.cuh"
 #include "head_kernels.cuh"
 #include "nce_cluster.cuh"
+#include "nce_fused.cuh"
 #include "row_kernels_v4.cuh"
 #include "kernels.h"
 #include "engine.h"
@@ -24,6 +25,8 @@
 namespace vldd {
 
 namespace {
+
+constexpr int kMaxDevicesNce = 64;
 
 struct Dims {
   int N, B, K, dt, d, Bp;   // Bp: leading dimension of the B x B matrices (multiple of 32 for the MN-major tensor maps)
@@ -46,7 +49,7 @@ Dims make_dims(int N, int B, int K, int dt, int d) {
 struct Saved {  // activations of one forward step, all fp32
   float *Yb, *Xb, *p, *h, *rhat, *yn, *dyn, *dz, *dr, *df, *dh, *dp;  // [B,dt] [B,d] then [B,d] x10
   float *rstd, *nz, *q, *lse_r, *lse_c;                               // [B]
-  float *S, *G;                                                       // [B,B]
+  float *S, *G, *Pr, *Pc;                                             // [B,B] (Pr, Pc: row / column softmax, small-batch path)
 };
 
 struct Bump {
@@ -100,7 +103,7 @@ void carve(Work& w, const Dims& m, void* base) {
     s.Xb = b.f(Bd); s.p = b.f(Bd); s.h = b.f(Bd); s.rhat = b.f(Bd); s.yn = b.f(Bd); s.dyn = b.f(Bd);
     s.dz = b.f(Bd); s.dr = b.f(Bd); s.df = b.f(Bd); s.dh = b.f(Bd); s.dp = b.f(Bd);
     s.rstd = b.f(m.B); s.nz = b.f(m.B); s.q = b.f(m.B); s.lse_r = b.f(m.B); s.lse_c = b.f(m.B);
-    s.S = b.f(BB); s.G = b.f(BB);
+    s.S = b.f(BB); s.G = b.f(BB); s.Pr = b.f(BB); s.Pc = b.f(BB);
   }
   const size_t pf = partial_floats(m);
   w.pa = b.f(pf > Bpd ? pf : Bpd);
@@ -194,6 +197,36 @@ bool nce_fused(int B, int ld) {
     }
   }
   return mode == 1 && nce_cluster_ok(B, ld);
+}
+
+// The two-kernel CUDA-core InfoNCE block (nce_fused.cuh: exact-fp32 logits without split-K slabs, then one kernel that
+// derives the softmax statistics in every CTA and produces G^T X from shared memory) is OPT-IN, VLDD_NCE=fused, for batches
+// of up to ~120 pairs.  Measured on B200 at the Flickr shape (bench.py, ms / iteration): tensor-core GEMMs + row / column
+// kernels 1.694, fused block 1.892 (first version with per-thread load loops: 2.19).  The five launches it replaces cost
+// 3-5 us each; the replacement's phases (bulk load, row pass, column pass, G, G^T X) are dependent stages of ~2-6 us
+// INSIDE one CTA at 4 warps per scheduler (csrc/dev/nce_fused_test.cu prints the phase times): 22 us against ~20 us.
+// On this chain a launch boundary (~1 us with programmatic dependent launch) is cheaper than a block-wide dependent phase.
+bool nce_small(int B, int d, int ld, const void* a, const void* b, const void* c) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("VLDD_NCE");
+    mode = (e && strcmp(e, "fused") == 0) ? 1 : 0;
+  }
+  if (mode != 1 || !nce_small_ok(B, d, ld, a, b, c)) return false;
+  static bool configured[kMaxDevicesNce] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevicesNce) return false;
+  if (!configured[dev]) {
+    const int cap = 224 * 1024;            // three B x B matrices + operand blocks: 141 KB at B = 100, 216 KB at B = 124
+    if (cudaFuncSetAttribute(small_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap) != cudaSuccess ||
+        cudaFuncSetAttribute(nce_gx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap) != cudaSuccess ||
+        cudaFuncSetAttribute(nce_t_gx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured[dev] = true;
+  }
+  return true;
 }
 
 // VLDD_PROFILE=1: serialise everything on one stream and time every launch with events (developer aid; prints a
@@ -322,7 +355,15 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
     launch_k(ln_fwd_kernel, B, 256, d * sizeof(float), st, w.pa, sp, Bd, b2, mask, s.p, gam, bet, d, s.rhat, nullptr, s.yn,
                                                      s.rstd, s.nz);
   prof_mark("ln_fwd_kernel", st);
-  // S = scale * Xb Yn^T ; lse ; G ; loss
+  // S = scale * Xb Yn^T ; lse ; G ; loss ; dyn_raw[j,:] = sum_i G[i,j] Xb[i,:]
+  if (nce_small(B, d, Bp, s.Xb, s.yn, w.pb)) {
+    launch_k(small_scores_kernel, dim3(ceil_div(B, kScoresTJ), ceil_div(B, kScoresTI)), kScoresThreads, scores_smem_bytes(d), st, (const float*)s.Xb, (const float*)s.yn, B, d, scale,
+             s.S, Bp);
+    prof_mark("small_scores_kernel", st);
+    launch_k(nce_gx_kernel, ceil_div(d, kNceGxCols), kNceGxThreads, nce_gx_smem_bytes(B, Bp), st, (const float*)s.S,
+             (const float*)s.Xb, B, Bp, d, s.lse_r, s.lse_c, s.G, s.Pr, s.Pc, ce_out, w.pb);
+    prof_mark("nce_gx_kernel", st);
+  } else {
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, s.yn, d, B, B, d), w.pa, &sp, st, kOldA)));
   prof_mark("gemm_partial<true,true> A=s.Xb", st);
   if (nce_fused(B, Bp)) {
@@ -341,6 +382,7 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   // (G is stored with leading dimension Bp and zero padding columns: rows B..Bp-1 of the product are zeros)
   CHECK_RC((gemm_store<false, false>(gemm_ops(s.G, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st, kOldB)));
   prof_mark("gemm_store<false,false> A=s.G", st);
+  }
   if (row_v4_ok(d))
     VLDD_ROW_V4_DISPATCH(d, norm_ln_bwd_v4_kernel, (B, 256, 0, st), (w.pb, scale, s.yn, s.nz, s.rhat, s.rstd, gam, mask, d,
                                                                         s.dyn, s.q, s.dz, s.dr, s.df));
@@ -405,10 +447,20 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
     launch_k(ln_tangent_kernel, B, 256, d * sizeof(float), st, w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz, gam,
                                                          gamd, betd, d, w.rhatd, w.ynd, w.t, w.nzd);
   prof_mark("ln_tangent_kernel", st);
-  // Sd = scale Xb Ynd^T ; rho, kappa, Gd ; L_dot ; dlr, dscale
+  // Sd = scale Xb Ynd^T ; rho, kappa, Gd ; L_dot ; dlr, dscale ; dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
+  const bool small = nce_small(B, d, Bp, s.Xb, w.ynd, w.pb);
+  const bool fused_nce = !small && nce_fused(B, Bp);
+  if (small) {
+    launch_k(small_scores_kernel, dim3(ceil_div(B, kScoresTJ), ceil_div(B, kScoresTI)), kScoresThreads, scores_smem_bytes(d), st, (const float*)s.Xb, (const float*)w.ynd, B, d, scale,
+             w.Sd, Bp);
+    prof_mark("small_scores_kernel", st);
+    launch_k(nce_t_gx_kernel, ceil_div(d, kNceGxCols), kNceGxThreads, nce_gx_smem_bytes(B, Bp), st, (const float*)s.S,
+             (const float*)w.Sd, (const float*)s.Pr, (const float*)s.Pc, (const float*)s.Xb, B, Bp, d, lr, scale, w.Gd, dlr,
+             dscale, w.pb);
+    prof_mark("nce_t_gx_kernel", st);
+  } else {
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Xb, d, w.ynd, d, B, B, d), w.pa, &sp, st, kOldA)));
   prof_mark("gemm_partial<true,true> A=s.Xb", st);
-  const bool fused_nce = nce_fused(B, Bp);
   if (fused_nce) {
     launch_cluster_k(nce_t_cluster_kernel, kNceCluster, kNceThreads, nce_cluster_smem_bytes(B, Bp), st, w.pa, sp,
                      (size_t)B * B, scale, s.S, s.lse_r, s.lse_c, s.G, B, Bp, w.Gd, lr, dlr, dscale);
@@ -422,6 +474,7 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
     launch_k(nce_t_grad_kernel, B, 128, 0, st, s.S, s.lse_r, s.lse_c, w.Sd, w.rho, w.kap, B, Bp, w.Gd, w.rowB);
     prof_mark("nce_t_grad_kernel", st);
   }
+  }
   // branch 1: dXn_dot = scale (Gd Yn + G Ynd)  ->  dXn[perm] -= lr * scale * raw
   CHECK_RC(lane_edge(st, L.s1));
   L.s1_busy = true;
@@ -429,13 +482,15 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   prof_mark("gemm_store<true,false> A=w.Gd", L.s1);
   launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pc, 1, Bd, perm, d, lr, scale, w.dXn, m.N);
   prof_mark("scatter_add_rows_kernel", L.s1);
-  if (!fused_nce) {        // the dlr / dscale accumulation is off the critical path: side stream, ordered step to step
+  if (!small && !fused_nce) {        // the dlr / dscale accumulation is off the critical path: side stream, ordered step to step
     launch_k(nce_t_finish_kernel, 1, 128, 0, L.s1, w.rowA, w.rowB, B, lr, scale, dlr, dscale);
     prof_mark("nce_t_finish_kernel", L.s1);
   }
-  // dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
-  CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st, kOldB)));
-  prof_mark("gemm_store<false,false> A=w.Gd", st);
+  if (!small) {
+    // dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
+    CHECK_RC((gemm_store<false, false>(gemm_ops(w.Gd, Bp, s.Xb, d, Bp, d, B), w.pb, d, 1.0f, st, kOldB)));
+    prof_mark("gemm_store<false,false> A=w.Gd", st);
+  }
   if (row_v4_ok(d))
     VLDD_ROW_V4_DISPATCH(d, norm_ln_bwd_tangent_v4_kernel, (B, 256, 0, st), (w.pb, scale, s.yn, w.ynd, s.dyn, s.q, s.nz, w.nzd, s.dz, s.rhat, w.rhatd, s.rstd,
                                              w.t, s.dr, gam, gamd, mask, d, w.dzd, w.drd, w.dfd));

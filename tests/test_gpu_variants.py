@@ -1,7 +1,9 @@
 """Alternative code paths of the engine selected by environment variables, each run in a fresh process (the switches are
 read once per process) and compared with the default path and the oracle on the same seeded problem.
 
-  VLDD_NCE=cluster   InfoNCE as one 8-CTA cluster launch (csrc/nce_cluster.cuh) instead of the row / column kernels
+  VLDD_NCE=fused     logits and the InfoNCE block as two CUDA-core kernels (csrc/nce_fused.cuh; measured slower, kept opt-in)
+                     instead of the split-K tensor-core GEMM + row / column softmax kernels + tensor-core G^T X
+  VLDD_NCE=cluster   as rows, with InfoNCE as one 8-CTA cluster launch (csrc/nce_cluster.cuh)
   VLDD_GRAPH=0       plain stream launches instead of CUDA-graph replay
   VLDD_PDL=0         no programmatic dependent launch
 """
@@ -45,10 +47,11 @@ def _close(a, b, rtol):
 def test_engine_variants_agree(tmp_path, N, B, dt, d):
     base = _run(tmp_path, "default", {}, N, B, dt, d)
     # (the GEMM backend switches VLDD_GEMM=simt|tf32 exist only in developer builds, -DVLDD_DEV_GEMM_SWITCH)
-    for tag, env in (("cluster", {"VLDD_NCE": "cluster"}), ("nograph", {"VLDD_GRAPH": "0"}), ("nopdl", {"VLDD_PDL": "0"})):
+    for tag, env in (("fused", {"VLDD_NCE": "fused"}), ("cluster", {"VLDD_NCE": "cluster"}), ("nograph", {"VLDD_GRAPH": "0"}),
+                     ("nopdl", {"VLDD_PDL": "0"})):
         got = _run(tmp_path, tag, env, N, B, dt, d)
-        # scheduling switches do not change arithmetic; the cluster kernel keeps the score bits but sums the softmax
-        # statistics in a different order
+        # scheduling switches do not change arithmetic; the tensor-core logits (3xTF32) differ from the CUDA-core ones (exact
+        # fp32 FMA) in the last bits, and the cluster kernel sums the softmax statistics in yet another order
         exact = tag in ("nograph", "nopdl")
         for k in ("out5", "ce", "dY", "dU"):
             if exact:
