@@ -87,11 +87,17 @@ int vldd_sim_rank(const float* img, const float* txt, int n_img, int n_txt, int 
                   const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx, int32_t* ranks_i2t,
                   int32_t* ranks_t2i, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Same result as vldd_sim_rank without ever writing the score matrix: two passes of the tcgen05 GEMM whose epilogues
- * (1) extract the ground-truth scores from the tiles that contain them and (2) count, per image row and per caption
- * column, the entries ranked ahead of the ground truth.  nnz = img2txt_ptr[n_img] (number of CSR entries).  Requires
- * 16-byte aligned embeddings and dim % 4 == 0 (tensor-map constraints); workspace is O(n_img + n_txt + tiles). */
-size_t vldd_sim_rank_fused_workspace_bytes(int n_img, int n_txt, int nnz);
+/* Same result as vldd_sim_rank without ever writing the score matrix: passes of the tcgen05 GEMM whose epilogues
+ * (1) extract the ground-truth scores from the tiles that contain them (3xTF32) and (2) count, per image row and per
+ * caption column, the entries ranked ahead of the ground truth.  From ~4 M pairs on (and dim % 8 == 0) pass 2 is a
+ * SCREEN: a bf16x3 product (half the tensor time) counts every pair whose distance to its threshold exceeds the proven
+ * error band alpha * eps(dim) * |img_m| * |txt_n|; the pairs inside the band (ties included) are listed, gathered and
+ * decided by the 3xTF32 kernel itself, so the ranks are bit-identical to the materialised path; if the list overflows
+ * (capacity ~ pairs / 2048) the exact count pass runs over everything.  nnz = img2txt_ptr[n_img] (number of CSR
+ * entries).  Requires 16-byte aligned embeddings and dim % 4 == 0 (tensor-map constraints).  Workspace:
+ * O(n_img + n_txt + tiles), plus -- for the screen -- the bf16 hi / lo copies of both embedding sets and the gathered
+ * rows of the listed pairs (<= 2 GB). */
+size_t vldd_sim_rank_fused_workspace_bytes(int n_img, int n_txt, int dim, int nnz);
 int vldd_sim_rank_fused(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale,
                         const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx, int nnz,
                         int32_t* ranks_i2t, int32_t* ranks_t2i, void* workspace, size_t workspace_bytes, void* stream);

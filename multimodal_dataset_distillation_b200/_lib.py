@@ -33,7 +33,7 @@ _SIGS = {
     "vldd_topk_fill": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "vldd_sim_rank_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "vldd_sim_rank": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
-    "vldd_sim_rank_fused_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "vldd_sim_rank_fused_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "vldd_sim_rank_fused": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, C.c_int, _P, _P, _P,
                                       C.c_size_t, _P]),
     "vldd_itm_eval_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),

@@ -174,9 +174,9 @@ int vldd_sim_rank(const float* img, const float* txt, int n_img, int n_txt, int 
   return ranks_cols(s_i2t, n_txt, n_img, n_txt, txt2img, ranks_t2i, S(stream));                   // text -> image: columns
 }
 
-size_t vldd_sim_rank_fused_workspace_bytes(int n_img, int n_txt, int nnz) {
+size_t vldd_sim_rank_fused_workspace_bytes(int n_img, int n_txt, int dim, int nnz) {
   if (n_img <= 0 || n_txt <= 0 || nnz < 0) return 256;
-  return sim_rank_fused_workspace_bytes(n_img, n_txt, nnz);
+  return sim_rank_fused_workspace_bytes(n_img, n_txt, dim, nnz);
 }
 
 int vldd_sim_rank_fused(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale,
@@ -188,8 +188,8 @@ int vldd_sim_rank_fused(const float* img, const float* txt, int n_img, int n_txt
   VLDD_REQUIRE(sim_rank_fused_ok(img, txt, n_img, n_txt, dim),
                "sim_rank_fused: operands do not satisfy the tensor-map constraints (16-byte aligned, dim %% 4 == 0); use "
                "vldd_sim_rank");
-  if (workspace == nullptr || workspace_bytes < vldd_sim_rank_fused_workspace_bytes(n_img, n_txt, nnz)) {
-    set_error("sim_rank_fused: workspace too small (need %zu bytes)", vldd_sim_rank_fused_workspace_bytes(n_img, n_txt, nnz));
+  if (workspace == nullptr || workspace_bytes < vldd_sim_rank_fused_workspace_bytes(n_img, n_txt, dim, nnz)) {
+    set_error("sim_rank_fused: workspace too small (need %zu bytes)", vldd_sim_rank_fused_workspace_bytes(n_img, n_txt, dim, nnz));
     return VLDD_ERR_WORKSPACE;
   }
   return sim_rank_fused(img, txt, n_img, n_txt, dim, scale, txt2img, img2txt_ptr, img2txt_idx, nnz, ranks_i2t, ranks_t2i,

@@ -38,7 +38,7 @@ int count_rows(const float* S, int64_t ld, int nrows, int ncols, int col_offset,
 int recall_counts(const int32_t* ranks, int n, int32_t* counts3, cudaStream_t st);
 int sim_scores(const float* img, const float* txt, int I, int T, int D, float scale, float* S_i2t, float* S_t2i,
                cudaStream_t st);
-size_t sim_rank_fused_workspace_bytes(int I, int T, int nnz);
+size_t sim_rank_fused_workspace_bytes(int I, int T, int D, int nnz);
 bool sim_rank_fused_ok(const float* img, const float* txt, int I, int T, int D);
 int sim_rank_fused(const float* img, const float* txt, int I, int T, int D, float scale, const int32_t* txt2img,
                    const int32_t* gt_ptr, const int32_t* gt_idx, int nnz, int32_t* ranks_i2t, int32_t* ranks_t2i,

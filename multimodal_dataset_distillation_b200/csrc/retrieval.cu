@@ -430,10 +430,139 @@ __global__ void __launch_bounds__(256) rank_finalize_kernel(const int32_t* __res
   if (t < T && col_thr_idx[t] < 0) ranks_t2i[t] = I;
 }
 
-size_t sim_rank_fused_workspace_bytes(int I, int T, int nnz) {
-  const size_t tiles = (size_t)ceil_div(I, tc::BM) * ceil_div(T, 128);
+// ---- screened count pass: bf16x3 screen, exact 3xTF32 decision of the borderline pairs ----------------------------------
+// x = hi + lo + r with hi = bf16(x), lo = bf16(x - hi): |r| <= 2^-18 |x|.  The screen computes sum (hi hi + hi lo + lo hi): it
+// drops lo lo and the r terms (<= 3 * 2^-18 sum |x_k y_k|) and accumulates in the tensor core's truncating fp32 (<= 2^-23 of
+// the running magnitude per MMA: K/16 * 3 MMAs here, K/8 * 3 in the 3xTF32 product it is compared with).  With
+// sum |x_k y_k| <= |x| |y| the two scores of a pair differ by at most  alpha * eps_rel(K) * |x| |y|;  the factor 2 is margin.
+inline float screen_eps_rel(int D) { return 2.0f * (3.0f / 262144.0f + (float)D * (3.0f / 16.0f + 3.0f / 8.0f) / 8388608.0f); }
+
+// (max_norm: one int-punned float per side, atomicMax -- norms are non-negative, so integer order == float order)
+__global__ void __launch_bounds__(256) split_rows_bf16_kernel(const float* __restrict__ x, int D, uint16_t* __restrict__ hi,
+                                                              uint16_t* __restrict__ lo, int* __restrict__ max_norm) {
+  pdl_enter();
+  __shared__ float scratch[34];
+  const size_t base = (size_t)blockIdx.x * D;
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    const float v = x[base + j];
+    const uint32_t u = __float_as_uint(v);
+    const uint32_t hr = (u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u;             // round to nearest even (finite inputs)
+    const float h = __uint_as_float(hr);
+    const float l = v - h;                                                             // exact
+    const uint32_t ul = __float_as_uint(l);
+    const uint32_t lr = (ul + 0x7FFFu + ((ul >> 16) & 1u)) & 0xFFFF0000u;
+    hi[base + j] = (uint16_t)(hr >> 16);
+    lo[base + j] = (uint16_t)(lr >> 16);
+    ss = fmaf(v, v, ss);
+  }
+  ss = block_sum<float>(ss, scratch);
+  if (threadIdx.x == 0) atomicMax(max_norm, __float_as_int(sqrtf(ss) * 1.000001f));
+}
+__global__ void screen_band_kernel(const int* __restrict__ max_norms, float eps_alpha, float* __restrict__ band) {
+  pdl_enter();
+  if (threadIdx.x == 0) *band = eps_alpha * __int_as_float(max_norms[0]) * __int_as_float(max_norms[1]) * 1.000002f;
+}
+// n_pairs = borderline pairs to decide (0 when the list overflowed: the exact pass then recounts everything), the diagonal
+// tiles of the gathered product, and the work count of the exact fall-back pass
+__global__ void __launch_bounds__(256) decide_prepare_kernel(const int32_t* __restrict__ amb_count, int cap, int tiles_n_gather,
+                                                             int exact_tiles, int32_t* __restrict__ n_pairs,
+                                                             int* __restrict__ tile_list, int* __restrict__ tile_count,
+                                                             int* __restrict__ ident_list, int* __restrict__ fb_count) {
+  pdl_enter();
+  const int cnt = *amb_count;
+  const bool overflow = cnt > cap;
+  const int n = overflow ? 0 : cnt;
+  const int nt = (n + 127) / 128;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int i = t; i < nt; i += stride) tile_list[i] = i * (tiles_n_gather + 1);
+  for (int i = t; i < exact_tiles; i += stride) ident_list[i] = i;
+  if (t == 0) { *n_pairs = n; *tile_count = nt; *fb_count = overflow ? exact_tiles : 0; }
+}
+__global__ void __launch_bounds__(256) gather_pairs_kernel(const tc::AmbiguousPair* __restrict__ list, const int32_t* __restrict__ n_pairs,
+                                                           const float* __restrict__ img, const float* __restrict__ txt, int D,
+                                                           float* __restrict__ Ag, float* __restrict__ Bg) {
+  pdl_enter();
+  const int n = *n_pairs;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int p = warp; p < n; p += nwarps) {
+    const tc::AmbiguousPair a = list[p];
+    const float4* si = reinterpret_cast<const float4*>(img + (size_t)a.m * D);
+    const float4* sj = reinterpret_cast<const float4*>(txt + (size_t)a.n * D);
+    float4* di = reinterpret_cast<float4*>(Ag + (size_t)p * D);
+    float4* dj = reinterpret_cast<float4*>(Bg + (size_t)p * D);
+    for (int k = lane; k < (D >> 2); k += 32) { di[k] = si[k]; dj[k] = sj[k]; }
+  }
+}
+// the borderline list overflowed: forget the screen's counts, the exact pass recounts every tile
+__global__ void __launch_bounds__(256) fallback_reset_kernel(const int* __restrict__ fb_count, int I, int T, int32_t* __restrict__ ranks_i2t,
+                                                             int32_t* __restrict__ ranks_t2i) {
+  pdl_enter();
+  if (*fb_count == 0) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int i = t; i < I; i += stride) ranks_i2t[i] = 0;
+  for (int i = t; i < T; i += stride) ranks_t2i[i] = 0;
+}
+
+// borderline-list capacity: pairs / 2048, at least 4096, at most what 2 GB of gathered rows hold (VLDD_SCREEN_CAP: test hook)
+int screen_cap(int I, int T, int D) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("VLDD_SCREEN_CAP"); forced = e ? atoi(e) : 0; }
+  long long cap = forced > 0 ? forced : (long long)I * T / 2048;
+  const long long hi = (1ll << 31) / (8ll * D), top = 1ll << 20;
+  if (forced <= 0 && cap < 4096) cap = 4096;
+  if (cap > hi) cap = hi;
+  if (cap > top) cap = top;
+  if (cap < 128) cap = 128;
+  return (int)((cap + 127) / 128 * 128);
+}
+// the screen pays for its extra launches (two splits, prepare, gather, decide, fall-back) from ~4 M pairs on
+bool screen_wanted(const float* img, const float* txt, int I, int T, int D) {
+  static long long min_pairs = -1;
+  if (min_pairs < 0) { const char* e = getenv("VLDD_SCREEN_MIN_PAIRS"); min_pairs = e ? atoll(e) : 4000000ll; }
+  return D % 8 == 0 && aligned16(img) && aligned16(txt) && (long long)I * T >= min_pairs;
+}
+
+namespace {
+struct FusedWs {
+  float *gt_val, *col_val, *row_thr; int32_t *row_thr_idx, *col_thr_idx; int *flags, *list, *count;
+  // screened pass
+  uint16_t *img_hi, *img_lo, *txt_hi, *txt_lo; int* max_norms; float* band; tc::AmbiguousPair* amb; int32_t *amb_count, *n_pairs;
+  int *tile_list, *tile_count, *ident_list, *fb_count; float *Ag, *Bg;
+  size_t bytes;
+};
+void carve_fused(FusedWs& w, void* base, int I, int T, int D, int nnz, bool screen) {
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-  return al((size_t)nnz * 4 + 4) + al((size_t)T * 4) + al((size_t)I * 4) * 2 + al((size_t)T * 4) + al(tiles * 4) * 2 + 256;
+  char* p = reinterpret_cast<char*>(base);
+  const size_t tiles = (size_t)ceil_div(I, tc::BM) * ceil_div(T, 128);
+  auto take = [&](size_t b) { char* r = p; p += al(b); return r; };
+  w.gt_val = (float*)take((size_t)nnz * 4 + 4);
+  w.col_val = (float*)take((size_t)T * 4);
+  w.row_thr = (float*)take((size_t)I * 4);
+  w.row_thr_idx = (int32_t*)take((size_t)I * 4);
+  w.col_thr_idx = (int32_t*)take((size_t)T * 4);
+  w.flags = (int*)take(tiles * 4);
+  w.list = (int*)take(tiles * 4);
+  w.count = (int*)take(256);
+  if (screen) {
+    const int cap = screen_cap(I, T, D);
+    w.img_hi = (uint16_t*)take((size_t)I * D * 2); w.img_lo = (uint16_t*)take((size_t)I * D * 2);
+    w.txt_hi = (uint16_t*)take((size_t)T * D * 2); w.txt_lo = (uint16_t*)take((size_t)T * D * 2);
+    w.amb = (tc::AmbiguousPair*)take((size_t)cap * sizeof(tc::AmbiguousPair));
+    w.amb_count = (int32_t*)take(256); w.n_pairs = w.amb_count + 1; w.tile_count = (int*)(w.amb_count + 2); w.fb_count = (int*)(w.amb_count + 3);
+    w.max_norms = (int*)(w.amb_count + 4); w.band = (float*)(w.amb_count + 6);
+    w.tile_list = (int*)take((size_t)(cap / 128) * 4);
+    w.ident_list = (int*)take(tiles * 4);
+    w.Ag = (float*)take((size_t)cap * D * 4); w.Bg = (float*)take((size_t)cap * D * 4);
+  }
+  w.bytes = (size_t)(p - reinterpret_cast<char*>(base));
+}
+}  // namespace
+
+size_t sim_rank_fused_workspace_bytes(int I, int T, int D, int nnz) {
+  FusedWs w;
+  carve_fused(w, nullptr, I, T, D, nnz, D % 8 == 0);       // sized for the screened pass whenever the shape allows it
+  return w.bytes + 256;
 }
 
 bool sim_rank_fused_ok(const float* img, const float* txt, int I, int T, int D) {
@@ -444,31 +573,59 @@ int sim_rank_fused(const float* img, const float* txt, int I, int T, int D, floa
                    const int32_t* gt_ptr, const int32_t* gt_idx, int nnz, int32_t* ranks_i2t, int32_t* ranks_t2i,
                    void* workspace, cudaStream_t st) {
   const int tiles_m = ceil_div(I, tc::BM), tiles_n = ceil_div(T, 128), tiles = tiles_m * tiles_n;
-  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-  char* p = reinterpret_cast<char*>(workspace);
-  float* gt_val = reinterpret_cast<float*>(p); p += al((size_t)nnz * 4 + 4);
-  float* col_val = reinterpret_cast<float*>(p); p += al((size_t)T * 4);
-  float* row_thr = reinterpret_cast<float*>(p); p += al((size_t)I * 4);
-  int32_t* row_thr_idx = reinterpret_cast<int32_t*>(p); p += al((size_t)I * 4);
-  int32_t* col_thr_idx = reinterpret_cast<int32_t*>(p); p += al((size_t)T * 4);
-  int* flags = reinterpret_cast<int*>(p); p += al((size_t)tiles * 4);
-  int* list = reinterpret_cast<int*>(p); p += al((size_t)tiles * 4);
-  int* count = reinterpret_cast<int*>(p);
-  VLDD_CUDA(cudaMemsetAsync(flags, 0, (size_t)tiles * 4, st));
-  VLDD_CUDA(cudaMemsetAsync(count, 0, 4, st));
+  const bool screen = screen_wanted(img, txt, I, T, D);
+  FusedWs w;
+  carve_fused(w, workspace, I, T, D, nnz, D % 8 == 0);
+  VLDD_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)tiles * 4, st));
+  VLDD_CUDA(cudaMemsetAsync(w.count, 0, 4, st));
   VLDD_CUDA(cudaMemsetAsync(ranks_i2t, 0, (size_t)I * 4, st));
   VLDD_CUDA(cudaMemsetAsync(ranks_t2i, 0, (size_t)T * 4, st));
   const int nmax = I > T ? I : T;
-  launch_k(mark_gt_tiles_kernel, ceil_div(nmax, 256), 256, 0, st, gt_ptr, gt_idx, txt2img, I, T, tiles_n, flags);
-  launch_k(compact_tiles_kernel, ceil_div(tiles, 256), 256, 0, st, (const int*)flags, tiles, list, count);
+  launch_k(mark_gt_tiles_kernel, ceil_div(nmax, 256), 256, 0, st, gt_ptr, gt_idx, txt2img, I, T, tiles_n, w.flags);
+  launch_k(compact_tiles_kernel, ceil_div(tiles, 256), 256, 0, st, (const int*)w.flags, tiles, w.list, w.count);
   const GemmOperands g = gemm_ops(img, D, txt, D, I, T, D);
-  int rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankExtract{scale, gt_ptr, gt_idx, gt_val, txt2img, col_val}, st, list, count);
+  // pass 1 (exact, 3xTF32): the scores at the ground-truth positions, from the tiles that hold one
+  int rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankExtract{scale, gt_ptr, gt_idx, w.gt_val, txt2img, w.col_val}, st, w.list, w.count);
   if (rc) return rc;
-  launch_k(rank_thresholds_kernel, ceil_div(nmax, 256), 256, 0, st, gt_ptr, gt_idx, (const float*)gt_val, txt2img, I, T, row_thr,
-           row_thr_idx, col_thr_idx);
-  rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankCount{scale, row_thr, row_thr_idx, ranks_i2t, col_val, col_thr_idx, ranks_t2i}, st);
-  if (rc) return rc;
-  launch_k(rank_finalize_kernel, ceil_div(nmax, 256), 256, 0, st, (const int32_t*)row_thr_idx, (const int32_t*)col_thr_idx, I, T,
+  launch_k(rank_thresholds_kernel, ceil_div(nmax, 256), 256, 0, st, gt_ptr, gt_idx, (const float*)w.gt_val, txt2img, I, T, w.row_thr,
+           w.row_thr_idx, w.col_thr_idx);
+  if (!screen) {
+    // pass 2 (exact): every tile, count the entries ranked ahead of the ground truth per row and per column
+    rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankCount{scale, w.row_thr, w.row_thr_idx, ranks_i2t, w.col_val, w.col_thr_idx, ranks_t2i}, st);
+    if (rc) return rc;
+  } else {
+    // pass 2 (screen): the same count from a bf16x3 product at half the tensor time; pairs within the error band of their
+    // threshold go to a list ...
+    const int cap = screen_cap(I, T, D);
+    VLDD_CUDA(cudaMemsetAsync(w.amb_count, 0, 32, st));          // list count, pair count, tile count, fall-back count, max norms, band
+    launch_k(split_rows_bf16_kernel, I, 256, 0, st, img, D, w.img_hi, w.img_lo, w.max_norms);
+    launch_k(split_rows_bf16_kernel, T, 256, 0, st, txt, D, w.txt_hi, w.txt_lo, w.max_norms + 1);
+    launch_k(screen_band_kernel, 1, 32, 0, st, (const int*)w.max_norms, screen_eps_rel(D) * fabsf(scale), w.band);
+    rc = tc::launch_bf16x3<tc::EpiRankScreen, 256>(
+        w.img_hi, w.img_lo, w.txt_hi, w.txt_lo, I, T, D,
+        tc::EpiRankScreen{scale, w.row_thr, w.row_thr_idx, ranks_i2t, w.col_val, w.col_thr_idx, ranks_t2i, w.band, w.amb, w.amb_count,
+                          cap},
+        st);
+    if (rc) return rc;
+    // ... pass 3 (exact): the listed pairs are gathered into a [P, D] x [P, D]^T problem whose diagonal tiles the 3xTF32 kernel
+    // computes -- the same arithmetic, k order and epilogue scaling as pass 1, hence the same bits as the materialised matrix
+    launch_k(decide_prepare_kernel, 64, 256, 0, st, (const int32_t*)w.amb_count, cap, cap / 128, tiles, w.n_pairs, w.tile_list,
+             w.tile_count, w.ident_list, w.fb_count);
+    launch_k(gather_pairs_kernel, num_sms() * 4, 256, 0, st, (const tc::AmbiguousPair*)w.amb, (const int32_t*)w.n_pairs, img, txt, D, w.Ag,
+             w.Bg);
+    const GemmOperands gg = gemm_ops(w.Ag, D, w.Bg, D, cap, cap, D);
+    rc = tc::launch<true, true, 3>(gg, 1,
+                                   tc::EpiPairDecide{scale, w.amb, w.n_pairs, w.row_thr, w.row_thr_idx, ranks_i2t, w.col_val, w.col_thr_idx,
+                                                     ranks_t2i},
+                                   st, w.tile_list, w.tile_count);
+    if (rc) return rc;
+    // list overflow (far more near-ties than the capacity provides for): recount everything exactly
+    launch_k(fallback_reset_kernel, num_sms(), 256, 0, st, (const int*)w.fb_count, I, T, ranks_i2t, ranks_t2i);
+    rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankCount{scale, w.row_thr, w.row_thr_idx, ranks_i2t, w.col_val, w.col_thr_idx, ranks_t2i}, st,
+                                   w.ident_list, w.fb_count);
+    if (rc) return rc;
+  }
+  launch_k(rank_finalize_kernel, ceil_div(nmax, 256), 256, 0, st, (const int32_t*)w.row_thr_idx, (const int32_t*)w.col_thr_idx, I, T,
            ranks_i2t, ranks_t2i);
   return check_launch("sim_rank_fused");
 }

@@ -30,6 +30,10 @@ constexpr int UMMA_K = 8;                           // tf32
 constexpr int TILE_BYTES = BM * BK * 4;             // 16 KB per operand per stage
 constexpr int kBaseThreads = 192;                   // producer, MMA, 4 splitter warps; + 32 per epilogue warp (4 or 8 of them)
 
+// kSplit == 6 ("bf16x3"): operands arrive PRE-SPLIT as bf16 hi / lo pairs (x = hi + lo + O(2^-18 |x|)), K-major only, four
+//   tensor maps (a0 = A_hi, a1 = A_lo, b0 = B_hi, b1 = B_lo; no second K segment); per 16-element k-step the MMA warp issues
+//   lo*hi + hi*lo + hi*hi as kind::f16 -- half the tensor time of 3xTF32 and no splitter work.  Error ~3 * 2^-18 per product:
+//   used as the SCREEN of the fused retrieval ranking, whose borderline pairs are re-decided in 3xTF32.
 // Stage layout (kSplit == 3):  K-major A  -> [A | B | B_lo]            48 KB x 4 stages; A_hi / A_lo live in TMEM
 //                              MN-major A -> [A | B | A_lo | B_lo]     64 KB x 3 stages
 //               (kSplit == 1):              [A | B]                    32 KB x 6 stages
@@ -38,12 +42,15 @@ struct Cfg {
   static_assert(kEpiWarps == 4 || kEpiWarps == 8, "one or two epilogue warps per TMEM lane quadrant");
   static constexpr int kThreads = kBaseThreads + 32 * kEpiWarps;
   static constexpr int kTileB = BN * BK * 4;                              // B tile bytes (12 KB at BN = 96)
-  static constexpr int kStageBytes = kSplit == 3 ? (A_TMEM ? TILE_BYTES + 2 * kTileB : 2 * TILE_BYTES + 2 * kTileB)
-                                                 : TILE_BYTES + kTileB;
+  static constexpr int kStageBytes = kSplit == 6 ? 2 * TILE_BYTES + 2 * kTileB
+                                     : kSplit == 3 ? (A_TMEM ? TILE_BYTES + 2 * kTileB : 2 * TILE_BYTES + 2 * kTileB)
+                                                   : TILE_BYTES + kTileB;
   // Pipeline depth.  One stage's round trip (TMA issue -> data landed ~0.8-1.0 us, operand split ~0.25 us, its 12 MMAs
   // ~0.4 us, commit -> producer) is ~1.8 us, so with d stages a k-block costs max(MMA time, 1.8 us / d): narrower N tiles
   // buy depth (shared memory: 48 / 40 / 32 KB per stage at BN = 128 / 96 / 64; tensor memory: 64 columns of A per stage).
-  static constexpr int kStagesDefault = (kSplit == 3 ? (A_TMEM ? (BN <= 64 ? 6 : (BN <= 96 ? 5 : 4)) : 3) : 6) - (kEpiWarps == 8 ? 1 : 0);
+  static constexpr int kStagesDefault =
+      kSplit == 6 ? (BN > 128 ? 2 : 3)
+                  : (kSplit == 3 ? (A_TMEM ? (BN <= 64 ? 6 : (BN <= 96 ? 5 : 4)) : 3) : 6) - (kEpiWarps == 8 ? 1 : 0);
   static constexpr int kStages = kStagesT > 0 ? kStagesT : kStagesDefault;
   static constexpr int kEpiBytes = kEpiWarps * 32 * 36 * 4;               // private transpose patches of the epilogue warps
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -134,6 +141,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // A operand from tensor memory (lane = row, 8 consecutive 32-bit columns = the K=8 tf32 values of that row)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -200,8 +217,13 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(bool a_mn_major, bool b_m
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// instruction descriptor for kind::f16 with bf16 operands, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- epilogues -------------------------------------------------------------------------------------------
-enum EpiKind { kEpiStore = 0, kEpiRankExtract = 1, kEpiRankCount = 2 };
+enum EpiKind { kEpiStore = 0, kEpiRankExtract = 1, kEpiRankCount = 2, kEpiRankScreen = 3, kEpiPairDecide = 4 };
 
 struct EpiPartial {   // raw fp32 tile -> slab z of [splits][M*N]
   static constexpr int kKind = kEpiStore;
@@ -256,6 +278,43 @@ struct EpiRankCount {
   const float* col_thr; const int32_t* col_thr_idx; int32_t* col_cnt;   // [N]
 };
 
+//  screened count: the tile comes from a CHEAPER product (bf16x3) whose distance to the 3xTF32 score of the same pair is
+//                    bounded by *band (one scalar: alpha * eps(K) * max |img row| * max |txt row|).  Entries clearly ahead of the
+//                    threshold are counted, entries clearly behind are not, entries inside the band are appended to a list
+//                    (pair + direction) and decided exactly afterwards.  Ties (and the ground-truth entries themselves) always
+//                    fall inside the band.  The hot loop is branch-free: two compares and two adds per entry and direction;
+//                    only a chunk that holds a borderline entry (#{v >= thr - band} != #{v > thr + band}) is rescanned.
+struct AmbiguousPair { int32_t m, n, dir; };      // dir 1: image -> text (row count of image m), 2: text -> image (column count of n)
+struct EpiRankScreen {
+  static constexpr int kKind = kEpiRankScreen;
+  float alpha;
+  __device__ __forceinline__ float coef() const { return alpha; }
+  __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
+  __device__ __forceinline__ float* row_ptr(int, int, int) const { return nullptr; }
+  __device__ __forceinline__ float apply(float a, float, float) const { return a; }
+  const float* row_thr; const int32_t* row_thr_idx; int32_t* row_cnt;    // [M]
+  const float* col_thr; const int32_t* col_thr_idx; int32_t* col_cnt;    // [N]
+  const float* band;                                                     // device scalar
+  AmbiguousPair* list; int32_t* list_count; int32_t list_cap;
+  __device__ __forceinline__ void push(int m, int n, int dir) const {
+    const int at = atomicAdd(list_count, 1);
+    if (at < list_cap) list[at] = AmbiguousPair{m, n, dir};
+  }
+};
+//  pair decide:      tile t of a [P, D] x [P, D]^T product of GATHERED rows (pair p = image m_p against caption n_p): only the
+//                    diagonal is read; S = alpha * acc[p, p] is the 3xTF32 score of the pair, compared like the exact count.
+struct EpiPairDecide {
+  static constexpr int kKind = kEpiPairDecide;
+  float alpha;
+  __device__ __forceinline__ float coef() const { return alpha; }
+  __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
+  __device__ __forceinline__ float* row_ptr(int, int, int) const { return nullptr; }
+  __device__ __forceinline__ float apply(float a, float, float) const { return a; }
+  const AmbiguousPair* list; const int32_t* n_pairs;
+  const float* row_thr; const int32_t* row_thr_idx; int32_t* row_cnt;
+  const float* col_thr; const int32_t* col_thr_idx; int32_t* col_cnt;
+};
+
 #ifdef VLDD_TC_TIMELINE
 __device__ long long g_timeline[148 * 10 * 16];   // [cta][slot]: globaltimer at phase boundaries (developer harness only)
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -280,7 +339,9 @@ template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0,
 __global__ void __launch_bounds__(kBaseThreads + 32 * kEpiWarps, 1)
 tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, int splits, Epi epi,
                const int* __restrict__ work_list, const int* __restrict__ work_count, int old_mask) {
-  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 128, "N tile: 64, 96 or 128 (32-column epilogue chunks, MN-major boxes)");
+  static_assert(BN % 32 == 0 && BN >= 64 && (BN <= 128 || (kSplit == 6 && BN <= 256)),
+                "N tile: 64, 96 or 128 (32-column epilogue chunks, MN-major boxes); up to 256 for the bf16 mode");
+  static_assert(kSplit != 6 || (A_KMAJOR && B_KMAJOR), "bf16x3 operands are K-major");
   constexpr bool A_TMEM = kSplit == 3;                 // hi/lo of the A tile are staged in tensor memory (either major)
   using C = Cfg<kSplit, A_TMEM, kStagesT, BN, kEpiWarps>;
   constexpr int TILE_B = C::kTileB;
@@ -298,7 +359,8 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TL(0);
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-  const int nkb0 = (K0 + BK - 1) / BK, nkb1 = (K1 + BK - 1) / BK, nkb = nkb0 + nkb1;
+  constexpr int BKE = kSplit == 6 ? 64 : BK;               // elements of K per k-block (128 bytes either way)
+  const int nkb0 = (K0 + BKE - 1) / BKE, nkb1 = (K1 + BKE - 1) / BKE, nkb = nkb0 + nkb1;
   const int per = (nkb + splits - 1) / splits;
   // optional device-side work list (tile indices chosen by an earlier kernel, e.g. "tiles holding a ground-truth pair");
   // it is written by a predecessor kernel, so it may only be read after pdl_wait() -- see below
@@ -354,7 +416,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   //   A in TMEM: [A | B | B_lo]      A in smem: [A | A_lo | B | B_lo]   (A / A_lo and B / B_lo adjacent: one split loop each)
   constexpr int OFF_A = 0;
   constexpr int OFF_ALO = TILE_BYTES;                               // only when A is fed from shared memory
-  constexpr int OFF_B = (A_TMEM || kSplit != 3) ? TILE_BYTES : 2 * TILE_BYTES;
+  constexpr int OFF_B = (kSplit == 6) ? 2 * TILE_BYTES : ((A_TMEM || kSplit != 3) ? TILE_BYTES : 2 * TILE_BYTES);
   constexpr int OFF_BLO = OFF_B + TILE_B;
 
   // Drain columns [c_begin, c_end) of accumulator `acc` for work item `it`: TMEM lane quadrant is fixed by warp index % 4.
@@ -398,6 +460,22 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     if constexpr (Epi::kKind == kEpiRankCount) {
       if (my_m < M) { row_thr = epi.row_thr[my_m]; row_thr_idx = epi.row_thr_idx[my_m]; }
     }
+    // screened count: thresholds with the band folded in; +inf for a row / column without ground truth (never counted, never
+    // borderline).  The column thresholds of the NEXT chunk are fetched while the current one is processed.
+    [[maybe_unused]] float rhi = INFINITY, rlo = INFINITY, band = 0.f, cthr_next = INFINITY;
+    auto col_thr_of = [&](int c) {
+      const int n = n0 + c + lane;
+      float t = INFINITY;
+      if constexpr (Epi::kKind == kEpiRankScreen) {
+        if (c < c_end && n < N && epi.col_thr_idx[n] >= 0) t = epi.col_thr[n];
+      }
+      return t;
+    };
+    if constexpr (Epi::kKind == kEpiRankScreen) {
+      band = *epi.band;
+      if (my_m < M && epi.row_thr_idx[my_m] >= 0) { const float t = epi.row_thr[my_m]; rhi = t + band; rlo = t - band; }
+      cthr_next = col_thr_of(c_begin);
+    }
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += c_step) {
       float v[32];
@@ -423,6 +501,27 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
             const int n = n0 + c + j;
             row_count += (n < N) && ((v[j] > row_thr) || (v[j] == row_thr && n < row_thr_idx));
           }
+        }
+      }
+      [[maybe_unused]] float cthr = INFINITY;
+      if constexpr (Epi::kKind == kEpiRankScreen) {
+        cthr = cthr_next;
+        cthr_next = col_thr_of(c + c_step);
+        // image -> text: this thread's row against the 32 captions of the chunk
+        const int jmax = N - (n0 + c);                   // >= 32 except in the last tile of a row of tiles
+        int gt = 0, ge = 0;
+        if (jmax >= 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { gt += v[j] > rhi; ge += v[j] >= rlo; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { gt += (j < jmax) && v[j] > rhi; ge += (j < jmax) && v[j] >= rlo; }
+        }
+        row_count += gt;
+        if (ge != gt) {                                  // rare: a borderline entry in this row of the chunk
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < jmax && v[j] >= rlo && !(v[j] > rhi)) epi.push(my_m, n0 + c + j, 1);
         }
       }
       __syncwarp();
@@ -467,6 +566,40 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
           const int g = epi.col_gt[n] - (m0 + quad * 32);
           if (g >= 0 && g < 32) epi.col_val[n] = stage[g * LDS + lane];
         }
+      } else if constexpr (Epi::kKind == kEpiRankScreen) {   // text -> image: lane j owns caption n, 32 image rows of the quadrant
+        const int n = n0 + c + lane;
+        const float chi = cthr + band, clo = cthr - band;      // +inf: no ground truth / past the last caption
+        const int mbase = m0 + quad * 32;
+        const int nvalid = min(32, M - mbase);
+        int gt = 0, ge = 0;
+        if (nvalid == 32) {
+#pragma unroll 16
+          for (int rr = 0; rr < 32; ++rr) { const float sv_ = stage[rr * LDS + lane]; gt += sv_ > chi; ge += sv_ >= clo; }
+        } else {
+          for (int rr = 0; rr < nvalid; ++rr) { const float sv_ = stage[rr * LDS + lane]; gt += sv_ > chi; ge += sv_ >= clo; }
+        }
+        if (gt) atomicAdd(epi.col_cnt + n, gt);
+        if (ge != gt) {
+          for (int rr = 0; rr < nvalid; ++rr) {
+            const float sv_ = stage[rr * LDS + lane];
+            if (sv_ >= clo && !(sv_ > chi)) epi.push(mbase + rr, n, 2);
+          }
+        }
+      } else if constexpr (Epi::kKind == kEpiPairDecide) {   // diagonal tiles of the gathered product: pair p = row p = column p
+        if (c == quad * 32 && m0 == n0) {
+          const int p = m0 + quad * 32 + lane;
+          if (p < *epi.n_pairs) {
+            const float sc = stage[lane * LDS + lane];
+            const AmbiguousPair a = epi.list[p];
+            if (a.dir == 1) {
+              const float thr = epi.row_thr[a.m];
+              if (sc > thr || (sc == thr && a.n < epi.row_thr_idx[a.m])) atomicAdd(epi.row_cnt + a.m, 1);
+            } else {
+              const float thr = epi.col_thr[a.n];
+              if (sc > thr || (sc == thr && a.m < epi.col_thr_idx[a.n])) atomicAdd(epi.col_cnt + a.n, 1);
+            }
+          }
+        }
       } else {   // kEpiRankCount, column direction: lane j counts the 32 rows of this quadrant for caption n
         const int n = n0 + c + lane;
         if (n < N) {
@@ -485,7 +618,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         }
       }
     }
-    if constexpr (Epi::kKind == kEpiRankCount) {
+    if constexpr (Epi::kKind == kEpiRankCount || Epi::kKind == kEpiRankScreen) {
       if (row_count) atomicAdd(epi.row_cnt + my_m, row_count);
     }
   };
@@ -494,6 +627,15 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     // ===== TMA producer: the whole warp walks the loop (uniform control flow), one elected lane issues =====
     auto issue = [&](const WorkItem& it, int i, int s, bool load_a, bool load_b) {
       const int kb = it.kb_begin + i;
+      if constexpr (kSplit == 6) {        // four bf16 tiles: A_hi | A_lo | B_hi | B_lo, 64 elements of K each
+        uint8_t* st0 = smem + s * C::kStageBytes;
+        const int k = kb * 64;
+        tma_load_2d(st0 + OFF_A, &maps.a0, &full[s], k, it.m0);
+        tma_load_2d(st0 + OFF_ALO, &maps.a1, &full[s], k, it.m0);
+        tma_load_2d(st0 + OFF_B, &maps.b0, &full[s], k, it.n0);
+        tma_load_2d(st0 + OFF_BLO, &maps.b1, &full[s], k, it.n0);
+        return;
+      }
       const bool seg1 = kb >= nkb0;
       const int k = (seg1 ? kb - nkb0 : kb) * BK;
       const CUtensorMap* ma = seg1 ? &maps.a1 : &maps.a0;
@@ -529,7 +671,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         } else {
           if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
           if (elect_one()) {
-            mbar_expect_tx(&full[s], TILE_BYTES + TILE_B);
+            mbar_expect_tx(&full[s], kSplit == 6 ? 2 * (TILE_BYTES + TILE_B) : TILE_BYTES + TILE_B);
             issue(it, i, s, true, true);
           }
         }
@@ -573,7 +715,15 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t db = smem_desc(sb + k * b_step, b_lbo, b_sbo, b_lt);
-              if (kSplit == 3) {
+              if constexpr (kSplit == 6) {
+                constexpr uint32_t idesc16 = instr_desc_bf16(BM, BN);
+                const uint64_t dbl = smem_desc(sbl + k * b_step, b_lbo, b_sbo, b_lt);
+                const uint64_t da = smem_desc(sa + k * a_step, a_lbo, a_sbo, a_lt);
+                const uint64_t dal = smem_desc(sal + k * a_step, a_lbo, a_sbo, a_lt);
+                umma_bf16(tacc, dal, db, idesc16, accumulate);
+                umma_bf16(tacc, da, dbl, idesc16, 1);
+                umma_bf16(tacc, da, db, idesc16, 1);
+              } else if (kSplit == 3) {
                 const uint64_t dbl = smem_desc(sbl + k * b_step, b_lbo, b_sbo, b_lt);
                 if (A_TMEM) {
                   umma_tf32_ts(tacc, ta_lo + k * UMMA_K, db, idesc, accumulate);

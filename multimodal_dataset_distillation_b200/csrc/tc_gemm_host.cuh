@@ -88,6 +88,65 @@ inline int get_map(const float* ptr, int rows, int K, int ld, bool kmajor, CUten
   return VLDD_OK;
 }
 
+// K-major bf16 operand [rows, K] (row stride ld elements): 2-D map, box 64 x box_rows, SWIZZLE_128B
+inline int get_map_bf16(const void* ptr, int rows, int K, int ld, CUtensorMap* out, int box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, rows, K, ld, 2, box_rows};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return VLDD_OK; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VLDD_ERR_CUDA; }
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t es[2] = {1, 1};
+  const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(bf16) failed (%d) for rows=%d K=%d ld=%d", (int)r, rows, K, ld);
+    return VLDD_ERR_CUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return VLDD_OK;
+}
+
+// C = A B^T from pre-split bf16 operands (A = A_hi + A_lo [M, K], B = B_hi + B_lo [N, K], K-major, K % 8 == 0, 16-byte
+// aligned): three bf16 tensor-core products per k-step (tc_gemm.cuh, kSplit == 6), 128 x BN tiles.
+template <class Epi, int BN = 256>
+inline int launch_bf16x3(const void* A_hi, const void* A_lo, const void* B_hi, const void* B_lo, int M, int N, int K, Epi epi,
+                         cudaStream_t st, const int* work_list = nullptr, const int* work_count = nullptr) {
+  using C = Cfg<6, false, 0, BN, 4>;
+  auto kern = tc_gemm_kernel<true, true, 6, Epi, 0, BN, 4>;
+  static bool configured[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("tc::launch_bf16x3: bad device ordinal"); return VLDD_ERR_CUDA; }
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%d) failed: %s", C::kSmemBytes, cudaGetErrorString(e)); return VLDD_ERR_CUDA; }
+    configured[dev] = true;
+  }
+  if (K % 8 != 0 || !aligned16(A_hi) || !aligned16(A_lo) || !aligned16(B_hi) || !aligned16(B_lo)) {
+    set_error("launch_bf16x3: K %% 8 != 0 or unaligned operand");
+    return VLDD_ERR_ARG;
+  }
+  Maps maps;
+  int rc = get_map_bf16(A_hi, M, K, K, &maps.a0, BM);
+  if (!rc) rc = get_map_bf16(A_lo, M, K, K, &maps.a1, BM);
+  if (!rc) rc = get_map_bf16(B_hi, N, K, K, &maps.b0, BN);
+  if (!rc) rc = get_map_bf16(B_lo, N, K, K, &maps.b1, BN);
+  if (rc) return rc;
+  const int work = ceil_div(N, BN) * ceil_div(M, BM);
+  dim3 grid(work < num_sms() ? work : num_sms());
+  launch_k(kern, grid, C::kThreads, C::kSmemBytes, st, maps, M, N, K, 0, 1, epi, work_list, work_count, 0);
+  return VLDD_OK;
+}
+
 template <bool A_KMAJOR, bool B_KMAJOR>
 inline bool gemm_ok(const GemmOperands& g) {
   if (!operand_ok(g.A0, g.M, g.K0, g.lda0, A_KMAJOR) || !operand_ok(g.B0, g.N, g.K0, g.ldb0, B_KMAJOR)) return false;

@@ -222,7 +222,7 @@ def sim_rank_fused(img: torch.Tensor, txt: torch.Tensor, txt2img: torch.Tensor, 
     I, T, D = img.shape[0], txt.shape[0], img.shape[1]
     idx = _req(img2txt_idx, "img2txt_idx", torch.int32)
     nnz = idx.numel()
-    need = lib().vldd_sim_rank_fused_workspace_bytes(I, T, nnz)
+    need = lib().vldd_sim_rank_fused_workspace_bytes(I, T, D, nnz)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=img.device)
     r1 = torch.empty(I, dtype=torch.int32, device=img.device)

@@ -36,7 +36,7 @@ def run(I, C, D, reps=5):
         ref = int((S[k] > S[k, best]).sum())
         ok &= abs(int(r1[i]) - ref) <= 2          # fp32 summation-order near-ties only
     rec = [(r1 < k).float().mean().item() * 100 for k in (1, 5, 10)]
-    wsf = torch.empty(ops.lib().vldd_sim_rank_fused_workspace_bytes(I, T, T), dtype=torch.uint8, device="cuda")
+    wsf = torch.empty(ops.lib().vldd_sim_rank_fused_workspace_bytes(I, T, D, T), dtype=torch.uint8, device="cuda")
     f1, f2 = ops.sim_rank_fused(img, txt, t2i, ptr, idx, 14.285714, wsf)
     same = bool(torch.equal(f1, r1) and torch.equal(f2, r2))
     tf = []

@@ -104,3 +104,45 @@ def test_itm_eval_on_the_reference_flickr30k_maps():
     Sg = s1.cpu().numpy()
     assert np.array_equal(r1.cpu().numpy(), RR.ranks_i2t(Sg, img2txt))
     assert np.array_equal(r2.cpu().numpy(), RR.ranks_t2i(np.ascontiguousarray(Sg.T), txt2img))
+
+
+SCREEN_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+from oracle import retrieval_ref as RR
+from multimodal_dataset_distillation_b200 import ops
+I, C, D, quant = {I}, {C}, {D}, {quant}
+img, txt = RR.synthetic_retrieval(I, C, D, seed=11)
+if quant:                                    # exact ties by the thousand, also between ground-truth captions
+    img, txt = (np.round(img * 8) / 8).astype(np.float32), (np.round(txt * 8) / 8).astype(np.float32)
+T = I * C
+txt2img, img2txt = RR.flickr_maps(I, C)
+t2i, ptr, idx = ops.maps_to_arrays(txt2img, img2txt, I, T)
+dev = lambda a: torch.from_numpy(a).cuda()
+f1, f2 = ops.sim_rank_fused(dev(img), dev(txt), dev(t2i), dev(ptr), dev(idx), 14.285714)
+m1, m2 = ops.sim_rank(dev(img), dev(txt), dev(t2i), dev(ptr), dev(idx), 14.285714)
+S = ops.sim_scores(dev(img), dev(txt), 14.285714, want_t2i=False)[0].cpu().numpy()
+ok = bool(torch.equal(f1, m1) and torch.equal(f2, m2))
+ok = ok and np.array_equal(f1.cpu().numpy(), RR.ranks_i2t(S, img2txt)) and np.array_equal(f2.cpu().numpy(), RR.ranks_t2i(np.ascontiguousarray(S.T), txt2img))
+print("RESULT", ok, int(f1.sum()), int(f2.sum()))
+sys.exit(0 if ok else 1)
+"""
+
+
+@pytest.mark.parametrize("I,C,D,quant,env", [
+    (300, 5, 64, False, {"VLDD_SCREEN_MIN_PAIRS": "0"}),                                  # screen + decide on a small problem
+    (300, 5, 64, True, {"VLDD_SCREEN_MIN_PAIRS": "0"}),                                   # tie-heavy: thousands of borderline pairs
+    (300, 5, 64, True, {"VLDD_SCREEN_MIN_PAIRS": "0", "VLDD_SCREEN_CAP": "128"}),         # list overflow -> exact fall-back pass
+    (257, 3, 200, False, {"VLDD_SCREEN_MIN_PAIRS": "0"}),                                 # ragged tiles, K not a multiple of 64
+    (300, 5, 64, True, {"VLDD_SCREEN_MIN_PAIRS": "1000000000"}),                          # screen off: the exact count pass
+])
+def test_screened_count_is_bit_identical_to_materialised(I, C, D, quant, env):
+    """vldd_sim_rank_fused's bf16x3 screen + exact 3xTF32 decision (and its overflow fall-back) give the ranks of the
+    materialised 3xTF32 score matrix bit for bit -- on tie-free data, on heavily tied data, and when the borderline list
+    overflows.  The switches are read once per process, hence the child process."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, "-c", SCREEN_CHILD.format(root=ROOT, I=I, C=C, D=D, quant=quant)],
+                       env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
