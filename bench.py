@@ -275,8 +275,8 @@ def gpu_retrieval_set(I, Cc, D, dev, seed=0):
 
 def bench_retrieval_large(dev, world, rank, reps=3):
     """configs[3]/[4]: 5000 x 25000 and 25000 x 125000 (D = 768).  One GPU: vldd_sim_rank_fused.  N > 1: captions sharded
-    per rank (dist.sharded_ranks: one [I, T/N] score GEMM per rank, two 8 B/image all-gathers + one int32 all-reduce),
-    ranks asserted equal to rank 0's single-GPU result; time = max over ranks."""
+    per rank (dist.sharded_ranks_fused: the same fused ranking per [I, T/N] shard -- no score matrix --, two 8 B/image
+    all-gathers + one int32 all-reduce), ranks asserted equal to rank 0's single-GPU result; time = max over ranks."""
     import torch.distributed as dist
     from multimodal_dataset_distillation_b200 import ops, dist as D
     pk = peaks()
@@ -302,8 +302,9 @@ def bench_retrieval_large(dev, world, rank, reps=3):
         else:
             lo, hi = D.shard_bounds(T, world, rank)
             txt_s, t2i_s = txt[lo:hi].contiguous(), t2i[lo:hi].contiguous()
+            shard = ops.FusedRankShard(img, txt_s, lo, t2i_s, gptr, gidx, 14.285714)
             def sharded():
-                return D.sharded_ranks(img, txt_s, lo, t2i_s, gptr, gidx, 14.285714)
+                return D.sharded_ranks_fused(img, txt_s, lo, t2i_s, gptr, gidx, 14.285714, T, shard=shard)
             sharded()
             dist.barrier(); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -324,11 +325,11 @@ def bench_retrieval_large(dev, world, rank, reps=3):
                 r1, r2 = single()
                 ok = bool(torch.equal(r1, ri)) and bool(torch.equal(r2, torch.cat(parts)))
                 assert ok, "sharded ranks differ from the single-GPU ranks"
-            entry.update(path=f"dist.sharded_ranks: captions sharded {world}-way, images replicated",
+            entry.update(path=f"dist.sharded_ranks_fused: captions sharded {world}-way, images replicated, fused ranking per shard",
                          collectives="2 x all_gather of 8 B/image (best ground-truth candidate per shard) + 1 x int32 "
                                      "all_reduce of I counts (NCCL over NVLink); latency-bound, the GEMM dominates",
                          ranks_equal_single_gpu=ok)
-            del txt_s, t2i_s
+            del txt_s, t2i_s, shard
         tflops = 2.0 * I * T * Dm / (ms / 1e3) / 1e12
         entry.update(ms=ms, value=I * T / (ms / 1e3), unit="pairs/s",
                      roofline={"bound": "tensor", "achieved": tflops, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tflops / pk["tf"],

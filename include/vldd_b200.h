@@ -102,6 +102,23 @@ int vldd_sim_rank_fused(const float* img, const float* txt, int n_img, int n_txt
                         const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx, int nnz,
                         int32_t* ranks_i2t, int32_t* ranks_t2i, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same fused ranking for ONE CAPTION SHARD (multi-GPU: images replicated, captions [col_offset, col_offset + n_txt) of
+ * the full set on this rank; epoch_original.py:94-105 + epoch.py:219-244 over the whole set).  img2txt_idx holds GLOBAL
+ * caption ids.  Phase A: per image the best ground-truth candidate among the local captions, cand_score[n_img] (+inf: none
+ * here) and cand_idx[n_img] (global caption id, -1: none).  The caller merges the candidates of all shards (higher score,
+ * then lower index) and calls phase B with thr_score (+inf: the image has no ground truth anywhere) and
+ * thr_idx_local = global id - col_offset (any integer): row_counts[n_img] = local captions ranked ahead of the threshold
+ * (to be summed over the shards; `invalid_row_rank` for +inf rows), ranks_t2i[n_txt] = final text -> image ranks of the
+ * local captions.  Both phases take the SAME workspace (vldd_sim_rank_fused_workspace_bytes), phase B reads what phase A
+ * left in it. */
+int vldd_sim_rank_fused_candidates(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale,
+                                   const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx, int nnz,
+                                   int col_offset, float* cand_score, int32_t* cand_idx, void* workspace, size_t workspace_bytes,
+                                   void* stream);
+int vldd_sim_rank_fused_count(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale, const float* thr_score,
+                              const int32_t* thr_idx_local, int nnz, int invalid_row_rank, int32_t* row_counts, int32_t* ranks_t2i,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* Host-buffer drop-in for `itm_eval(scores_i2t, scores_t2i, txt2img, img2txt)` (numpy arrays in the reference):
  * copies the matrices to the device, ranks, copies ranks back and fills result9 in the reference's key order
  * {txt_r1, txt_r5, txt_r10, txt_r_mean, img_r1, img_r5, img_r10, img_r_mean, r_mean}.  ranks_*_host may be NULL. */

@@ -36,6 +36,10 @@ _SIGS = {
     "vldd_sim_rank_fused_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "vldd_sim_rank_fused": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, C.c_int, _P, _P, _P,
                                       C.c_size_t, _P]),
+    "vldd_sim_rank_fused_candidates": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, C.c_int, C.c_int, _P, _P,
+                                                 _P, C.c_size_t, _P]),
+    "vldd_sim_rank_fused_count": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, C.c_int, C.c_int, _P, _P, _P,
+                                            C.c_size_t, _P]),
     "vldd_itm_eval_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
     "vldd_proj_head_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "vldd_proj_head_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),

@@ -196,6 +196,37 @@ int vldd_sim_rank_fused(const float* img, const float* txt, int n_img, int n_txt
                         workspace, S(stream));
 }
 
+// caption-sharded form of the fused ranking: phase A (candidates) and phase B (counts) with the exchange in between left to
+// the caller (dist.sharded_ranks_fused: all-gather of the candidates, merge, all-reduce of the row counts)
+int vldd_sim_rank_fused_candidates(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale,
+                                   const int32_t* txt2img, const int32_t* img2txt_ptr, const int32_t* img2txt_idx, int nnz,
+                                   int col_offset, float* cand_score, int32_t* cand_idx, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  VLDD_REQUIRE(n_img > 0 && n_txt > 0 && dim > 0 && nnz >= 0 && img && txt, "sim_rank_fused_candidates: bad arguments");
+  VLDD_REQUIRE(txt2img && img2txt_ptr && img2txt_idx && cand_score && cand_idx, "sim_rank_fused_candidates: null ground truth / outputs");
+  VLDD_REQUIRE(sim_rank_fused_ok(img, txt, n_img, n_txt, dim),
+               "sim_rank_fused_candidates: operands do not satisfy the tensor-map constraints (16-byte aligned, dim %% 4 == 0)");
+  if (workspace == nullptr || workspace_bytes < vldd_sim_rank_fused_workspace_bytes(n_img, n_txt, dim, nnz)) {
+    set_error("sim_rank_fused_candidates: workspace too small (need %zu bytes)", vldd_sim_rank_fused_workspace_bytes(n_img, n_txt, dim, nnz));
+    return VLDD_ERR_WORKSPACE;
+  }
+  return sim_rank_fused_candidates(img, txt, n_img, n_txt, dim, scale, txt2img, img2txt_ptr, img2txt_idx, nnz, col_offset, cand_score,
+                                   cand_idx, workspace, S(stream));
+}
+
+int vldd_sim_rank_fused_count(const float* img, const float* txt, int n_img, int n_txt, int dim, float scale, const float* thr_score,
+                              const int32_t* thr_idx_local, int nnz, int invalid_row_rank, int32_t* row_counts, int32_t* ranks_t2i,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  VLDD_REQUIRE(n_img > 0 && n_txt > 0 && dim > 0 && nnz >= 0 && img && txt && thr_score && thr_idx_local && row_counts && ranks_t2i,
+               "sim_rank_fused_count: bad arguments");
+  if (workspace == nullptr || workspace_bytes < vldd_sim_rank_fused_workspace_bytes(n_img, n_txt, dim, nnz)) {
+    set_error("sim_rank_fused_count: workspace too small (need %zu bytes)", vldd_sim_rank_fused_workspace_bytes(n_img, n_txt, dim, nnz));
+    return VLDD_ERR_WORKSPACE;
+  }
+  return sim_rank_fused_count(img, txt, n_img, n_txt, dim, scale, thr_score, thr_idx_local, nnz, invalid_row_rank, row_counts, ranks_t2i,
+                              workspace, S(stream));
+}
+
 int vldd_itm_eval_host(const float* scores_i2t_host, const float* scores_t2i_host, int n_img, int n_txt,
                        const int32_t* txt2img_host, const int32_t* img2txt_ptr_host, const int32_t* img2txt_idx_host,
                        int32_t* ranks_i2t_host, int32_t* ranks_t2i_host, double* result9, void* stream) {

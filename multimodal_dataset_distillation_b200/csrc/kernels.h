@@ -40,6 +40,12 @@ int sim_scores(const float* img, const float* txt, int I, int T, int D, float sc
                cudaStream_t st);
 size_t sim_rank_fused_workspace_bytes(int I, int T, int D, int nnz);
 bool sim_rank_fused_ok(const float* img, const float* txt, int I, int T, int D);
+int sim_rank_fused_candidates(const float* img, const float* txt, int I, int T, int D, float scale, const int32_t* txt2img,
+                              const int32_t* gt_ptr, const int32_t* gt_idx, int nnz, int col_offset, float* cand_score,
+                              int32_t* cand_idx, void* workspace, cudaStream_t st);
+int sim_rank_fused_count(const float* img, const float* txt, int I, int T, int D, float scale, const float* thr_score,
+                         const int32_t* thr_idx_local, int nnz, int invalid_row_rank, int32_t* ranks_i2t, int32_t* ranks_t2i,
+                         void* workspace, cudaStream_t st);
 int sim_rank_fused(const float* img, const float* txt, int I, int T, int D, float scale, const int32_t* txt2img,
                    const int32_t* gt_ptr, const int32_t* gt_idx, int nnz, int32_t* ranks_i2t, int32_t* ranks_t2i,
                    void* workspace, cudaStream_t st);

@@ -378,12 +378,12 @@ int nearest_rows(const float* query, const float* bank, int Q, int T, int D, int
 // ranked ahead of the ground truth (integer atomics).  Result == ranking the materialised matrix, bit for bit.
 __global__ void __launch_bounds__(256) mark_gt_tiles_kernel(const int32_t* __restrict__ gt_ptr, const int32_t* __restrict__ gt_idx,
                                                             const int32_t* __restrict__ txt2img, int I, int T, int tiles_n,
-                                                            int* __restrict__ flags) {
+                                                            int col_offset, int* __restrict__ flags) {
   pdl_enter();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < I) {
     for (int e = gt_ptr[t]; e < gt_ptr[t + 1]; ++e) {
-      const int c = gt_idx[e];
+      const int c = gt_idx[e] - col_offset;
       if (c >= 0 && c < T) flags[(t / tc::BM) * tiles_n + c / 128] = 1;
     }
   }
@@ -398,35 +398,38 @@ __global__ void __launch_bounds__(256) compact_tiles_kernel(const int* __restric
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n && flags[t]) list[atomicAdd(count, 1)] = t;
 }
+// Best ground-truth candidate per image among the captions of THIS product (columns [col_offset, col_offset + T) of the full
+// problem): score (+inf when the image has none here -- as a threshold "+inf" means nothing ranks ahead) and the GLOBAL caption
+// index (-1: none).  Also the validity of every local caption's own ground truth.
 __global__ void __launch_bounds__(256) rank_thresholds_kernel(const int32_t* __restrict__ gt_ptr, const int32_t* __restrict__ gt_idx,
                                                               const float* __restrict__ gt_val, const int32_t* __restrict__ txt2img,
-                                                              int I, int T, float* __restrict__ row_thr,
-                                                              int32_t* __restrict__ row_thr_idx, int32_t* __restrict__ col_thr_idx) {
+                                                              int I, int T, int col_offset, float* __restrict__ cand_score,
+                                                              int32_t* __restrict__ cand_idx, int32_t* __restrict__ col_thr_idx) {
   pdl_enter();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < I) {
-    float bs = -INFINITY;
+    float bs = INFINITY;
     int bc = -1;
     for (int e = gt_ptr[t]; e < gt_ptr[t + 1]; ++e) {
-      const int c = gt_idx[e];
+      const int cg = gt_idx[e], c = cg - col_offset;
       if (c < 0 || c >= T) continue;
       const float sc = gt_val[e];
-      if (bc < 0 || sc > bs || (sc == bs && c < bc)) { bs = sc; bc = c; }
+      if (bc < 0 || sc > bs || (sc == bs && cg < bc)) { bs = sc; bc = cg; }
     }
-    row_thr[t] = bs;
-    row_thr_idx[t] = bc;
+    cand_score[t] = bs;
+    cand_idx[t] = bc;
   }
   if (t < T) {
     const int g = txt2img[t];
     col_thr_idx[t] = (g >= 0 && g < I) ? g : -1;
   }
 }
-__global__ void __launch_bounds__(256) rank_finalize_kernel(const int32_t* __restrict__ row_thr_idx,
-                                                            const int32_t* __restrict__ col_thr_idx, int I, int T,
-                                                            int32_t* __restrict__ ranks_i2t, int32_t* __restrict__ ranks_t2i) {
+__global__ void __launch_bounds__(256) rank_finalize_kernel(const float* __restrict__ row_thr, const int32_t* __restrict__ col_thr_idx,
+                                                            int I, int T, int invalid_row_rank, int32_t* __restrict__ ranks_i2t,
+                                                            int32_t* __restrict__ ranks_t2i) {
   pdl_enter();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < I && row_thr_idx[t] < 0) ranks_i2t[t] = T;      // no valid ground truth: never retrieved
+  if (t < I && row_thr[t] == INFINITY) ranks_i2t[t] = invalid_row_rank;      // no valid ground truth: never retrieved
   if (t < T && col_thr_idx[t] < 0) ranks_t2i[t] = I;
 }
 
@@ -569,33 +572,50 @@ bool sim_rank_fused_ok(const float* img, const float* txt, int I, int T, int D) 
   return tc_enabled() && tc::gemm_ok<true, true>(gemm_ops(img, D, txt, D, I, T, D));
 }
 
-int sim_rank_fused(const float* img, const float* txt, int I, int T, int D, float scale, const int32_t* txt2img,
-                   const int32_t* gt_ptr, const int32_t* gt_idx, int nnz, int32_t* ranks_i2t, int32_t* ranks_t2i,
-                   void* workspace, cudaStream_t st) {
+// Phase A: the 3xTF32 scores at the ground-truth positions (only the tiles that hold one are computed) -> per image the best
+// local candidate (score, global caption index); the per-caption thresholds stay in the workspace for phase B.
+int sim_rank_fused_candidates(const float* img, const float* txt, int I, int T, int D, float scale, const int32_t* txt2img,
+                              const int32_t* gt_ptr, const int32_t* gt_idx, int nnz, int col_offset, float* cand_score,
+                              int32_t* cand_idx, void* workspace, cudaStream_t st) {
   const int tiles_m = ceil_div(I, tc::BM), tiles_n = ceil_div(T, 128), tiles = tiles_m * tiles_n;
-  const bool screen = screen_wanted(img, txt, I, T, D);
   FusedWs w;
   carve_fused(w, workspace, I, T, D, nnz, D % 8 == 0);
   VLDD_CUDA(cudaMemsetAsync(w.flags, 0, (size_t)tiles * 4, st));
   VLDD_CUDA(cudaMemsetAsync(w.count, 0, 4, st));
+  const int nmax = I > T ? I : T;
+  launch_k(mark_gt_tiles_kernel, ceil_div(nmax, 256), 256, 0, st, gt_ptr, gt_idx, txt2img, I, T, tiles_n, col_offset, w.flags);
+  launch_k(compact_tiles_kernel, ceil_div(tiles, 256), 256, 0, st, (const int*)w.flags, tiles, w.list, w.count);
+  const GemmOperands g = gemm_ops(img, D, txt, D, I, T, D);
+  int rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankExtract{scale, gt_ptr, gt_idx, w.gt_val, txt2img, w.col_val, col_offset}, st, w.list,
+                                     w.count);
+  if (rc) return rc;
+  launch_k(rank_thresholds_kernel, ceil_div(nmax, 256), 256, 0, st, gt_ptr, gt_idx, (const float*)w.gt_val, txt2img, I, T, col_offset,
+           cand_score, cand_idx, w.col_thr_idx);
+  return check_launch("sim_rank_fused_candidates");
+}
+
+// Phase B: per image the number of LOCAL captions ranked ahead of its threshold (score, caption index in local numbering -- any
+// integer: a threshold that lives in another shard simply never wins or loses the index tie-break), per local caption its final
+// text -> image rank.  Same workspace as phase A.  Rows whose threshold is +inf get `invalid_row_rank`.
+int sim_rank_fused_count(const float* img, const float* txt, int I, int T, int D, float scale, const float* thr_score,
+                         const int32_t* thr_idx_local, int nnz, int invalid_row_rank, int32_t* ranks_i2t, int32_t* ranks_t2i,
+                         void* workspace, cudaStream_t st) {
+  const int tiles_m = ceil_div(I, tc::BM), tiles_n = ceil_div(T, 128), tiles = tiles_m * tiles_n;
+  const bool screen = screen_wanted(img, txt, I, T, D);
+  FusedWs w;
+  carve_fused(w, workspace, I, T, D, nnz, D % 8 == 0);
   VLDD_CUDA(cudaMemsetAsync(ranks_i2t, 0, (size_t)I * 4, st));
   VLDD_CUDA(cudaMemsetAsync(ranks_t2i, 0, (size_t)T * 4, st));
   const int nmax = I > T ? I : T;
-  launch_k(mark_gt_tiles_kernel, ceil_div(nmax, 256), 256, 0, st, gt_ptr, gt_idx, txt2img, I, T, tiles_n, w.flags);
-  launch_k(compact_tiles_kernel, ceil_div(tiles, 256), 256, 0, st, (const int*)w.flags, tiles, w.list, w.count);
   const GemmOperands g = gemm_ops(img, D, txt, D, I, T, D);
-  // pass 1 (exact, 3xTF32): the scores at the ground-truth positions, from the tiles that hold one
-  int rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankExtract{scale, gt_ptr, gt_idx, w.gt_val, txt2img, w.col_val}, st, w.list, w.count);
-  if (rc) return rc;
-  launch_k(rank_thresholds_kernel, ceil_div(nmax, 256), 256, 0, st, gt_ptr, gt_idx, (const float*)w.gt_val, txt2img, I, T, w.row_thr,
-           w.row_thr_idx, w.col_thr_idx);
+  int rc;
   if (!screen) {
-    // pass 2 (exact): every tile, count the entries ranked ahead of the ground truth per row and per column
-    rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankCount{scale, w.row_thr, w.row_thr_idx, ranks_i2t, w.col_val, w.col_thr_idx, ranks_t2i}, st);
+    // exact: every tile, count the entries ranked ahead of the ground truth per row and per column
+    rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankCount{scale, thr_score, thr_idx_local, ranks_i2t, w.col_val, w.col_thr_idx, ranks_t2i}, st);
     if (rc) return rc;
   } else {
-    // pass 2 (screen): the same count from a bf16x3 product at half the tensor time; pairs within the error band of their
-    // threshold go to a list ...
+    // screen: the same count from a bf16x3 product at half the tensor time; pairs within the error band of their threshold go
+    // to a list ...
     const int cap = screen_cap(I, T, D);
     VLDD_CUDA(cudaMemsetAsync(w.amb_count, 0, 32, st));          // list count, pair count, tile count, fall-back count, max norms, band
     launch_k(split_rows_bf16_kernel, I, 256, 0, st, img, D, w.img_hi, w.img_lo, w.max_norms);
@@ -603,31 +623,40 @@ int sim_rank_fused(const float* img, const float* txt, int I, int T, int D, floa
     launch_k(screen_band_kernel, 1, 32, 0, st, (const int*)w.max_norms, screen_eps_rel(D) * fabsf(scale), w.band);
     rc = tc::launch_bf16x3<tc::EpiRankScreen, 256>(
         w.img_hi, w.img_lo, w.txt_hi, w.txt_lo, I, T, D,
-        tc::EpiRankScreen{scale, w.row_thr, w.row_thr_idx, ranks_i2t, w.col_val, w.col_thr_idx, ranks_t2i, w.band, w.amb, w.amb_count,
-                          cap},
+        tc::EpiRankScreen{scale, thr_score, thr_idx_local, ranks_i2t, w.col_val, w.col_thr_idx, ranks_t2i, w.band, w.amb, w.amb_count, cap},
         st);
     if (rc) return rc;
-    // ... pass 3 (exact): the listed pairs are gathered into a [P, D] x [P, D]^T problem whose diagonal tiles the 3xTF32 kernel
-    // computes -- the same arithmetic, k order and epilogue scaling as pass 1, hence the same bits as the materialised matrix
+    // ... decided exactly: the listed pairs are gathered into a [P, D] x [P, D]^T problem whose diagonal tiles the 3xTF32 kernel
+    // computes -- the same arithmetic, k order and epilogue scaling as phase A, hence the same bits as the materialised matrix
     launch_k(decide_prepare_kernel, 64, 256, 0, st, (const int32_t*)w.amb_count, cap, cap / 128, tiles, w.n_pairs, w.tile_list,
              w.tile_count, w.ident_list, w.fb_count);
     launch_k(gather_pairs_kernel, num_sms() * 4, 256, 0, st, (const tc::AmbiguousPair*)w.amb, (const int32_t*)w.n_pairs, img, txt, D, w.Ag,
              w.Bg);
     const GemmOperands gg = gemm_ops(w.Ag, D, w.Bg, D, cap, cap, D);
     rc = tc::launch<true, true, 3>(gg, 1,
-                                   tc::EpiPairDecide{scale, w.amb, w.n_pairs, w.row_thr, w.row_thr_idx, ranks_i2t, w.col_val, w.col_thr_idx,
+                                   tc::EpiPairDecide{scale, w.amb, w.n_pairs, thr_score, thr_idx_local, ranks_i2t, w.col_val, w.col_thr_idx,
                                                      ranks_t2i},
                                    st, w.tile_list, w.tile_count);
     if (rc) return rc;
     // list overflow (far more near-ties than the capacity provides for): recount everything exactly
     launch_k(fallback_reset_kernel, num_sms(), 256, 0, st, (const int*)w.fb_count, I, T, ranks_i2t, ranks_t2i);
-    rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankCount{scale, w.row_thr, w.row_thr_idx, ranks_i2t, w.col_val, w.col_thr_idx, ranks_t2i}, st,
+    rc = tc::launch<true, true, 3>(g, 1, tc::EpiRankCount{scale, thr_score, thr_idx_local, ranks_i2t, w.col_val, w.col_thr_idx, ranks_t2i}, st,
                                    w.ident_list, w.fb_count);
     if (rc) return rc;
   }
-  launch_k(rank_finalize_kernel, ceil_div(nmax, 256), 256, 0, st, (const int32_t*)w.row_thr_idx, (const int32_t*)w.col_thr_idx, I, T,
-           ranks_i2t, ranks_t2i);
-  return check_launch("sim_rank_fused");
+  launch_k(rank_finalize_kernel, ceil_div(nmax, 256), 256, 0, st, thr_score, (const int32_t*)w.col_thr_idx, I, T, invalid_row_rank, ranks_i2t,
+           ranks_t2i);
+  return check_launch("sim_rank_fused_count");
+}
+
+int sim_rank_fused(const float* img, const float* txt, int I, int T, int D, float scale, const int32_t* txt2img,
+                   const int32_t* gt_ptr, const int32_t* gt_idx, int nnz, int32_t* ranks_i2t, int32_t* ranks_t2i,
+                   void* workspace, cudaStream_t st) {
+  FusedWs w;
+  carve_fused(w, workspace, I, T, D, nnz, D % 8 == 0);
+  int rc = sim_rank_fused_candidates(img, txt, I, T, D, scale, txt2img, gt_ptr, gt_idx, nnz, 0, w.row_thr, w.row_thr_idx, workspace, st);
+  if (rc) return rc;
+  return sim_rank_fused_count(img, txt, I, T, D, scale, w.row_thr, w.row_thr_idx, nnz, T, ranks_i2t, ranks_t2i, workspace, st);
 }
 
 // Keep each row's k largest entries, everything else := fill (epoch_original.py:95-105).

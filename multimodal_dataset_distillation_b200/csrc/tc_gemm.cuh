@@ -266,7 +266,8 @@ struct EpiRankExtract {
   __device__ __forceinline__ float apply(float a, float, float) const { return a; }
   const int32_t* gt_ptr; const int32_t* gt_idx; float* gt_val;      // img2txt CSR and its score slots
   const int32_t* col_gt; float* col_val;                            // txt2img and its score slots
-};
+  int col_offset;                                                   // gt_idx holds GLOBAL caption ids; this product covers
+};                                                                  // captions [col_offset, col_offset + N) (caption shards)
 struct EpiRankCount {
   static constexpr int kKind = kEpiRankCount;
   float alpha;
@@ -473,7 +474,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     };
     if constexpr (Epi::kKind == kEpiRankScreen) {
       band = *epi.band;
-      if (my_m < M && epi.row_thr_idx[my_m] >= 0) { const float t = epi.row_thr[my_m]; rhi = t + band; rlo = t - band; }
+      if (my_m < M) { const float t = epi.row_thr[my_m]; rhi = t + band; rlo = t - band; }      // +inf: no ground truth
       cthr_next = col_thr_of(c_begin);
     }
 #pragma unroll 1
@@ -495,7 +496,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         for (int j = 0; j < 32; ++j) v[j] *= coef;               // the score, exactly as EpiScale would have stored it
       }
       if constexpr (Epi::kKind == kEpiRankCount) {
-        if (my_m < M && row_thr_idx >= 0) {
+        if (my_m < M) {                        // (a row without ground truth carries thr = +inf: nothing is ahead of it)
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + c + j;
@@ -556,7 +557,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         // rows: the ground-truth captions of image my_m that fall into this 32-column chunk
         if (my_m < M) {
           for (int e = epi.gt_ptr[my_m]; e < epi.gt_ptr[my_m + 1]; ++e) {
-            const int cidx = epi.gt_idx[e] - (n0 + c);
+            const int cidx = epi.gt_idx[e] - epi.col_offset - (n0 + c);
             if (cidx >= 0 && cidx < 32) epi.gt_val[e] = stage[lane * LDS + cidx];
           }
         }

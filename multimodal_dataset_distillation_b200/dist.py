@@ -123,6 +123,31 @@ def sharded_ranks(img, txt_shard, lo: int, txt2img_shard, img2txt_ptr, img2txt_i
     return counts, ranks_t
 
 
+def sharded_ranks_fused(img, txt_shard, lo: int, txt2img_shard, img2txt_ptr, img2txt_idx, scale: float, n_txt_total: int,
+                        group=None, shard=None):
+    """sharded_ranks without a score matrix: every rank runs the fused tensor-core ranking (ops.FusedRankShard: exact 3xTF32
+    candidates, bf16x3-screened count with exact decisions) on its caption shard; the exchange is the same as above -- all-gather
+    of one (score, global index) candidate per image and shard, merge, all-reduce of the int32 counts.  Returns
+    (ranks_i2t[I] -- identical on every rank, ranks_t2i[T_r]).  Pass a prepared ``shard`` to reuse its workspace across calls."""
+    from . import ops
+    sh = shard if shard is not None else ops.FusedRankShard(img, txt_shard, lo, txt2img_shard, img2txt_ptr, img2txt_idx, scale)
+    cand_s, cand_i = sh.candidates()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        all_s = [torch.empty_like(cand_s) for _ in range(world)]
+        all_i = [torch.empty_like(cand_i) for _ in range(world)]
+        dist.all_gather(all_s, cand_s, group=group)
+        dist.all_gather(all_i, cand_i, group=group)
+        thr_s, thr_i = merge_candidates(torch.stack(all_s), torch.stack(all_i))
+    else:
+        thr_s, thr_i = merge_candidates(cand_s.unsqueeze(0), cand_i.unsqueeze(0))
+    counts, ranks_t = sh.count(thr_s, thr_i, 0)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    ranks_i = torch.where(thr_i >= 0, counts, torch.full_like(counts, int(n_txt_total)))      # no ground truth: never retrieved
+    return ranks_i, ranks_t
+
+
 def sharded_result(ranks_i2t, ranks_t2i_shard, n_txt_total: int, group=None) -> dict:
     """Recall dict of epoch.py:227-244 from sharded ranks (one 3-int all-reduce for the caption side)."""
     ks = torch.tensor([1, 5, 10], device=ranks_i2t.device)

@@ -233,6 +233,46 @@ def sim_rank_fused(img: torch.Tensor, txt: torch.Tensor, txt2img: torch.Tensor, 
     return r1, r2
 
 
+class FusedRankShard:
+    """Caption-shard form of sim_rank_fused (multi-GPU retrieval): phase A ``candidates()``, exchange, phase B ``count()``.
+
+    img [I, D] replicated; txt_shard [T_r, D] = captions [lo, lo + T_r) of the full set; txt2img_shard int32 [T_r];
+    img2txt CSR with GLOBAL caption ids.  The workspace is owned by the object and shared by both phases.
+    """
+
+    def __init__(self, img, txt_shard, lo: int, txt2img_shard, img2txt_ptr, img2txt_idx, scale: float = LOGIT_SCALE_EVAL):
+        self.img, self.txt = _req(img, "img"), _req(txt_shard, "txt_shard")
+        self.t2i = _req(txt2img_shard, "txt2img_shard", torch.int32)
+        self.ptr, self.idx = _req(img2txt_ptr, "img2txt_ptr", torch.int32), _req(img2txt_idx, "img2txt_idx", torch.int32)
+        self.lo, self.scale = int(lo), float(scale)
+        self.I, self.T, self.D = self.img.shape[0], self.txt.shape[0], self.img.shape[1]
+        self.nnz = self.idx.numel()
+        need = lib().vldd_sim_rank_fused_workspace_bytes(self.I, self.T, self.D, self.nnz)
+        self.ws = torch.empty(need, dtype=torch.uint8, device=self.img.device)
+
+    def candidates(self):
+        """(score[I] f32, +inf where the image has no ground truth in this shard; global caption id[I] i32, -1 = none)."""
+        cs = torch.empty(self.I, dtype=torch.float32, device=self.img.device)
+        ci = torch.empty(self.I, dtype=torch.int32, device=self.img.device)
+        check(lib().vldd_sim_rank_fused_candidates(_ptr(self.img), _ptr(self.txt), self.I, self.T, self.D, self.scale, _ptr(self.t2i),
+                                                   _ptr(self.ptr), _ptr(self.idx), self.nnz, self.lo, _ptr(cs), _ptr(ci), _ptr(self.ws),
+                                                   self.ws.numel(), _stream()), "sim_rank_fused_candidates")
+        return cs, ci
+
+    def count(self, thr_score: torch.Tensor, thr_idx_global: torch.Tensor, invalid_row_rank: int = 0):
+        """(row_counts[I], ranks_t2i[T_r]) for the merged thresholds (score +inf / index -1: no ground truth anywhere)."""
+        ts = _req(thr_score, "thr_score")
+        ti = _req(thr_idx_global, "thr_idx_global", torch.int32)
+        ts = torch.where(ti >= 0, ts, torch.full_like(ts, float("inf"))).contiguous()
+        tl = (ti - self.lo).to(torch.int32).contiguous()
+        rc = torch.empty(self.I, dtype=torch.int32, device=self.img.device)
+        rt = torch.empty(self.T, dtype=torch.int32, device=self.img.device)
+        check(lib().vldd_sim_rank_fused_count(_ptr(self.img), _ptr(self.txt), self.I, self.T, self.D, self.scale, _ptr(ts), _ptr(tl),
+                                              self.nnz, int(invalid_row_rank), _ptr(rc), _ptr(rt), _ptr(self.ws), self.ws.numel(),
+                                              _stream()), "sim_rank_fused_count")
+        return rc, rt
+
+
 RESULT_KEYS = ("txt_r1", "txt_r5", "txt_r10", "txt_r_mean", "img_r1", "img_r5", "img_r10", "img_r_mean", "r_mean")
 
 

@@ -146,3 +146,42 @@ def test_screened_count_is_bit_identical_to_materialised(I, C, D, quant, env):
     r = subprocess.run([sys.executable, "-c", SCREEN_CHILD.format(root=ROOT, I=I, C=C, D=D, quant=quant)],
                        env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.parametrize("I,C,D,shards,quant", [(600, 5, 768, 2, False), (600, 5, 768, 3, True), (257, 3, 64, 4, True)])
+def test_caption_sharded_fused_ranking_equals_single_call(I, C, D, shards, quant):
+    """Multi-GPU retrieval without the GPUs: the caption axis cut into `shards` pieces, each through the shard form of the fused
+    ranking (ops.FusedRankShard: candidates -> dist.merge_candidates -> counts, summed) == one vldd_sim_rank_fused call over
+    everything == the oracle on the materialised scores.  (The collectives themselves are covered by tests/test_dist_gloo.py
+    and by bench.py at N > 1, which asserts the same equality across real ranks.)"""
+    from multimodal_dataset_distillation_b200 import ops, dist as Dm
+    img, txt = RR.synthetic_retrieval(I, C, D, seed=5)
+    if quant:
+        img, txt = (np.round(img * 8) / 8).astype(np.float32), (np.round(txt * 8) / 8).astype(np.float32)
+    T = I * C
+    txt2img, img2txt = RR.flickr_maps(I, C)
+    del img2txt[3]
+    img2txt[3] = []                                           # an image without any caption: rank T by convention
+    t2i, ptr, idx = ops.maps_to_arrays(txt2img, img2txt, I, T)
+    dev = lambda a: torch.from_numpy(a).cuda()
+    img_d, txt_d, t2i_d, ptr_d, idx_d = dev(img), dev(txt), dev(t2i), dev(ptr), dev(idx)
+    f1, f2 = ops.sim_rank_fused(img_d, txt_d, t2i_d, ptr_d, idx_d, SCALE)
+    parts = []
+    for r in range(shards):
+        lo, hi = Dm.shard_bounds(T, shards, r)
+        parts.append(ops.FusedRankShard(img_d, txt_d[lo:hi].contiguous(), lo, t2i_d[lo:hi].contiguous(), ptr_d, idx_d, SCALE))
+    cands = [p.candidates() for p in parts]
+    thr_s, thr_i = Dm.merge_candidates(torch.stack([c[0] for c in cands]), torch.stack([c[1] for c in cands]))
+    outs = [p.count(thr_s, thr_i, 0) for p in parts]
+    counts = sum(o[0] for o in outs)
+    r1 = torch.where(thr_i >= 0, counts, torch.full_like(counts, T))
+    r2 = torch.cat([o[1] for o in outs])
+    assert torch.equal(r1, f1) and torch.equal(r2, f2)
+    assert int(f1[3]) == T
+    S = ops.sim_scores(img_d, txt_d, SCALE, want_t2i=False)[0].cpu().numpy()
+    ref_maps = dict(img2txt)
+    ref_maps[3] = [0]                                          # (the oracle needs some caption for image 3: ignored below)
+    ref = RR.ranks_i2t(S, ref_maps)
+    keep = np.arange(I) != 3
+    assert np.array_equal(f1.cpu().numpy()[keep], ref[keep])
+    assert np.array_equal(f2.cpu().numpy(), RR.ranks_t2i(np.ascontiguousarray(S.T), txt2img))
