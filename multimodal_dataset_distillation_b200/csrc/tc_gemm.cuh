@@ -467,11 +467,21 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     auto col_thr_of = [&](int c) {
       const int n = n0 + c + lane;
       float t = INFINITY;
-      if constexpr (Epi::kKind == kEpiRankScreen) {
+      if constexpr (Epi::kKind == kEpiRankScreen || Epi::kKind == kEpiRankCount) {
         if (c < c_end && n < N && epi.col_thr_idx[n] >= 0) t = epi.col_thr[n];
       }
       return t;
     };
+    [[maybe_unused]] auto col_idx_of = [&](int c) {
+      const int n = n0 + c + lane;
+      int t = -1;
+      if constexpr (Epi::kKind == kEpiRankCount) {
+        if (c < c_end && n < N) t = epi.col_thr_idx[n];
+      }
+      return t;
+    };
+    [[maybe_unused]] int cidx_next = -1;
+    if constexpr (Epi::kKind == kEpiRankCount) { cthr_next = col_thr_of(c_begin); cidx_next = col_idx_of(c_begin); }
     if constexpr (Epi::kKind == kEpiRankScreen) {
       band = *epi.band;
       if (my_m < M) { const float t = epi.row_thr[my_m]; rhi = t + band; rlo = t - band; }      // +inf: no ground truth
@@ -495,16 +505,29 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= coef;               // the score, exactly as EpiScale would have stored it
       }
+      [[maybe_unused]] float cthr = INFINITY;
+      [[maybe_unused]] int cidx = -1;
       if constexpr (Epi::kKind == kEpiRankCount) {
+        // branch-free hot loop: #{v > thr} and #{v == thr}; only a chunk with an exact tie runs the index tie-break
+        cthr = cthr_next; cidx = cidx_next;
+        cthr_next = col_thr_of(c + c_step); cidx_next = col_idx_of(c + c_step);
         if (my_m < M) {                        // (a row without ground truth carries thr = +inf: nothing is ahead of it)
+          const int jmax = N - (n0 + c);
+          int gt = 0, eq = 0;
+          if (jmax >= 32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c + j;
-            row_count += (n < N) && ((v[j] > row_thr) || (v[j] == row_thr && n < row_thr_idx));
+            for (int j = 0; j < 32; ++j) { gt += v[j] > row_thr; eq += v[j] == row_thr; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { gt += (j < jmax) && v[j] > row_thr; eq += (j < jmax) && v[j] == row_thr; }
+          }
+          row_count += gt;
+          if (eq) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) row_count += (j < jmax) && v[j] == row_thr && (n0 + c + j) < row_thr_idx;
           }
         }
       }
-      [[maybe_unused]] float cthr = INFINITY;
       if constexpr (Epi::kKind == kEpiRankScreen) {
         cthr = cthr_next;
         cthr_next = col_thr_of(c + c_step);
@@ -603,20 +626,19 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         }
       } else {   // kEpiRankCount, column direction: lane j counts the 32 rows of this quadrant for caption n
         const int n = n0 + c + lane;
-        if (n < N) {
-          const float thr = epi.col_thr[n];
-          const int tidx = epi.col_thr_idx[n];
-          if (tidx >= 0) {
-            int cnt = 0;
-            const int mbase = m0 + quad * 32;
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              const float sv_ = stage[rr * LDS + lane];
-              cnt += (mbase + rr < M) && ((sv_ > thr) || (sv_ == thr && mbase + rr < tidx));
-            }
-            if (cnt) atomicAdd(epi.col_cnt + n, cnt);
-          }
+        const int mbase = m0 + quad * 32;
+        const int nvalid = min(32, M - mbase);
+        int gt = 0, eq = 0;                    // cthr = +inf: no ground truth / past the last caption -> both stay 0
+        if (nvalid == 32) {
+#pragma unroll 16
+          for (int rr = 0; rr < 32; ++rr) { const float sv_ = stage[rr * LDS + lane]; gt += sv_ > cthr; eq += sv_ == cthr; }
+        } else {
+          for (int rr = 0; rr < nvalid; ++rr) { const float sv_ = stage[rr * LDS + lane]; gt += sv_ > cthr; eq += sv_ == cthr; }
         }
+        if (eq) {
+          for (int rr = 0; rr < nvalid; ++rr) gt += stage[rr * LDS + lane] == cthr && mbase + rr < cidx;
+        }
+        if (gt) atomicAdd(epi.col_cnt + n, gt);
       }
     }
     if constexpr (Epi::kKind == kEpiRankCount || Epi::kKind == kEpiRankScreen) {
