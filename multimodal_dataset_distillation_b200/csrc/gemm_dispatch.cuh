@@ -75,10 +75,12 @@ template <bool AK, bool BKm>
 inline int gemm_partial(const GemmOperands& g, float* part, int* splits, cudaStream_t st, int old_mask = 0) {
   const int Kt = g.K0 + g.K1;
   if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) {
+#ifdef VLDD_DEV_GEMM_SWITCH
     if (tf32_single_pass()) {
       *splits = tc::pick_splits(g.M, g.N, Kt);
       return tc::launch<AK, BKm, 1, tc::EpiPartial>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st, nullptr, nullptr, old_mask);
     }
+#endif
     *splits = tc_partial_splits(g);
     if (narrow_tile(g))
       return tc::launch<AK, BKm, 3, tc::EpiPartial, VLDD_STAGES_PARTIAL, 64>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st, nullptr, nullptr, old_mask);
@@ -92,7 +94,9 @@ inline int gemm_partial(const GemmOperands& g, float* part, int* splits, cudaStr
 template <bool AK, bool BKm>
 inline int gemm_store(const GemmOperands& g, float* C, int ldc, float alpha, cudaStream_t st, int old_mask = 0) {
   if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) {
+#ifdef VLDD_DEV_GEMM_SWITCH
     if (tf32_single_pass()) return tc::launch<AK, BKm, 1>(g, 1, tc::EpiScale{C, ldc, alpha}, st, nullptr, nullptr, old_mask);
+#endif
     return tc::launch<AK, BKm, 3>(g, 1, tc::EpiScale{C, ldc, alpha}, st, nullptr, nullptr, old_mask);
   }
   launch_gemm<AK, BKm>(g, 1, nullptr, EpiStore{C, ldc, alpha}, st);
@@ -102,8 +106,10 @@ inline int gemm_store(const GemmOperands& g, float* C, int ldc, float alpha, cud
 template <bool AK, bool BKm>
 inline int gemm_axpy(const GemmOperands& g, const float* src, float* dst, int ld, const float* lr, cudaStream_t st,
                      int old_mask = 0) {
+#ifdef VLDD_DEV_GEMM_SWITCH
   if (tc_enabled() && tc::gemm_ok<AK, BKm>(g) && tf32_single_pass())
     return tc::launch<AK, BKm, 1, tc::EpiAxpyTC>(g, 1, tc::EpiAxpyTC{src, dst, ld, lr}, st, nullptr, nullptr, old_mask);
+#endif
   if (tc_enabled() && tc::gemm_ok<AK, BKm>(g)) {
     // 128 x 96 tiles when they divide N: 2304 x 2304 -> 432 work items = 2.92 per SM (three even rounds) instead of
     // 324 = 2.19 (28 CTAs run a third round while 120 idle)
