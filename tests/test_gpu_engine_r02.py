@@ -163,3 +163,45 @@ def test_step_fast_refuses_to_step_on_nan_loss():
     loss = eng.step_fast(0, 0)
     assert not torch.isfinite(loss).item() and int(eng.ws.skipped) == 1
     assert torch.equal(eng.U.detach(), U0) and torch.equal(eng.Y.detach(), Y0)
+
+
+def test_segment_cache_lru_uploads_only_misses():
+    """distill.SegmentCache: device-side LRU of uploaded expert snapshots (the reference re-uploads theta_start / theta_target
+    every iteration, distill.py:466-476): hits copy nothing, eviction is least-recently-used, contents are always right."""
+    from multimodal_dataset_distillation_b200 import distill
+    host = torch.randn(3, 5, 1000)                       # 3 experts x 5 snapshots
+    cache = distill.SegmentCache(host, "cuda", capacity=4)
+    P4 = 1000 * 4
+
+    def fetch(e, s, k=1):
+        cache.prefetch(e, s, k)
+        sl = cache.get()
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(sl["th0"].cpu(), host[e, s]) and torch.equal(sl["tgt"].cpu(), host[e, s + k])
+        cache.release(sl)
+
+    fetch(0, 0)                                          # misses: (0,0), (0,1)
+    assert cache.h2d_bytes == 2 * P4 and (cache.hits, cache.misses) == (0, 2)
+    fetch(0, 1)                                          # (0,1) hit, (0,2) miss
+    assert cache.h2d_bytes == 3 * P4 and (cache.hits, cache.misses) == (1, 3)
+    fetch(0, 0)                                          # both resident
+    assert cache.h2d_bytes == 3 * P4 and cache.hits == 3
+    fetch(1, 0)                                          # 2 misses: 5 snapshots wanted, capacity 4 -> (0,2), the LRU, is evicted
+    assert len(cache.slots) == 4 and (0, 2) not in cache.slots and (0, 0) in cache.slots
+    fetch(0, 1)                                          # (0,1) still there, (0,2) comes back
+    assert torch.equal(cache.slots[(0, 2)]["buf"].cpu(), host[0, 2])
+    for i in range(12):                                  # churn through everything: contents stay right (asserted in fetch)
+        fetch(i % 3, (i * 2) % 4)
+
+
+def test_distill_main_writes_the_distilled_set(tmp_path, capsys):
+    """distill.main ends with {save_path}/distilled_{it}.pt holding U, Y and the learned student learning rates."""
+    from multimodal_dataset_distillation_b200 import distill
+    args = distill.parse_args(["--synthetic", "--num_queries", "8", "--mini_batch_size", "8", "--syn_steps", "1", "--expert_epochs", "1",
+                               "--max_start_epoch", "2", "--Iteration", "3", "--lr_img", "1", "--lr_txt", "1", "--save_path",
+                               str(tmp_path / "out"), "--student_dropout", "0.1"])
+    eng = distill.main(args)
+    blob = torch.load(eng.saved_to)
+    assert blob["iteration"] == 3 and tuple(blob["U"].shape) == (8, 2304) and tuple(blob["Y"].shape) == (8, 768)
+    assert torch.equal(blob["U"], eng.U.detach().cpu()) and blob["syn_lr_txt"] == float(eng.syn_lr_txt.detach())
+    assert "iter = 0000" in capsys.readouterr().out
