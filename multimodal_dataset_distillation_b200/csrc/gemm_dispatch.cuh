@@ -63,11 +63,12 @@ inline int max_splits(int M, int N, int Ktot) {
 // The main loop is bound by the shared-memory port: per k-block the A tile crosses it twice (TMA write, splitter read) and the
 // B tile six times (TMA write, splitter read, B_lo write, three MMA reads) = 32 KB + 6 * BN * 128 B at 128 B/clk, i.e.
 // 0.50 us at BN = 128 and 0.32 us at BN = 64, and a 64-wide tile needs half the K splits to fill one wave, so its consumer
-// sums half as many slabs: p (K = 768) 10.1 -> 8.8 us, S 10.9 -> 9.8, dY 12.2 -> 11.0, f / dh (K = 2304) 13.2 -> 13.1.
-// Only the long-K, wide-N products (K >= 4608: f-tangent, dh-tangent) keep 128 columns (18.1 vs 19.1 us): with 36 k-blocks per
-// CTA the re-read of the activation tile by twice as many n-tiles outweighs the slabs.
+// sums half as many slabs: p (K = 768) 10.1 -> 8.8 us, S 10.9 -> 9.8, dY (N = 768) 12.2 -> 11.0.  The wide-N products with
+// K >= 2304 keep 128 columns: f / dh (K = 2304) are a tie as a pair (13.2 vs 13.1 us) but the GEMM alone is 9.1 vs 10.1 us, and the
+// K = 4608 tangent products lose (18.1 vs 19.1 us): with 18-36 k-blocks per CTA the re-read of the activation tile by twice as many
+// n-tiles outweighs the slabs.
 // (one M tile only: with many M tiles there is no split-K to save and the wider tile does more MMA work per byte of shared memory)
-inline bool narrow_tile(const GemmOperands& g) { return g.M <= tc::BM && !(g.K0 + g.K1 >= 4096 && g.N >= 1024); }
+inline bool narrow_tile(const GemmOperands& g) { return g.M <= tc::BM && !(g.K0 + g.K1 >= 2048 && g.N >= 1024); }
 inline int tc_partial_splits(const GemmOperands& g) { return tc::pick_splits(g.M, g.N, g.K0 + g.K1, narrow_tile(g) ? 64 : 128); }
 
 // partial slabs: part[z][M*N], returns the split count through *splits
