@@ -39,6 +39,33 @@ def init_from_env(backend: str | None = None):
     return rank, world, local
 
 
+def bind_to_local_numa(device_index: int) -> list[int] | None:
+    """Best effort: restrict this process to the CPUs of the NUMA node its GPU hangs off, so that pinned staging buffers
+    allocated AFTERWARDS are first-touched on that node and the per-step host->device copies of 8 ranks do not all cross the
+    socket interconnect (the reference keeps expert trajectories in host memory and uploads a segment every iteration,
+    distill.py:466-476).  Returns the CPU list it bound to, or None when the topology cannot be read (then nothing changes)."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = []
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
     """Contiguous balanced shard [lo, hi) of n items; the first n % world shards get one extra item."""
     base, extra = divmod(n, world)

@@ -531,6 +531,8 @@ def main(args):
     # replicated synthetic set; gradients are all-reduced (NCCL) before the identical update on every rank
     rank, world, local = dist_mod.init_from_env()
     torch.cuda.set_device(local)
+    if world > 1:
+        dist_mod.bind_to_local_numa(local)                                   # host-side staging next to this rank's GPU
     dev = torch.device("cuda", local)
     args.device = str(dev)                                                   # distill.py:214
     N = int(args.num_queries)
@@ -555,8 +557,25 @@ def main(args):
     eng.eval_history = []
     if rank == 0:
         os.makedirs(save_path, exist_ok=True)                                # fail now, not after the last iteration
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-    it = 0
+    # distill.py:599-600: a NaN loss ends the run BEFORE the update is applied.  The update kernel itself refuses to step on a
+    # non-finite loss (device-side, every iteration); the host reads every iteration's loss too, one iteration late, so that
+    # enqueueing iteration i+1 overlaps the GPU's work on iteration i instead of waiting for a 4-byte result.
+    loss_bufs = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_evs = [torch.cuda.Event() for _ in range(2)]
+    stamp = lambda: datetime.datetime.now().strftime("[%Y-%m-%d %H:%M:%S]")
+
+    def read_loss(j):                       # loss of iteration j; True when the run has to stop
+        loss_evs[j % 2].synchronize()
+        v = float(loss_bufs[j % 2])
+        if math.isnan(v) or math.isinf(v):
+            if rank == 0:
+                print("%s iter = %04d, loss = %s: stopping, synthetic set left at the last finite iteration" % (stamp(), j, v))
+            return True
+        if j % 10 == 0 and rank == 0:
+            print("%s iter = %04d, loss = %.4f" % (stamp(), j, v))
+        return False
+
+    it, stop = 0, False
     for it in range(int(args.Iteration) + 1):
         if it in eval_it_pool:                                               # distill.py:293-330
             if rank == 0:
@@ -566,19 +585,13 @@ def main(args):
             if world > 1:
                 torch.distributed.barrier()
         loss = eng.iteration()
-        # distill.py:599-600: a NaN loss ends the run BEFORE the update is applied.  The update kernel itself refuses to step
-        # on a non-finite loss (device-side, every iteration); the host looks at the loss every iteration too -- one 4-byte
-        # read that the engine's ~2 ms of queued work hides.
-        loss_host.copy_(loss.detach().reshape(()), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        v = float(loss_host)
-        if math.isnan(v) or math.isinf(v):
-            if rank == 0:
-                print("%s iter = %04d, loss = %s: stopping, synthetic set left at the last finite iteration" % (
-                    datetime.datetime.now().strftime("[%Y-%m-%d %H:%M:%S]"), it, v))
+        loss_bufs[it % 2].copy_(loss.detach().reshape(()), non_blocking=True)
+        loss_evs[it % 2].record()
+        if it > 0 and read_loss(it - 1):
+            stop = True
             break
-        if it % 10 == 0 and rank == 0:
-            print("%s iter = %04d, loss = %.4f" % (datetime.datetime.now().strftime("[%Y-%m-%d %H:%M:%S]"), it, v))
+    if not stop:
+        read_loss(it)
     if rank == 0:
         near = nearest_neighbor(sentences, eng.Y.detach(), train_text) if sentences is not None else None
         eng.saved_to = save_distilled(eng, save_path, it, near)
