@@ -83,6 +83,13 @@ inline int gemm_partial(const GemmOperands& g, float* part, int* splits, cudaStr
     }
 #endif
     *splits = tc_partial_splits(g);
+#ifndef VLDD_NO_TMA_STORE
+    if (tc::slabs_tma_ok(part, g.M, g.N)) {          // slabs leave through TMA stores (one instruction per 32 x 32 block)
+      if (narrow_tile(g))
+        return tc::launch<AK, BKm, 3, tc::EpiPartialTma, VLDD_STAGES_PARTIAL, 64>(g, *splits, tc::EpiPartialTma{part, (long long)g.M * g.N}, st, nullptr, nullptr, old_mask);
+      return tc::launch<AK, BKm, 3, tc::EpiPartialTma, VLDD_STAGES_PARTIAL>(g, *splits, tc::EpiPartialTma{part, (long long)g.M * g.N}, st, nullptr, nullptr, old_mask);
+    }
+#endif
     if (narrow_tile(g))
       return tc::launch<AK, BKm, 3, tc::EpiPartial, VLDD_STAGES_PARTIAL, 64>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st, nullptr, nullptr, old_mask);
     return tc::launch<AK, BKm, 3, tc::EpiPartial, VLDD_STAGES_PARTIAL>(g, *splits, tc::EpiPartial{part, (long long)g.M * g.N}, st, nullptr, nullptr, old_mask);

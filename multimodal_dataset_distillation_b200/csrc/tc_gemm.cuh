@@ -20,6 +20,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vldd {
@@ -37,7 +39,7 @@ constexpr int kBaseThreads = 192;                   // producer, MMA, 4 splitter
 // Stage layout (kSplit == 3):  K-major A  -> [A | B | B_lo]            48 KB x 4 stages; A_hi / A_lo live in TMEM
 //                              MN-major A -> [A | B | A_lo | B_lo]     64 KB x 3 stages
 //               (kSplit == 1):              [A | B]                    32 KB x 6 stages
-template <int kSplit, bool A_TMEM, int kStagesT = 0, int BN = 128, int kEpiWarps = 4>
+template <int kSplit, bool A_TMEM, int kStagesT = 0, int BN = 128, int kEpiWarps = 4, bool kTmaEpi = false>
 struct Cfg {
   static_assert(kEpiWarps == 4 || kEpiWarps == 8, "one or two epilogue warps per TMEM lane quadrant");
   static constexpr int kThreads = kBaseThreads + 32 * kEpiWarps;
@@ -52,7 +54,10 @@ struct Cfg {
       kSplit == 6 ? (BN > 128 ? 2 : 3)
                   : (kSplit == 3 ? (A_TMEM ? (BN <= 64 ? 6 : (BN <= 96 ? 5 : 4)) : 3) : 6) - (kEpiWarps == 8 ? 1 : 0);
   static constexpr int kStages = kStagesT > 0 ? kStagesT : kStagesDefault;
-  static constexpr int kEpiBytes = kEpiWarps * 32 * 36 * 4;               // private transpose patches of the epilogue warps
+  // private patches of the epilogue warps: 32 x 36 floats (padded, conflict-free transposed reads) for the register -> global
+  // epilogues; 32 x 32 floats in the 128-byte-swizzled box layout (1 KB aligned) when the tile leaves through a TMA store
+  static constexpr int kEpiPatchBytes = kTmaEpi ? 4096 : 32 * 36 * 4;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiPatchBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kAccStride = BN;                                   // accumulator a lives in TMEM columns [a*BN, a*BN + BN)
   static constexpr uint32_t kTmemA = 2 * BN;                              // first column of the staged A operand (hi | lo per stage)
@@ -119,6 +124,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
       : "memory");
 }
+// TMA store of a [1 x 32 x 32] fp32 box (slab z, rows y.., columns x..) from shared memory; rows / columns past the tensor's extent
+// are clipped by the hardware
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(x),
+               "r"(y), "r"(z)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -223,7 +238,7 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
 }
 
 // ---- epilogues -------------------------------------------------------------------------------------------
-enum EpiKind { kEpiStore = 0, kEpiRankExtract = 1, kEpiRankCount = 2, kEpiRankScreen = 3, kEpiPairDecide = 4 };
+enum EpiKind { kEpiStore = 0, kEpiRankExtract = 1, kEpiRankCount = 2, kEpiRankScreen = 3, kEpiPairDecide = 4, kEpiStoreTma = 5 };
 
 struct EpiPartial {   // raw fp32 tile -> slab z of [splits][M*N]
   static constexpr int kKind = kEpiStore;
@@ -233,6 +248,17 @@ struct EpiPartial {   // raw fp32 tile -> slab z of [splits][M*N]
   __device__ __forceinline__ float apply(float acc, float, float) const { return acc; }
   __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
 };
+struct EpiPartialTma {   // the same slabs, written by TMA stores (Maps::c: 3-D map {N, M, splits}, box 32 x 32 x 1, SWIZZLE_128B): each
+  static constexpr int kKind = kEpiStoreTma;   // warp parks a 32 x 32 block in shared memory and one instruction ships it; rows >= M
+  static constexpr bool kTmaStore = true;      // are clipped by the hardware.  Needs N % 4 == 0 and 16-byte aligned slabs.
+  float* part; long long stride;
+  __device__ __forceinline__ float* row_ptr(int m, int N, int z) const { return part + (size_t)z * stride + (size_t)m * N; }
+  __device__ __forceinline__ float coef() const { return 1.0f; }
+  __device__ __forceinline__ float apply(float acc, float, float) const { return acc; }
+  __device__ __forceinline__ const float* src_row(int) const { return nullptr; }
+};
+template <class E, class = void> struct epi_uses_tma : std::false_type {};
+template <class E> struct epi_uses_tma<E, std::void_t<decltype(E::kTmaStore)>> : std::bool_constant<E::kTmaStore> {};
 struct EpiScale {     // C = alpha * acc
   static constexpr int kKind = kEpiStore;
   float* C; int ldc; float alpha;
@@ -330,6 +356,7 @@ __constant__ uint32_t g_dbg[4];   // {lbo, sbo, step, unused} overrides for MN-m
 
 struct Maps {
   CUtensorMap a0, b0, a1, b1;
+  CUtensorMap c;      // output map of the TMA-store epilogue (EpiPartialTma), unused otherwise
 };
 
 // ---- the kernel ----------------------------------------------------------------------------------------
@@ -344,11 +371,12 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
                 "N tile: 64, 96 or 128 (32-column epilogue chunks, MN-major boxes); up to 256 for the bf16 mode");
   static_assert(kSplit != 6 || (A_KMAJOR && B_KMAJOR), "bf16x3 operands are K-major");
   constexpr bool A_TMEM = kSplit == 3;                 // hi/lo of the A tile are staged in tensor memory (either major)
-  using C = Cfg<kSplit, A_TMEM, kStagesT, BN, kEpiWarps>;
+  using C = Cfg<kSplit, A_TMEM, kStagesT, BN, kEpiWarps, epi_uses_tma<Epi>::value>;
   constexpr int TILE_B = C::kTileB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* epi_stage = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);        // 4 warps x 32 x 36 floats
+  float* epi_stage = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);        // one patch per epilogue warp
+  constexpr int kPatchFloats = C::kEpiPatchBytes / 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kEpiBytes);
   uint64_t* full = bars;                       // TMA landed
   uint64_t* ready = bars + C::kStages;         // split done (kSplit == 3 only)
@@ -501,7 +529,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         tc_fence_before();
         mbar_arrive(&tmem_empty[acc]);
       }
-      if constexpr (Epi::kKind != kEpiStore) {
+      if constexpr (Epi::kKind != kEpiStore && Epi::kKind != kEpiStoreTma) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= coef;               // the score, exactly as EpiScale would have stored it
       }
@@ -548,12 +576,32 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
             if (j < jmax && v[j] >= rlo && !(v[j] > rhi)) epi.push(my_m, n0 + c + j, 1);
         }
       }
-      __syncwarp();
+      if constexpr (Epi::kKind == kEpiStoreTma) {
+        // the 32 x 32 block goes to shared memory in the box layout of the output map (row = 128 bytes, 16-byte chunk q of row r
+        // at q ^ (r & 7)) and leaves with ONE TMA store; the previous chunk's store must have finished READING the patch first
+        if (elect_one()) bulk_wait_read0();
+        __syncwarp();
+        uint8_t* patch = reinterpret_cast<uint8_t*>(stage) + lane * 128;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(stage + lane * LDS + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      __syncwarp();
-      if constexpr (Epi::kKind == kEpiStore) {
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(patch + ((q ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_3d(&maps.c, stage, n0 + c, m0 + quad * 32, z);
+          bulk_commit();
+        }
+        __syncwarp();
+      } else {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * LDS + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+      }
+      if constexpr (Epi::kKind == kEpiStoreTma) {
+        // (shipped above)
+      } else if constexpr (Epi::kKind == kEpiStore) {
         float4 cur[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = sv[i];
@@ -644,6 +692,8 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     if constexpr (Epi::kKind == kEpiRankCount || Epi::kKind == kEpiRankScreen) {
       if (row_count) atomicAdd(epi.row_cnt + my_m, row_count);
     }
+    // (TMA stores: only the READS of the patch have to be over before the next chunk reuses it -- checked there; the writes
+    //  themselves are awaited once, before the CTA exits)
   };
 
   if (warp == 0) {
@@ -862,9 +912,9 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
       const bool last = w + (int)gridDim.x >= total_work;
       if (kGroups == 1) {
         // the CTA's last item has nothing to overlap with: the (by then idle) splitter warps take the upper two chunks
-        drain(it, local & 1, (local >> 1) & 1, 0, (last && kSplit == 3) ? kHalfN : BN, 32, epi_stage + (warp - 6) * 32 * 36, !last);
+        drain(it, local & 1, (local >> 1) & 1, 0, (last && kSplit == 3) ? kHalfN : BN, 32, epi_stage + (warp - 6) * kPatchFloats, !last);
       } else {
-        drain(it, local & 1, (local >> 1) & 1, 32 * grp, BN, 32 * kGroups, epi_stage + (warp - 6) * 32 * 36, true);
+        drain(it, local & 1, (local >> 1) & 1, 32 * grp, BN, 32 * kGroups, epi_stage + (warp - 6) * kPatchFloats, true);
       }
       if (local == 0) TL(6);
     }
@@ -875,7 +925,11 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     const int local = n_items - 1;
     const WorkItem it = decode((int)blockIdx.x + local * (int)gridDim.x);
     // pipeline stage 0 is free once tmem_full of the last item has fired (drain waits for it before touching it)
-    drain(it, local & 1, (local >> 1) & 1, kHalfN, BN, 32, reinterpret_cast<float*>(smem) + (warp - 2) * 32 * 36, false);
+    drain(it, local & 1, (local >> 1) & 1, kHalfN, BN, 32, reinterpret_cast<float*>(smem) + (warp - 2) * kPatchFloats, false);
+  }
+  if constexpr (Epi::kKind == kEpiStoreTma) {
+    if (warp >= 2 && elect_one()) bulk_wait0();          // every TMA store this warp issued has completed (global writes done)
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

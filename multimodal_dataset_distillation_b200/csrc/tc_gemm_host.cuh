@@ -116,6 +116,35 @@ inline int get_map_bf16(const void* ptr, int rows, int K, int ld, CUtensorMap* o
   return VLDD_OK;
 }
 
+// output map of the TMA-store epilogue: slabs part[z][M][N] fp32 as a 3-D tensor {N, M, splits}, box 32 x 32 x 1, SWIZZLE_128B
+inline int get_map_slabs(const float* part, int M, int N, int splits, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{part, M, N, splits, 3, 32};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return VLDD_OK; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VLDD_ERR_CUDA; }
+  CUtensorMap m;
+  const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
+  const cuuint64_t strides[2] = {(cuuint64_t)N * 4, (cuuint64_t)M * N * 4};
+  const cuuint32_t box[3] = {32, 32, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(part), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(slabs) failed (%d) for M=%d N=%d splits=%d", (int)r, M, N, splits);
+    return VLDD_ERR_CUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return VLDD_OK;
+}
+inline bool slabs_tma_ok(const float* part, int M, int N) { return aligned16(part) && N % 4 == 0 && ((long long)M * N) % 4 == 0; }
+
 // C = A B^T from pre-split bf16 operands (A = A_hi + A_lo [M, K], B = B_hi + B_lo [N, K], K-major, K % 8 == 0, 16-byte
 // aligned): three bf16 tensor-core products per k-step (tc_gemm.cuh, kSplit == 6), 128 x BN tiles.
 template <class Epi, int BN = 256>
@@ -158,7 +187,7 @@ inline bool gemm_ok(const GemmOperands& g) {
 template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128, int kEpiWarps = 4>
 inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st, const int* work_list = nullptr,
                   const int* work_count = nullptr, int old_mask = 0) {
-  using C = Cfg<kSplit, kSplit == 3, kStagesT, BN, kEpiWarps>;
+  using C = Cfg<kSplit, kSplit == 3, kStagesT, BN, kEpiWarps, epi_uses_tma<Epi>::value>;
   auto kern = tc_gemm_kernel<A_KMAJOR, B_KMAJOR, kSplit, Epi, kStagesT, BN, kEpiWarps>;
   // the attribute is per device (a process may drive several GPUs): one flag per device ordinal and template instance
   static bool configured[64] = {};
@@ -182,6 +211,11 @@ inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st, c
   } else {
     maps.a1 = maps.a0;
     maps.b1 = maps.b0;
+  }
+  maps.c = maps.a0;
+  if constexpr (epi_uses_tma<Epi>::value) {
+    rc = get_map_slabs(epi.part, g.M, g.N, splits, &maps.c);
+    if (rc) return rc;
   }
   const int work = ceil_div(g.N, BN) * ceil_div(g.M, BM) * splits;
   dim3 grid(work < num_sms() ? work : num_sms());                         // persistent: one CTA per SM at most
