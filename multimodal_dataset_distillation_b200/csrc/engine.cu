@@ -144,16 +144,53 @@ __global__ void __launch_bounds__(256) dot_over_scale_kernel(const float* __rest
   if (threadIdx.x == 0) *out = acc / (*scale);
 }
 
-// the padding columns [B, Bp) of S, G, Sd, Gd must read as zeros (they feed GEMMs as extra, all-zero rows)
-int zero_square_matrices(const Dims& m, Work& w, cudaStream_t st) {
-  const size_t bytes = (size_t)m.B * m.Bp * sizeof(float);
-  if (m.Bp == m.B) return VLDD_OK;
-  for (int k = 0; k < m.K; ++k) {
-    VLDD_CUDA(cudaMemsetAsync(w.sv[k].G, 0, bytes, st));
-    VLDD_CUDA(cudaMemsetAsync(w.sv[k].S, 0, bytes, st));
+#define CHECK_RC(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+// Everything a call has to clear, in ONE launch (as memset nodes these were 2 K + 7 serial ~1.1 us graph nodes ahead of the
+// first kernel): the accumulators (dY, dXn, dlr / dscale, the matching-loss scratch, the bad-index flag) and S, G, Sd, Gd, whose
+// padding columns [B, Bp) must read as zeros (they feed GEMMs as extra, all-zero rows).
+constexpr int kMaxZeroSegs = 24;
+struct ZeroSegs {
+  void* p[kMaxZeroSegs];
+  unsigned long long bytes[kMaxZeroSegs];      // multiples of 4
+};
+__global__ void __launch_bounds__(256) zero_segments_kernel(ZeroSegs z) {
+  pdl_enter();
+  char* p = static_cast<char*>(z.p[blockIdx.y]);
+  const size_t bytes = z.bytes[blockIdx.y];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+  if (((reinterpret_cast<uintptr_t>(p) | bytes) & 15) == 0) {
+    for (size_t i = t; i < bytes / 16; i += nt) reinterpret_cast<float4*>(p)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (size_t i = t; i < bytes / 4; i += nt) reinterpret_cast<float*>(p)[i] = 0.f;
   }
-  VLDD_CUDA(cudaMemsetAsync(w.Gd, 0, bytes, st));
-  VLDD_CUDA(cudaMemsetAsync(w.Sd, 0, bytes, st));
+}
+struct ZeroList {
+  ZeroSegs z;
+  int n = 0;
+  cudaStream_t st;
+  int flush() {
+    if (n == 0) return VLDD_OK;
+    launch_k(zero_segments_kernel, dim3(16, n), 256, 0, st, z);
+    n = 0;
+    return check_launch("zero_segments");
+  }
+  int add(void* p, size_t bytes) {
+    if (bytes == 0) return VLDD_OK;
+    z.p[n] = p; z.bytes[n] = bytes;
+    if (++n == kMaxZeroSegs) return flush();
+    return VLDD_OK;
+  }
+};
+int zero_square_matrices(const Dims& m, Work& w, ZeroList& zl) {
+  if (m.Bp == m.B) return VLDD_OK;
+  // S, G, Pr, Pc of a step are carved next to each other (carve()): S and G are cleared as the run [S, G + B*Bp)
+  const size_t bytes = (size_t)m.B * m.Bp * sizeof(float);
+  for (int k = 0; k < m.K; ++k) {
+    if (w.sv[k].G == w.sv[k].S + (size_t)m.B * m.Bp) CHECK_RC(zl.add(w.sv[k].S, 2 * bytes));
+    else { CHECK_RC(zl.add(w.sv[k].S, bytes)); CHECK_RC(zl.add(w.sv[k].G, bytes)); }
+  }
+  if (w.Gd == w.Sd + (size_t)m.B * m.Bp) CHECK_RC(zl.add(w.Sd, 2 * bytes));
+  else { CHECK_RC(zl.add(w.Sd, bytes)); CHECK_RC(zl.add(w.Gd, bytes)); }
   return VLDD_OK;
 }
 
@@ -166,7 +203,6 @@ inline int ew_grid(size_t n) {
   return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
-#define CHECK_RC(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 
 // VLDD_EARLY_LOADS=0 disables the pre-wait operand loads of the tensor-core GEMMs (A/B runs)
 bool early_loads() {
@@ -271,6 +307,8 @@ void prof_report() {
 struct Lanes {
   cudaStream_t main, s1, s2;
   bool s1_busy, s2_busy;
+  // reverse sweep: side-lane work of the PREVIOUS step that the next step has not waited for yet (tangent_step)
+  cudaEvent_t ev_small = nullptr, ev_s1_tail = nullptr, ev_s2 = nullptr;
 };
 std::mutex g_lane_mu;
 // side streams, event pool and capture stream are per device (a process may drive several GPUs)
@@ -291,6 +329,14 @@ int current_device_state(DeviceState** out) {
   return VLDD_OK;
 }
 
+bool relaxed_joins() {          // VLDD_JOIN=step restores the whole-step join of the reverse sweep (developer comparison)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLDD_JOIN");
+    v = (e && strcmp(e, "step") == 0) ? 0 : 1;
+  }
+  return v == 1 && !prof_enabled();
+}
 int lanes_init(Lanes& L, cudaStream_t main) {
   std::lock_guard<std::mutex> lock(g_lane_mu);
   CHECK_RC(current_device_state(&g_cur));
@@ -315,7 +361,24 @@ int lane_edge(cudaStream_t from, cudaStream_t to) {   // everything enqueued on 
   VLDD_CUDA(cudaStreamWaitEvent(to, e, 0));
   return VLDD_OK;
 }
+int lane_record(cudaStream_t on, cudaEvent_t* out) {     // an event after everything enqueued on `on` so far
+  if (g_cur->event_next == g_cur->events.size()) {
+    cudaEvent_t e;
+    VLDD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g_cur->events.push_back(e);
+  }
+  *out = g_cur->events[g_cur->event_next++];
+  VLDD_CUDA(cudaEventRecord(*out, on));
+  return VLDD_OK;
+}
+int lane_wait(cudaStream_t st, cudaEvent_t* ev) {        // consume a pending event (no-op when there is none)
+  if (*ev == nullptr) return VLDD_OK;
+  VLDD_CUDA(cudaStreamWaitEvent(st, *ev, 0));
+  *ev = nullptr;
+  return VLDD_OK;
+}
 int lanes_join(Lanes& L) {
+  L.ev_small = L.ev_s1_tail = L.ev_s2 = nullptr;          // subsumed by the full joins below
   if (L.s1_busy) { CHECK_RC(lane_edge(L.s1, L.main)); L.s1_busy = false; }
   if (L.s2_busy) { CHECK_RC(lane_edge(L.s2, L.main)); L.s2_busy = false; }
   return VLDD_OK;
@@ -435,6 +498,11 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   int sp = 1;
   CHECK_RC((gemm_partial<true, true>(gemm_ops(s.Yb, dt, V1, dt, B, d, dt), w.pa, &sp, st, kOldA)));
   prof_mark("gemm_partial<true,true> A=s.Yb", st);
+  // The previous reverse step is not joined as a whole (its dY product would sit between its last weight GEMM and this step's
+  // first one): the GEMM above needs only v[W1], written on the main stream.  From here on: c1 / c2 / gamd / betd come from
+  // the previous step's column-sum kernel (side lane 1), V2 from its W2 GEMM (side lane 2), which also still reads w.hd.
+  CHECK_RC(lane_wait(st, &L.ev_small));
+  CHECK_RC(lane_wait(st, &L.ev_s2));
   launch_k(epi_pd_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, c1, s.p, B, d, w.pd, w.hd);
   prof_mark("epi_pd_kernel", st);
   // fd = hd W2^T + h V2^T + c2 ; LN / normalise tangents
@@ -508,24 +576,34 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   // dhd = dfd W2 + df V2 ; dpd
   CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), w.pa, &sp, st, kOldB)));
   prof_mark("gemm_partial<true,false> A=w.dfd", st);
+  // the previous step's dY product (side lane 1) reads w.dpd and v's buffer-mate a_out[W1]: both are rewritten from here on
+  CHECK_RC(lane_wait(st, &L.ev_s1_tail));
   launch_k(epi_dpd_kernel, ew_grid4(Bd, d), 256, 0, st, w.pa, sp, Bd, s.p, w.pd, s.dh, w.drd, Bd, w.dpd);
   prof_mark("epi_dpd_kernel", st);
-  // branch 1 (after dXn): dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.)
+  // branch 1 (after dXn): small parameters of a_k by column sums (the next step's second kernel needs them), then
+  // dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.), which nothing needs before the end of the sweep
   CHECK_RC(lane_edge(st, L.s1));
+  launch_k(colsum_tangent_update_kernel, ceil_div(d, 16), 256, 0, L.s1, 
+      w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
+      v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
+  prof_mark("colsum_tangent_update_kernel", L.s1);
+  if (relaxed_joins()) CHECK_RC(lane_record(L.s1, &L.ev_small));
   int sp_y = 1;
   CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dpd, d, W1, dt, d, s.dp, d, V1, dt, d, B, dt), w.pe, &sp_y, L.s1)));
   prof_mark("gemm_partial<true,false> A=w.dpd", L.s1);
   launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pe, sp_y, (size_t)B * dt, perm, dt, lr, nullptr, dY, m.N);
   prof_mark("scatter_add_rows_kernel", L.s1);
-  // small parameters of a_k by column sums: also on the side stream, next to the main stream's W1 GEMM
-  launch_k(colsum_tangent_update_kernel, ceil_div(d, 16), 256, 0, L.s1, 
-      w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
-      v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
-  prof_mark("colsum_tangent_update_kernel", L.s1);
-  // main: a_k[W1] = a_{k+1}[W1] - lr dpd^T Yb ; small params by column sums
+  // main: a_k[W1] = a_{k+1}[W1] - lr dpd^T Yb
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), v + m.oW1, a_out + m.oW1, dt, lr, st, kOldB)));
   prof_mark("gemm_axpy<false,false> A=w.dpd", st);
-  CHECK_RC(lanes_join(L));          // a_k, dXn, dY complete before the next reverse step reuses the scratch buffers
+  if (relaxed_joins()) {
+    // the next reverse step waits for exactly what it touches, where it touches it (see its head); the caller joins after
+    // the last step
+    CHECK_RC(lane_record(L.s1, &L.ev_s1_tail));
+    CHECK_RC(lane_record(L.s2, &L.ev_s2));
+  } else {
+    CHECK_RC(lanes_join(L));          // a_k, dXn, dY complete before the next reverse step reuses the scratch buffers
+  }
   return check_launch("tangent_step");
 }
 
@@ -559,12 +637,17 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   const size_t Bd = (size_t)B * d;
   Lanes L;
   CHECK_RC(lanes_init(L, st));
-  VLDD_CUDA(cudaMemsetAsync(w.ml_scratch, 0, 16, st));
-  VLDD_CUDA(cudaMemsetAsync(w.bad_index, 0, sizeof(int), st));
-  VLDD_CUDA(cudaMemsetAsync(out5 + 3, 0, 2 * sizeof(float), st));
-  VLDD_CUDA(cudaMemsetAsync(dY, 0, (size_t)N * dt * sizeof(float), st));
-  VLDD_CUDA(cudaMemsetAsync(w.dXn, 0, (size_t)N * d * sizeof(float), st));
-  CHECK_RC(zero_square_matrices(m, w, st));
+  {
+    ZeroList zl;
+    zl.st = st;
+    CHECK_RC(zl.add(w.ml_scratch, 16));
+    CHECK_RC(zl.add(w.bad_index, sizeof(int)));
+    CHECK_RC(zl.add(out5 + 3, 2 * sizeof(float)));
+    CHECK_RC(zl.add(dY, (size_t)N * dt * sizeof(float)));
+    CHECK_RC(zl.add(w.dXn, (size_t)N * d * sizeof(float)));
+    CHECK_RC(zero_square_matrices(m, w, zl));
+    CHECK_RC(zl.flush());
+  }
   MARK("start");
   // fresh dropout masks for the K student steps (networks.py:636,643), drawn by the engine itself on a side branch; the
   // reverse sweep reads the same buffer, i.e. replays the same masks.  First use: the LayerNorm kernel of step 0.
@@ -607,6 +690,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
                           perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L));
     float* t = a_cur; a_cur = a_nxt; a_nxt = t;
   }
+  CHECK_RC(lanes_join(L));
   launch_k(row_normalise_bwd_kernel, N, 256, 0, st, w.Xn, w.un, w.dXn, nullptr, d, dU);
   MARK("row_normalise_bwd");
   launch_k(finalize_kernel, 1, 256, 0, st, match_final_parts(w.ml_scratch), match_final_n_parts(m.P), (const float*)w.den,
@@ -725,7 +809,12 @@ int contrastive_step(const float* theta, const float* Y, const float* U, const f
   Saved& s = w.sv[0];
   const size_t Bd = (size_t)B * d;
   launch_k(fill_kernel, 1, 32, 0, st, w.neg_one, -1.0f, 4);
-  CHECK_RC(zero_square_matrices(m, w, st));
+  {
+    ZeroList zl;
+    zl.st = st;
+    CHECK_RC(zero_square_matrices(m, w, zl));
+    CHECK_RC(zl.flush());
+  }
   launch_k(row_normalise_kernel, B, 256, 0, st, U, d, w.Xn, w.un);
   VLDD_CUDA(cudaMemcpyAsync(s.Yb, Y, (size_t)B * dt * sizeof(float), cudaMemcpyDeviceToDevice, st));
   VLDD_CUDA(cudaMemcpyAsync(s.Xb, w.Xn, Bd * sizeof(float), cudaMemcpyDeviceToDevice, st));
