@@ -309,6 +309,8 @@ struct Lanes {
   bool s1_busy, s2_busy;
   // reverse sweep: side-lane work of the PREVIOUS step that the next step has not waited for yet (tangent_step)
   cudaEvent_t ev_small = nullptr, ev_s1_tail = nullptr, ev_s2 = nullptr;
+  // the dY product of the previous reverse step, not launched yet (run_pending_dy)
+  struct PendingDy { bool live = false; const float *dpd, *W1, *dp, *V1; const int64_t* perm; } dy;
 };
 std::mutex g_lane_mu;
 // side streams, event pool and capture stream are per device (a process may drive several GPUs)
@@ -336,6 +338,20 @@ bool relaxed_joins() {          // VLDD_JOIN=step restores the whole-step join o
     v = (e && strcmp(e, "step") == 0) ? 0 : 1;
   }
   return v == 1 && !prof_enabled();
+}
+bool env_on(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  return strcmp(e, "0") != 0;
+}
+// (stream priorities -- side lanes lowest, capture stream highest -- were measured and change nothing: the persistent GEMM CTAs
+//  of a side product hold their SMs until they are done, 1.5991 vs 1.5981 ms per iteration)
+// the dY product of reverse step k runs in step k-1's InfoNCE window (few busy SMs) instead of next to step k-1's first GEMM
+bool defer_dy() { static const bool v = env_on("VLDD_DEFER_DY", true); return v; }
+int dy_grid_cap() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VLDD_DY_CTAS"); v = e ? atoi(e) : 96; }
+  return v;
 }
 int lanes_init(Lanes& L, cudaStream_t main) {
   std::lock_guard<std::mutex> lock(g_lane_mu);
@@ -482,6 +498,7 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
 // One reverse step: tangent of the first-order step along theta_dot = v (= a_{k+1}); writes a_k = v - lr H v
 // and accumulates dlr, dscale, dY, dXn.
 // ---------------------------------------------------------------------------------------------------
+int run_pending_dy(const Dims& m, Work& w, const float* lr, float* dY, Lanes& L);
 int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const float* v, float* a_out,
                  const float* lr, const float* scale, const float* mask, const int64_t* perm, float* dY, float* dlr,
                  float* dscale, Lanes& L) {
@@ -515,6 +532,12 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
     launch_k(ln_tangent_kernel, B, 256, d * sizeof(float), st, w.pa, sp, Bd, c2, mask, w.pd, s.rhat, s.rstd, s.yn, s.nz, gam,
                                                          gamd, betd, d, w.rhatd, w.ynd, w.t, w.nzd);
   prof_mark("ln_tangent_kernel", st);
+  if (L.dy.live) {
+    // the previous step's dY product: from here to the end of the InfoNCE block the main lane keeps few SMs busy
+    CHECK_RC(lane_edge(st, L.s1));
+    CHECK_RC(run_pending_dy(m, w, lr, dY, L));
+    CHECK_RC(lane_record(L.s1, &L.ev_s1_tail));
+  }
   // Sd = scale Xb Ynd^T ; rho, kappa, Gd ; L_dot ; dlr, dscale ; dynd_raw[j,:] = sum_i Gd[i,j] Xb[i,:]
   const bool small = nce_small(B, d, Bp, s.Xb, w.ynd, w.pb);
   const bool fused_nce = !small && nce_fused(B, Bp);
@@ -588,23 +611,37 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
       v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
   prof_mark("colsum_tangent_update_kernel", L.s1);
   if (relaxed_joins()) CHECK_RC(lane_record(L.s1, &L.ev_small));
-  int sp_y = 1;
-  CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dpd, d, W1, dt, d, s.dp, d, V1, dt, d, B, dt), w.pe, &sp_y, L.s1)));
-  prof_mark("gemm_partial<true,false> A=w.dpd", L.s1);
-  launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pe, sp_y, (size_t)B * dt, perm, dt, lr, nullptr, dY, m.N);
-  prof_mark("scatter_add_rows_kernel", L.s1);
+  L.dy.live = true; L.dy.dpd = w.dpd; L.dy.W1 = W1; L.dy.dp = s.dp; L.dy.V1 = V1; L.dy.perm = perm;
+  if (!(relaxed_joins() && defer_dy())) CHECK_RC(run_pending_dy(m, w, lr, dY, L));
   // main: a_k[W1] = a_{k+1}[W1] - lr dpd^T Yb
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), v + m.oW1, a_out + m.oW1, dt, lr, st, kOldB)));
   prof_mark("gemm_axpy<false,false> A=w.dpd", st);
   if (relaxed_joins()) {
     // the next reverse step waits for exactly what it touches, where it touches it (see its head); the caller joins after
     // the last step
-    CHECK_RC(lane_record(L.s1, &L.ev_s1_tail));
+    if (!L.dy.live) CHECK_RC(lane_record(L.s1, &L.ev_s1_tail));
     CHECK_RC(lane_record(L.s2, &L.ev_s2));
   } else {
     CHECK_RC(lanes_join(L));          // a_k, dXn, dY complete before the next reverse step reuses the scratch buffers
   }
   return check_launch("tangent_step");
+}
+
+// dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.) of the step recorded in L.dy, on side lane 1 (capped grid: it runs next
+// to critical-path kernels)
+int run_pending_dy(const Dims& m, Work& w, const float* lr, float* dY, Lanes& L) {
+  if (!L.dy.live) return VLDD_OK;
+  L.dy.live = false;
+  const int B = m.B, d = m.d, dt = m.dt;
+  int sp_y = 1;
+  {
+    tc::GridCapScope cap(dy_grid_cap());
+    CHECK_RC((gemm_partial<true, false>(gemm_ops2(L.dy.dpd, d, L.dy.W1, dt, d, L.dy.dp, d, L.dy.V1, dt, d, B, dt), w.pe, &sp_y, L.s1)));
+  }
+  prof_mark("gemm_partial<true,false> A=w.dpd", L.s1);
+  launch_k(scatter_add_rows_kernel, B, 256, 0, L.s1, w.pe, sp_y, (size_t)B * dt, L.dy.perm, dt, lr, nullptr, dY, m.N);
+  prof_mark("scatter_add_rows_kernel", L.s1);
+  return VLDD_OK;
 }
 
 int validate(int N, int B, int K, int dt, int d) {
@@ -689,6 +726,10 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
     CHECK_RC(tangent_step(m, w, w.sv[k], th, a_cur, a_nxt, lr, scale, masks ? masks + k * Bd : nullptr,
                           perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L));
     float* t = a_cur; a_cur = a_nxt; a_nxt = t;
+  }
+  if (L.dy.live) {                      // the last step's dY product
+    CHECK_RC(lane_edge(st, L.s1));
+    CHECK_RC(run_pending_dy(m, w, lr, dY, L));
   }
   CHECK_RC(lanes_join(L));
   launch_k(row_normalise_bwd_kernel, N, 256, 0, st, w.Xn, w.un, w.dXn, nullptr, d, dU);

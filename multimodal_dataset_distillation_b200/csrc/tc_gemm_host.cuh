@@ -184,6 +184,15 @@ inline bool gemm_ok(const GemmOperands& g) {
   return true;
 }
 
+// Background GEMMs (launched on a side lane next to critical-path kernels) leave some SMs to the main lane: the caller caps
+// the persistent grid for the duration of a scope.
+inline int& grid_cap() { static thread_local int cap = 0; return cap; }
+struct GridCapScope {
+  int saved;
+  explicit GridCapScope(int cap) : saved(grid_cap()) { grid_cap() = cap; }
+  ~GridCapScope() { grid_cap() = saved; }
+};
+
 template <bool A_KMAJOR, bool B_KMAJOR, int kSplit, class Epi, int kStagesT = 0, int BN = 128, int kEpiWarps = 4>
 inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st, const int* work_list = nullptr,
                   const int* work_count = nullptr, int old_mask = 0) {
@@ -218,7 +227,9 @@ inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st, c
     if (rc) return rc;
   }
   const int work = ceil_div(g.N, BN) * ceil_div(g.M, BM) * splits;
-  dim3 grid(work < num_sms() ? work : num_sms());                         // persistent: one CTA per SM at most
+  int ctas = work < num_sms() ? work : num_sms();                         // persistent: one CTA per SM at most
+  if (grid_cap() > 0 && ctas > grid_cap()) ctas = grid_cap();
+  dim3 grid(ctas);
   launch_k(kern, grid, C::kThreads, C::kSmemBytes, st, maps, g.M, g.N, g.K0, g.K1, splits, epi, work_list, work_count, old_mask);
   return VLDD_OK;
 }
