@@ -394,13 +394,25 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   // optional device-side work list (tile indices chosen by an earlier kernel, e.g. "tiles holding a ground-truth pair");
   // it is written by a predecessor kernel, so it may only be read after pdl_wait() -- see below
   int total_work = tiles_m * tiles_n * splits;
+  constexpr bool kRaster = Epi::kKind != kEpiStore && Epi::kKind != kEpiStoreTma;      // the ranking kernels (many m-tiles)
   auto decode = [&](int w) {
     WorkItem it;
     if (work_list != nullptr) w = work_list[w];
     const int tile = w % (tiles_m * tiles_n);
     it.z = w / (tiles_m * tiles_n);
-    it.n0 = (tile % tiles_n) * BN;            // consecutive CTAs take consecutive n-tiles of one m-tile (A reuse in L2)
-    it.m0 = (tile / tiles_n) * BM;
+    if (kRaster && work_list == nullptr && tiles_m > 1) {
+      // bands of kRasterM m-tiles, m fastest inside a band: the CTAs running at one time cover kRasterM m-tiles x ~148/kRasterM
+      // n-tiles, so the A band stays in L2 for a whole sweep over n and every B tile is fetched from DRAM once per BAND instead
+      // of once per m-tile (25k x 125k x 768 screen: 60 GB of DRAM reads with n-fastest order, B = 384 MB > L2)
+      constexpr int kRasterM = 16;
+      const int band = tile / (kRasterM * tiles_n), r = tile - band * kRasterM * tiles_n;
+      const int h = min(kRasterM, tiles_m - band * kRasterM);
+      it.m0 = (band * kRasterM + r % h) * BM;
+      it.n0 = (r / h) * BN;
+    } else {
+      it.n0 = (tile % tiles_n) * BN;          // one m-tile (or listed tiles): consecutive CTAs take consecutive n-tiles
+      it.m0 = (tile / tiles_n) * BM;
+    }
     it.kb_begin = it.z * per;
     it.n_kb = max(min(nkb, it.kb_begin + per) - it.kb_begin, 0);
     return it;
