@@ -436,6 +436,16 @@ def run_ours(opt):
     ms_per_step = ms / opt.steps
     value = world * opt.steps / (ms / 1e3)
 
+    if opt.profile:                                  # ncu target: nothing but the loop above
+        clk.__exit__(None, None, None)
+        if world > 1:
+            dist.destroy_process_group()
+        if rank != 0:
+            return None
+        return {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": opt.steps,
+                "warmup": opt.warmup, "ms_per_step": ms_per_step, "gpu_launches": gpu_launches,
+                "profile_only": "developer run (--profile): no end-to-end, roofline, retrieval or baseline legs -- not a bench line"}
+
     # ---- end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ----
     # Expert trajectories stay in host memory as in the reference (distill.py:466-476 uploads the segment every
     # iteration).  "streamed": distill.SegmentPrefetcher copies segment i+1 on a copy stream while segment i is processed
@@ -546,9 +556,10 @@ def run_ours(opt):
                          "frac": dk_achieved / pk["hbm"], "traffic": dominant_kernel_traffic()[0],
                          "traffic_source": (dominant_kernel_traffic()[1] or {}).get("source"),
                          "peak_source": pk["src"],
-                         "kernel": "vldd::tc::tc_gemm_kernel<K-major,K-major,3xTF32,EpiPartial> launched as f = h W2^T "
-                                   "(M=100, N=K=2304, split-K %d): the GEMM family is ~62%% of the iteration's kernel time "
-                                   "(profiles/launches_r01g_summary.txt)" % dk["splits"],
+                         "kernel": "vldd::tc::tc_gemm_kernel<K-major,K-major,3xTF32,EpiPartialTma,BN=128> launched as "
+                                   "f = h W2^T (M=100, N=K=2304, split-K %d, slabs written by TMA stores): the GEMM family is "
+                                   "~65%% of the iteration's serialised kernel time (profiles/launches_r02z_summary.txt)"
+                                   % dk["splits"],
                          "algorithmic_bytes_per_launch": dk["abytes"], "avg_launch_us": dk["avg_us"],
                          "median_launch_us": dk["median_us"], "launches_timed": dk["launches"],
                          "tensor_tflops_3xtf32_equiv": 3 * dk["flops"] / (dk["avg_us"] * 1e-6) / 1e12,
