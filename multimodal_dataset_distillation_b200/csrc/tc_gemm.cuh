@@ -940,7 +940,10 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     drain(it, local & 1, (local >> 1) & 1, kHalfN, BN, 32, reinterpret_cast<float*>(smem) + (warp - 2) * kPatchFloats, false);
   }
   if constexpr (Epi::kKind == kEpiStoreTma) {
-    if (warp >= 2 && elect_one()) bulk_wait0();          // every TMA store this warp issued has completed (global writes done)
+    // the patches must outlive the stores' READS of them; the global writes themselves are ordinary in-flight stores at exit and
+    // are performed before the grid counts as complete (what a dependent's griddepcontrol.wait / the stream order waits for)
+    // (waiting for full completion instead measured 1.6038 vs 1.5973 ms per iteration)
+    if (warp >= 2 && elect_one()) bulk_wait_read0();
     __syncwarp();
   }
   tc_fence_before();
