@@ -498,10 +498,10 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
 // One reverse step: tangent of the first-order step along theta_dot = v (= a_{k+1}); writes a_k = v - lr H v
 // and accumulates dlr, dscale, dY, dXn.
 // ---------------------------------------------------------------------------------------------------
-int run_pending_dy(const Dims& m, Work& w, const float* lr, float* dY, Lanes& L);
+int run_pending_dy(const Dims& m, Work& w, const float* lr, float* dY, Lanes& L, bool full_grid = false);
 int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const float* v, float* a_out,
                  const float* lr, const float* scale, const float* mask, const int64_t* perm, float* dY, float* dlr,
-                 float* dscale, Lanes& L) {
+                 float* dscale, Lanes& L, bool last = false) {
   // early operand loads (see forward_step): theta_k and the saved activations are steps old.  v = a_{k+1} is NOT old for the
   // first GEMM: its W1 block is written by the previous reverse step's last main-stream kernel (or, in the first reverse
   // step, by the matching-loss backward kernel), i.e. by the immediate predecessor; from the second GEMM on it is.
@@ -590,12 +590,16 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
                                                                   s.dz, s.rhat, w.rhatd, s.rstd, w.t, s.dr, gam, gamd,
                                                                   mask, d, w.dzd, w.drd, w.dfd);
   prof_mark("norm_ln_bwd_tangent_kernel", st);
+  // `last` (k = 0): a_0, the adjoint of the expert's start parameters, is nobody's input (the outputs are dY, dXn, dlr,
+  // dscale) -- its two weight GEMMs and the column sums are not launched at all
   // branch 2: a_k[W2] = a_{k+1}[W2] - lr (dfd^T h + df^T hd)   (fused into the GEMM epilogue)
-  CHECK_RC(lane_edge(st, L.s2));
-  L.s2_busy = true;
-  CHECK_RC((gemm_axpy<false, false>(gemm_ops2(w.dfd, d, s.h, d, B, s.df, d, w.hd, d, B, d, d), v + m.oW2, a_out + m.oW2, d,
-                                    lr, L.s2)));
-  prof_mark("gemm_axpy<false,false> A=w.dfd", L.s2);
+  if (!last) {
+    CHECK_RC(lane_edge(st, L.s2));
+    L.s2_busy = true;
+    CHECK_RC((gemm_axpy<false, false>(gemm_ops2(w.dfd, d, s.h, d, B, s.df, d, w.hd, d, B, d, d), v + m.oW2, a_out + m.oW2, d,
+                                      lr, L.s2)));
+    prof_mark("gemm_axpy<false,false> A=w.dfd", L.s2);
+  }
   // dhd = dfd W2 + df V2 ; dpd
   CHECK_RC((gemm_partial<true, false>(gemm_ops2(w.dfd, d, W2, d, d, s.df, d, V2, d, d, B, d), w.pa, &sp, st, kOldB)));
   prof_mark("gemm_partial<true,false> A=w.dfd", st);
@@ -606,13 +610,16 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   // branch 1 (after dXn): small parameters of a_k by column sums (the next step's second kernel needs them), then
   // dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.), which nothing needs before the end of the sweep
   CHECK_RC(lane_edge(st, L.s1));
-  launch_k(colsum_tangent_update_kernel, ceil_div(d, 16), 256, 0, L.s1, 
-      w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
-      v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
-  prof_mark("colsum_tangent_update_kernel", L.s1);
-  if (relaxed_joins()) CHECK_RC(lane_record(L.s1, &L.ev_small));
+  if (!last) {
+    launch_k(colsum_tangent_update_kernel, ceil_div(d, 16), 256, 0, L.s1, 
+        w.dpd, w.dfd, w.dzd, s.dz, s.rhat, w.rhatd, B, d, lr, v + m.ob1, a_out + m.ob1, v + m.ob2, a_out + m.ob2,
+        v + m.og, a_out + m.og, v + m.obt, a_out + m.obt);
+    prof_mark("colsum_tangent_update_kernel", L.s1);
+    if (relaxed_joins()) CHECK_RC(lane_record(L.s1, &L.ev_small));
+  }
   L.dy.live = true; L.dy.dpd = w.dpd; L.dy.W1 = W1; L.dy.dp = s.dp; L.dy.V1 = V1; L.dy.perm = perm;
-  if (!(relaxed_joins() && defer_dy())) CHECK_RC(run_pending_dy(m, w, lr, dY, L));
+  if (last || !(relaxed_joins() && defer_dy())) CHECK_RC(run_pending_dy(m, w, lr, dY, L, /*full_grid=*/last));
+  if (last) return check_launch("tangent_step");            // the caller joins the lanes
   // main: a_k[W1] = a_{k+1}[W1] - lr dpd^T Yb
   CHECK_RC((gemm_axpy<false, false>(gemm_ops(w.dpd, d, s.Yb, dt, d, dt, B), v + m.oW1, a_out + m.oW1, dt, lr, st, kOldB)));
   prof_mark("gemm_axpy<false,false> A=w.dpd", st);
@@ -629,13 +636,13 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
 
 // dY_dot = dpd W1 + dp V1  ->  dY[perm] -= lr * (.) of the step recorded in L.dy, on side lane 1 (capped grid: it runs next
 // to critical-path kernels)
-int run_pending_dy(const Dims& m, Work& w, const float* lr, float* dY, Lanes& L) {
+int run_pending_dy(const Dims& m, Work& w, const float* lr, float* dY, Lanes& L, bool full_grid) {
   if (!L.dy.live) return VLDD_OK;
   L.dy.live = false;
   const int B = m.B, d = m.d, dt = m.dt;
   int sp_y = 1;
   {
-    tc::GridCapScope cap(dy_grid_cap());
+    tc::GridCapScope cap(full_grid ? 0 : dy_grid_cap());
     CHECK_RC((gemm_partial<true, false>(gemm_ops2(L.dy.dpd, d, L.dy.W1, dt, d, L.dy.dp, d, L.dy.V1, dt, d, B, dt), w.pe, &sp_y, L.s1)));
   }
   prof_mark("gemm_partial<true,false> A=w.dpd", L.s1);
@@ -724,7 +731,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   for (int k = K - 1; k >= 0; --k) {
     const float* th = w.traj + (size_t)k * m.P;
     CHECK_RC(tangent_step(m, w, w.sv[k], th, a_cur, a_nxt, lr, scale, masks ? masks + k * Bd : nullptr,
-                          perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L));
+                          perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L, /*last=*/k == 0));
     float* t = a_cur; a_cur = a_nxt; a_nxt = t;
   }
   if (L.dy.live) {                      // the last step's dY product

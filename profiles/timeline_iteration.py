@@ -13,22 +13,20 @@ eng = distill.DistillEngine(U, Y, bench.make_experts(1).cuda(), args, "cuda")
 for i in range(12):
     eng.step_fast(i % 4, i % 2)
 torch.cuda.synchronize()
+SYNC = os.environ.get("TIMELINE_SYNC", "0") == "1"        # 1: synchronise after every iteration (exposes the host's launch time)
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for i in range(3):
+    for i in range(5):
         eng.step_fast(i % 4, i % 2)
-        torch.cuda.synchronize()
+        if SYNC:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
 path = os.path.join(tempfile.mkdtemp(), "t.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
-# split into iterations at gaps > 200 us
-iters, cur = [], [ev[0]]
-for a, b in zip(ev, ev[1:]):
-    if b["ts"] - (a["ts"] + a["dur"]) > 200:
-        iters.append(cur); cur = []
-    cur.append(b)
-iters.append(cur)
-it = iters[-1]
+# one iteration = from a stage_segment_kernel (first kernel of vldd_unrolled_match, outside the graph) to the next one
+starts = [i for i, e in enumerate(ev) if "stage_segment_kernel" in e["name"]]
+it = ev[starts[-2]:starts[-1]] if not SYNC else ev[starts[-1]:]
 t0 = it[0]["ts"]
 end = max(e["ts"] + e["dur"] for e in it)
 print(f"# {len(it)} activities, span {end - t0:.1f} us")
