@@ -70,7 +70,9 @@ struct Work {
   float *neg_one;                      // device constant -1 (first-order API)
   int* bad_index;                      // set by the gather kernel when a minibatch index is out of range
   void* ml_scratch;
-  void* stage_scratch;                 // ticket + block partials of the staging kernel (runs outside the graph)
+  void* stage_scratch;                 // ticket + block partials of the staging kernel
+  void* stage_table;                   // {theta_0, theta*, perms}: the per-call addresses (written outside the graph)
+  int64_t* perms_copy;                 // [K, B] minibatch indices, copied by the gather kernel for the reverse sweep
   float* den;                          // |theta_0 - theta*|^2, produced while the segment is staged
   size_t bytes;
 };
@@ -119,6 +121,8 @@ void carve(Work& w, const Dims& m, void* base) {
   w.ml_scratch = b.f((size_t)match_loss_scratch_bytes() / sizeof(float) + 8);
   w.stage_scratch = b.f((size_t)match_loss_scratch_bytes() / sizeof(float) + 8);
   w.den = b.f(4);
+  w.stage_table = b.f(8);
+  w.perms_copy = reinterpret_cast<int64_t*>(b.f(2 * (size_t)(m.K > 0 ? m.K : 1) * m.B));
   w.bytes = b.off;
 }
 
@@ -681,6 +685,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   const size_t Bd = (size_t)B * d;
   Lanes L;
   CHECK_RC(lanes_init(L, st));
+  CHECK_RC(stage_segment_indirect(w.stage_table, w.traj, w.tgt, m.P, w.den, w.stage_scratch, st));
   {
     ZeroList zl;
     zl.st = st;
@@ -706,7 +711,8 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   // minibatches of all K steps in one launch (distill.py:510-513)
   if (K > 0) {
     const size_t step_stride = K > 1 ? (size_t)(w.sv[1].Yb - w.sv[0].Yb) : 0;
-    launch_k(gather_all_kernel, dim3(B, K, 2), 256, 0, st, Y, (const float*)w.Xn, perms, B, dt, d, w.sv[0].Yb, w.sv[0].Xb,
+    launch_k(gather_all_kernel, dim3(B, K, 2), 256, 0, st, Y, (const float*)w.Xn,
+             reinterpret_cast<const int64_t* const*>(static_cast<char*>(w.stage_table) + 2 * sizeof(void*)), w.perms_copy, B, dt, d, w.sv[0].Yb, w.sv[0].Xb,
              step_stride, N, w.bad_index);
     MARK("gather_all");
   }
@@ -731,7 +737,7 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   for (int k = K - 1; k >= 0; --k) {
     const float* th = w.traj + (size_t)k * m.P;
     CHECK_RC(tangent_step(m, w, w.sv[k], th, a_cur, a_nxt, lr, scale, masks ? masks + k * Bd : nullptr,
-                          perms + (size_t)k * B, dY, out5 + 3, out5 + 4, L, /*last=*/k == 0));
+                          w.perms_copy + (size_t)k * B, dY, out5 + 3, out5 + 4, L, /*last=*/k == 0));
     float* t = a_cur; a_cur = a_nxt; a_nxt = t;
   }
   if (L.dy.live) {                      // the last step's dY product
@@ -785,10 +791,12 @@ int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, 
   VLDD_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "dropout_p=%f out of range [0,1)", dropout_p);
   VLDD_REQUIRE(!(dropout_p > 0.f) || (masks != nullptr && rng_state != nullptr),
                "dropout_p > 0 needs a [K,B,d] mask buffer and an rng state {seed, draws}");
-  // stage the segment into the workspace (outside the graph: these two source addresses change every iteration); the same
-  // pass accumulates the denominator |theta_0 - theta*|^2 of the matching loss
-  VLDD_CUDA(cudaMemsetAsync(w.stage_scratch, 0, 16, st));
-  CHECK_RC(stage_segment(theta0, theta_tgt, w.traj, w.tgt, m.P, w.den, w.stage_scratch, st));
+  // The segment is staged into the workspace by the FIRST kernel of the body (same pass: denominator |theta_0 - theta*|^2 of
+  // the matching loss).  Its two source addresses change every iteration, so it reads them from a device table written here,
+  // outside the replayed graph.  (As a separate launch ahead of the graph the 22 us pass was followed by the graph's 2 us root
+  // kernel and ~10 us of launch latency before any second-level node ran -- profiles/timeline_r02z_steady.txt; as the root it
+  // covers that latency.)
+  CHECK_RC(set_stage_sources(theta0, theta_tgt, perms, w.stage_table, w.stage_scratch, st));
   if (!graphs_enabled() || prof_enabled()) {
     std::lock_guard<std::mutex> lock(g_graph_mu);   // the side streams / event pool are process-wide
     return unrolled_match_body(m, w, Y, U, lr, scale, perms, masks, dropout_p, rng_state, out5, ce, dY, dU, theta_K, st);
@@ -796,7 +804,8 @@ int unrolled_match(const float* theta0, const float* theta_tgt, const float* Y, 
 
   GraphKey key;
   memset(&key, 0, sizeof(key));
-  const void* ptrs[13] = {workspace, Y, U, lr, scale, perms, masks, out5, ce, dY, dU, theta_K, rng_state};
+  // (theta_0, theta* and perms are not part of the key: the graph reaches them through the device table)
+  const void* ptrs[13] = {workspace, Y, U, lr, scale, nullptr, masks, out5, ce, dY, dU, theta_K, rng_state};
   memcpy(key.p, ptrs, sizeof(ptrs));
   const int dims[5] = {N, B, K, dt, d};
   memcpy(key.dims, dims, sizeof(dims));

@@ -224,15 +224,20 @@ __device__ __forceinline__ size_t checked_row(int64_t idx, int N, int* bad_index
   }
   return (size_t)idx;
 }
+// The caller's index array is reached through a one-pointer device slot (its address may change from call to call while the
+// launch graph stays the same); the indices are copied into the workspace for the reverse sweep's scatter kernels.
 __global__ void __launch_bounds__(256) gather_all_kernel(const float* __restrict__ Y, const float* __restrict__ Xn,
-                                                         const int64_t* __restrict__ perms, int B, int dt, int d,
+                                                         const int64_t* const* __restrict__ perms_slot,
+                                                         int64_t* __restrict__ perms_copy, int B, int dt, int d,
                                                          float* __restrict__ Yb0, float* __restrict__ Xb0,
                                                          size_t step_stride, int N, int* __restrict__ bad_index) {
   pdl_enter();
   const int b = blockIdx.x, k = blockIdx.y;
   const bool isx = blockIdx.z == 1;
   const int cols = isx ? d : dt;
-  const size_t row = checked_row(perms[(size_t)k * B + b], N, bad_index);
+  const int64_t index = (*perms_slot)[(size_t)k * B + b];
+  if (!isx && threadIdx.x == 0) perms_copy[(size_t)k * B + b] = index;
+  const size_t row = checked_row(index, N, bad_index);
   const float* src = (isx ? Xn : Y) + row * cols;
   float* dst = (isx ? Xb0 : Yb0) + (size_t)k * step_stride + (size_t)b * cols;
   if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {

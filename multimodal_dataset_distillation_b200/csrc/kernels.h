@@ -17,6 +17,10 @@ int momentum_sgd(float* p, const float* g, float* buf, float lr, float momentum,
                  cudaStream_t st);
 int stage_segment(const float* th0_src, const float* tgt_src, float* th0_dst, float* tgt_dst, int64_t n, float* den_out,
                   void* scratch, cudaStream_t st);
+// per-call addresses (theta_0, theta*, minibatch indices) reach the replayed launch graph through a 3-pointer device table
+int set_stage_sources(const float* th0_src, const float* tgt_src, const void* perms, void* table, void* scratch, cudaStream_t st);
+int stage_segment_indirect(const void* table, float* th0_dst, float* tgt_dst, int64_t n, float* den_out, void* scratch,
+                           cudaStream_t st);
 int match_final_pass(const float* thK, const float* tgt, const float* den, int64_t n, float* a, void* scratch, cudaStream_t st);
 int match_final_finish(const float* den, int64_t n, float* out3, void* scratch, cudaStream_t finish_st);
 const double* match_final_parts(const void* scratch);   // block partials left by match_final_pass ...

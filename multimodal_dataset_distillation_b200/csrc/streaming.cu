@@ -190,12 +190,10 @@ __device__ __forceinline__ void finish_sum(float v, double* __restrict__ parts, 
 }
 
 // th0_dst = th0_src ; tgt_dst = tgt_src ; den = sum (th0 - tgt)^2            (16 B / param: 2 reads + 2 writes)
-__global__ void __launch_bounds__(kStreamThreads) stage_segment_kernel(const float* __restrict__ th0_src,
-                                                                       const float* __restrict__ tgt_src,
-                                                                       float* __restrict__ th0_dst, float* __restrict__ tgt_dst,
-                                                                       int64_t n, int vec, double* __restrict__ parts,
-                                                                       unsigned int* __restrict__ ticket, float* __restrict__ den_out) {
-  pdl_enter();
+__device__ __forceinline__ void stage_segment_body(const float* __restrict__ th0_src, const float* __restrict__ tgt_src,
+                                                   float* __restrict__ th0_dst, float* __restrict__ tgt_dst, int64_t n, int vec,
+                                                   double* __restrict__ parts, unsigned int* __restrict__ ticket,
+                                                   float* __restrict__ den_out) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
   float den = 0.f;
   if (vec) {
@@ -232,6 +230,35 @@ __global__ void __launch_bounds__(kStreamThreads) stage_segment_kernel(const flo
     }
   }
   finish_sum(den, parts, ticket, [&](double s) { *den_out = (float)s; });
+}
+__global__ void __launch_bounds__(kStreamThreads) stage_segment_kernel(const float* __restrict__ th0_src,
+                                                                       const float* __restrict__ tgt_src,
+                                                                       float* __restrict__ th0_dst, float* __restrict__ tgt_dst,
+                                                                       int64_t n, int vec, double* __restrict__ parts,
+                                                                       unsigned int* __restrict__ ticket, float* __restrict__ den_out) {
+  pdl_enter();
+  stage_segment_body(th0_src, tgt_src, th0_dst, tgt_dst, n, vec, parts, ticket, den_out);
+}
+// The same pass with the two SOURCE addresses read from a device table: the kernel's arguments are then the same for every
+// call, so it can be the first node of the engine's replayed launch graph (the sources change every iteration; the table is
+// written by set_stage_sources_kernel just before the graph is launched).
+__global__ void __launch_bounds__(kStreamThreads) stage_segment_indirect_kernel(const float* const* __restrict__ table,
+                                                                                float* __restrict__ th0_dst,
+                                                                                float* __restrict__ tgt_dst, int64_t n,
+                                                                                double* __restrict__ parts,
+                                                                                unsigned int* __restrict__ ticket,
+                                                                                float* __restrict__ den_out) {
+  pdl_enter();
+  const float* th0_src = table[0];
+  const float* tgt_src = table[1];
+  const int vec = ((reinterpret_cast<uintptr_t>(th0_src) | reinterpret_cast<uintptr_t>(tgt_src) | reinterpret_cast<uintptr_t>(th0_dst) |
+                    reinterpret_cast<uintptr_t>(tgt_dst)) & 15) == 0;
+  stage_segment_body(th0_src, tgt_src, th0_dst, tgt_dst, n, vec, parts, ticket, den_out);
+}
+__global__ void set_stage_sources_kernel(const void** table, const float* th0_src, const float* tgt_src, const void* perms,
+                                         unsigned int* ticket) {
+  pdl_enter();
+  if (threadIdx.x == 0) { table[0] = th0_src; table[1] = tgt_src; table[2] = perms; *ticket = 0u; }
 }
 
 // num = sum (thK - tgt)^2 ; a = 2 (thK - tgt) / den                      (12 B / param: 2 reads + 1 write)
@@ -417,6 +444,20 @@ int stage_segment(const float* th0_src, const float* tgt_src, float* th0_dst, fl
   launch_k(stage_segment_kernel, stream_grid(n / 8 + 1), kStreamThreads, 0, st, th0_src, tgt_src, th0_dst, tgt_dst, n, vec, parts,
            ticket, den_out);
   return check_launch("stage_segment");
+}
+
+int set_stage_sources(const float* th0_src, const float* tgt_src, const void* perms, void* table, void* scratch, cudaStream_t st) {
+  launch_k(set_stage_sources_kernel, 1, 32, 0, st, reinterpret_cast<const void**>(table), th0_src, tgt_src, perms,
+           reinterpret_cast<unsigned int*>(scratch));
+  return check_launch("set_stage_sources");
+}
+int stage_segment_indirect(const void* table, float* th0_dst, float* tgt_dst, int64_t n, float* den_out, void* scratch,
+                           cudaStream_t st) {
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
+  double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 16);
+  launch_k(stage_segment_indirect_kernel, stream_grid(n / 8 + 1), kStreamThreads, 0, st,
+           reinterpret_cast<const float* const*>(table), th0_dst, tgt_dst, n, parts, ticket, den_out);
+  return check_launch("stage_segment_indirect");
 }
 
 // streaming pass on `st`; the finish on `finish_st` -- the CALLER orders finish_st after the pass (same stream, or an event edge)

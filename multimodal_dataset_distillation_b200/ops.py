@@ -511,8 +511,9 @@ def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, worksp
         ws.lr.copy_(lr_t)
         ws.scale.copy_(sc_t)
         lr_t, sc_t = ws.lr, ws.scale
-    if K > 0 and perms.data_ptr() != ws.perms.data_ptr():
-        ws.perms.copy_(perms, non_blocking=True)
+    # (the engine reaches the index array through a device-side pointer slot and keeps its own copy for the reverse sweep, so
+    #  any device address may be passed from call to call without a copy here and without a new launch graph)
+    perms_arg = perms if K > 0 else ws.perms
     m_ptr = None
     rng = None
     if dropout_p > 0.0 and K > 0:
@@ -537,7 +538,7 @@ def unrolled_match(theta0, theta_tgt, Y, U, lr, scale, perms, masks=None, worksp
         ws.theta_K = torch.empty_like(theta0)
     thK = ws.theta_K if want_theta_K else None
     check(lib().vldd_unrolled_match(_ptr(theta0), _ptr(theta_tgt), _ptr(Y), _ptr(U), _ptr(lr_t), _ptr(sc_t),
-                                    _ptr(ws.perms), _ptr(m_ptr), float(dropout_p if rng is not None else 0.0), _ptr(rng),
+                                    _ptr(perms_arg), _ptr(m_ptr), float(dropout_p if rng is not None else 0.0), _ptr(rng),
                                     N, B, K, dt, d, _ptr(ws.out5), _ptr(ws.ce), _ptr(ws.dY), _ptr(ws.dU), _ptr(thK),
                                     _ptr(ws.buf), ws.buf.numel(), _stream()), "unrolled_match")
     if not clone_results:

@@ -24,8 +24,8 @@ path = os.path.join(tempfile.mkdtemp(), "t.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
 ev.sort(key=lambda e: e["ts"])
-# one iteration = from a stage_segment_kernel (first kernel of vldd_unrolled_match, outside the graph) to the next one
-starts = [i for i, e in enumerate(ev) if "stage_segment_kernel" in e["name"]]
+# one iteration = from a set_stage_sources_kernel (first kernel of vldd_unrolled_match, outside the graph) to the next one
+starts = [i for i, e in enumerate(ev) if "set_stage_sources_kernel" in e["name"]]
 it = ev[starts[-2]:starts[-1]] if not SYNC else ev[starts[-1]:]
 t0 = it[0]["ts"]
 end = max(e["ts"] + e["dur"] for e in it)

@@ -123,6 +123,30 @@ def test_engine_draws_its_own_masks_and_replays_them(N, B, K, dt, d):
         assert rms_rel_err(res["dY"], ref.dY) < RTOL and rms_rel_err(res["dU"], ref.dU) < RTOL
 
 
+def test_segment_and_index_addresses_may_change_between_replays():
+    """theta_0, theta* and the minibatch indices reach the replayed launch graph through a device-side pointer table: calls on
+    one workspace with DIFFERENT source tensors (other addresses, other contents) must each equal a fresh-workspace call."""
+    from multimodal_dataset_distillation_b200 import ops
+    N, B, K, dt, d = 40, 24, 3, 64, 96
+    prs = [R.make_problem(N=N, B=B, K=K, dt=dt, d=d, seed=s, lr=0.1, scale=2.6593) for s in (5, 6, 7)]
+    cs = [{k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in pr.items()} for pr in prs]
+    Y, U = cs[0]["Y"], cs[0]["U"]                         # the synthetic set keeps its address (it is part of the graph key)
+    ws = ops.UnrollWorkspace(N, B, K, dt, d, "cuda")
+    outs = []
+    for c in cs + cs[:1]:                                  # call 0 captures, the others replay with new sources
+        res = ops.unrolled_match(c["theta0"], c["theta_tgt"], Y, U, c["lr"], c["scale"], c["perms"], None, ws)
+        fresh = ops.unrolled_match(c["theta0"], c["theta_tgt"], Y, U, c["lr"], c["scale"], c["perms"], None,
+                                   ops.UnrollWorkspace(N, B, K, dt, d, "cuda"))
+        for k in ("out5", "dY", "dU"):
+            assert torch.equal(res[k], fresh[k]), k
+        outs.append(res["dY"].clone())
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+    assert torch.equal(outs[0], outs[3])
+    ref = R.unrolled_match_manual(**{k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v)
+                                     for k, v in dict(prs[2], Y=prs[0]["Y"], U=prs[0]["U"]).items()})
+    assert rel_err(outs[2], ref.dY) < RTOL
+
+
 @pytest.mark.parametrize("mode", ["fork", "upstream"])
 def test_step_fast_equals_autograd_path(mode):
     """DistillEngine.step_fast (engine call + fused update, no torch kernels) == segment_loss + backward + outer_step."""
