@@ -179,6 +179,31 @@ static void run_big(int M, int N, int K) {
   cudaFree(A); cudaFree(B); cudaFree(Cc);
 }
 
+// MMA rate by operand layout (timing only): K-major operands are [rows][K], MN-major ones [K][rows]
+template <bool AK, bool BKm>
+static void run_big_layout(int M, int N, int K) {
+  float *A = dev_rand((size_t)M * K, 1), *B = dev_rand((size_t)N * K, 2), *Cc;
+  CK(cudaMalloc(&Cc, (size_t)M * N * 4));
+  GemmOperands g = gemm_ops(A, AK ? K : M, B, BKm ? K : N, M, N, K);
+  auto one = [&]() {
+    int rc = tc::launch<AK, BKm, 3, tc::EpiScale, 0, 128, 4>(g, 1, tc::EpiScale{Cc, N, 1.0f}, 0);
+    if (rc) { printf("launch failed: %s\n", g_err); exit(1); }
+  };
+  one(); one();
+  CK(cudaDeviceSynchronize()); CK(cudaGetLastError());
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0)); one(); CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    best = ms < best ? ms : best;
+  }
+  printf("big %dx%dx%d 3xTF32 A %s-major, B %s-major | %8.1f us  %6.1f TFLOP/s of MMA work\n", M, N, K, AK ? "K" : "MN", BKm ? "K" : "MN",
+         best * 1000, 3 * 2.0 * M * N * K / (best * 1e-3) / 1e12);
+  fflush(stdout);
+  cudaFree(A); cudaFree(B); cudaFree(Cc);
+}
+
 template <int BN>
 static void run_big_bf16(int M, int N, int K) {
   uint16_t *Ah, *Al, *Bh, *Bl; float* Cc;
@@ -214,6 +239,19 @@ static void sweep_partial(const Shape& sh) {
 }
 
 int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'a') {       // "axpy": the weight-gradient GEMMs only (build with -DVLDD_EXP_NOSRC / _NOSTORE to take the epilogue apart)
+    const int B = 100, dt = 768, d = 2304;
+    const Shape dW2{"dW2", d, d, B, 0}, dW2k32{"dW2k32", d, d, 32, 0}, dW2t{"dW2t", d, d, B, B}, dW1{"dW1", d, dt, B, 0}, dW1k32{"dW1k32", d, dt, 32, 0};
+    run_axpy<96, 0, 8>(dW2); run_axpy<96, 0, 8>(dW2k32); run_axpy<96, 0, 4>(dW2t); run_axpy<96, 0, 8>(dW2t); run_axpy<96, 0, 8>(dW1); run_axpy<96, 0, 8>(dW1k32);
+    printf("done\n");
+    return 0;
+  }
+  if (argc > 1 && argv[1][0] == 'l') {       // "layout": tensor rate of the four operand layouts
+    run_big_layout<true, true>(8192, 8192, 2048); run_big_layout<true, false>(8192, 8192, 2048);
+    run_big_layout<false, false>(8192, 8192, 2048); run_big_layout<false, true>(8192, 8192, 2048);
+    printf("done\n");
+    return 0;
+  }
   if (argc > 1 && argv[1][0] == 'b') {       // "big": retrieval-shaped products only
     run_big<3, 128, 0, 4>(5000, 25000, 768);
     run_big<1, 128, 0, 4>(5000, 25000, 768);

@@ -49,5 +49,23 @@ int main() {
     CK(cudaDeviceSynchronize());
   }
   report("dW2 axpy (324 tiles on 148 persistent CTAs; epilogue columns = first tile tmem_full / all tiles done)", 148);
+  // the engine's configuration of the same product: 96-wide tiles, 8 epilogue warps; per-tile stamps
+  for (int rep = 0; rep < 3; ++rep) {
+    if (tc::launch<false, false, 3, tc::EpiAxpyTC, 0, 96, 8>(g2, 1, tc::EpiAxpyTC{src, dst, Nd, lr}, 0)) { printf("fail %s\n", g_err); return 1; }
+    CK(cudaDeviceSynchronize());
+  }
+  {
+    std::vector<long long> tl(148 * 10 * 16);
+    CK(cudaMemcpyFromSymbol(tl.data(), tc::g_timeline, tl.size() * 8));
+    long long t0 = (1ll << 62);
+    for (int c = 0; c < 148; ++c) if (tl[(c * 10 + 0) * 16 + 0] && tl[(c * 10 + 0) * 16 + 0] < t0) t0 = tl[(c * 10 + 0) * 16 + 0];
+    printf("dW2 axpy, BN=96, 8 epilogue warps, 432 tiles (ns since first CTA start)\n");
+    printf("  cta: start | mma: accumulator of tile 0,1,2 committed | epilogue warp 6 (chunks 0,64): tile0 begin end, tile1 begin end, tile2 begin end | warp 9 | exit\n");
+    for (int c : {0, 1, 74, 147}) {
+      auto T = [&](int w, int s) { long long v = tl[(c * 10 + w) * 16 + s]; return v ? (long long)(v - t0) : -1ll; };
+      printf("  cta %3d: %6lld | %6lld %6lld %6lld | %6lld %6lld  %6lld %6lld  %6lld %6lld | %6lld %6lld  %6lld %6lld  %6lld %6lld | %6lld\n", c, T(0, 0),
+             T(1, 8), T(1, 10), T(1, 12), T(6, 8), T(6, 9), T(6, 10), T(6, 11), T(6, 12), T(6, 13), T(9, 8), T(9, 9), T(9, 10), T(9, 11), T(9, 12), T(9, 13), T(0, 8));
+    }
+  }
   return 0;
 }

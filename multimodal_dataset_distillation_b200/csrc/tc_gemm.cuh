@@ -345,9 +345,11 @@ struct EpiPairDecide {
 #ifdef VLDD_TC_TIMELINE
 __device__ long long g_timeline[148 * 10 * 16];   // [cta][slot]: globaltimer at phase boundaries (developer harness only)
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define TL(slot) do { if (lane == 0) g_timeline[(blockIdx.x * 10 + warp) * 16 + (slot)] = gtime(); } while (0)
+#define TL(slot) do { if (lane == 0 && warp < 10) g_timeline[(blockIdx.x * 10 + warp) * 16 + (slot)] = gtime(); } while (0)
+#define TL_ITEM(base, item) do { if ((item) < 4) TL((base) + 2 * (item)); } while (0)     // per work item stamps, first 4 items
 #else
 #define TL(slot) do {} while (0)
+#define TL_ITEM(base, item) do {} while (0)
 #endif
 
 #ifdef VLDD_TC_DEBUG
@@ -463,6 +465,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
   // Drain columns [c_begin, c_end) of accumulator `acc` for work item `it`: TMEM lane quadrant is fixed by warp index % 4.
   // Each thread drains 32 columns of its own row (tcgen05.ld 32x32b.x32), the warp transposes the 32x32 block through a
   // private shared-memory patch and then touches global memory as 4 rows x 128 contiguous bytes per instruction.
+  [[maybe_unused]] int tl_item = 0;
   auto drain = [&](const WorkItem& it, int acc, uint32_t parity, int c_begin, int c_end, int c_step, float* stage, bool release) {
     const int quad = warp & 3;
     constexpr int LDS = 36;                                    // padded row stride (floats): conflict-free float4 access
@@ -477,7 +480,11 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
       for (int i = 0; i < 8; ++i) {
         const int m = m0 + quad * 32 + i * 4 + rsub, nb = n0 + c + q4;
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef VLDD_EXP_NOSRC
+        const float* src = nullptr;
+#else
         const float* src = (m < M && nb < N) ? epi.src_row(m) : nullptr;
+#endif
         if (src != nullptr) {
           if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(src + nb) & 15) == 0)) {
             t = *reinterpret_cast<const float4*>(src + nb);
@@ -494,6 +501,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     if constexpr (Epi::kKind == kEpiStore) load_src(c_begin);
     mbar_wait(&tmem_full[acc], parity);
     tc_fence_after();
+    TL_ITEM(8, tl_item);
     [[maybe_unused]] int row_count = 0;
     [[maybe_unused]] float row_thr = 0.f;
     [[maybe_unused]] int row_thr_idx = -1;
@@ -627,9 +635,14 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
           float* out = epi.row_ptr(m, N, z) + nb;
           const float4 o = make_float4(epi.apply(a.x, cur[i].x, coef), epi.apply(a.y, cur[i].y, coef),
                                        epi.apply(a.z, cur[i].z, coef), epi.apply(a.w, cur[i].w, coef));
+#ifdef VLDD_EXP_NOSTORE
+          if (o.x == 123.456f) *reinterpret_cast<float4*>(out) = o;
+          else if (false) {
+#else
           if (nb + 3 < N && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
             *reinterpret_cast<float4*>(out) = o;
           } else {
+#endif
             out[0] = o.x;
             if (nb + 1 < N) out[1] = o.y;
             if (nb + 2 < N) out[2] = o.z;
@@ -706,6 +719,8 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     }
     // (TMA stores: only the READS of the patch have to be over before the next chunk reuses it -- checked there; the writes
     //  themselves are awaited once, before the CTA exits)
+    TL_ITEM(9, tl_item);
+    ++tl_item;
   };
 
   if (warp == 0) {
@@ -834,6 +849,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         }
         if (elect_one()) umma_commit(&tmem_full[acc]);
         __syncwarp();
+        TL_ITEM(8, local);
       }
       TL(4);
     }
