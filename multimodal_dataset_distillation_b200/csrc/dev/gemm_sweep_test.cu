@@ -246,6 +246,13 @@ int main(int argc, char** argv) {
     printf("done\n");
     return 0;
   }
+  if (argc > 1 && argv[1][0] == 'f') {       // "flickr": the 1000 x 5000 x 768 score GEMM by tile width
+    run_big<3, 128, 0, 4>(1000, 5000, 768); run_big<3, 96, 0, 4>(1000, 5000, 768); run_big<3, 64, 0, 4>(1000, 5000, 768);
+    run_big<3, 128, 0, 8>(1000, 5000, 768); run_big<3, 96, 0, 8>(1000, 5000, 768); run_big<3, 64, 0, 8>(1000, 5000, 768);
+    run_big<3, 96, 0, 4>(1000, 5000, 2304); run_big<3, 128, 0, 4>(1000, 5000, 2304);
+    printf("done\n");
+    return 0;
+  }
   if (argc > 1 && argv[1][0] == 'l') {       // "layout": tensor rate of the four operand layouts
     run_big_layout<true, true>(8192, 8192, 2048); run_big_layout<true, false>(8192, 8192, 2048);
     run_big_layout<false, false>(8192, 8192, 2048); run_big_layout<false, true>(8192, 8192, 2048);

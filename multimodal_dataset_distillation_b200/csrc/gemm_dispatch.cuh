@@ -105,7 +105,17 @@ inline int gemm_store(const GemmOperands& g, float* C, int ldc, float alpha, cud
 #ifdef VLDD_DEV_GEMM_SWITCH
     if (tf32_single_pass()) return tc::launch<AK, BKm, 1>(g, 1, tc::EpiScale{C, ldc, alpha}, st, nullptr, nullptr, old_mask);
 #endif
-    return tc::launch<AK, BKm, 3>(g, 1, tc::EpiScale{C, ldc, alpha}, st, nullptr, nullptr, old_mask);
+    // Tile width by a two-term model of the persistent loop: rounds of tiles per SM x shared-memory traffic per k-block
+    // (32 KB for the A tile + 0.75 KB per column of B: TMA write, split read, lo write, three MMA reads).  Narrow tiles when
+    // even they give every CTA at most one tile (the engine's M = 100 products: 36 CTAs x 64 columns instead of 18 x 128),
+    // 96 columns when that saves a round (1000 x 5000: 424 tiles = 3 rounds of 104 KB instead of 320 tiles = 3 rounds of
+    // 128 KB: 45.2 vs 51.3 us, csrc/dev/gemm_sweep_test `flickr`).
+    const int tiles_m = ceil_div(g.M, tc::BM), sms = num_sms();
+    auto cost = [&](int bn) { return ceil_div(tiles_m * ceil_div(g.N, bn), sms) * (32.0 + 0.75 * bn); };
+    const tc::EpiScale epi{C, ldc, alpha};
+    if (tiles_m * ceil_div(g.N, 64) <= sms) return tc::launch<AK, BKm, 3, tc::EpiScale, 0, 64>(g, 1, epi, st, nullptr, nullptr, old_mask);
+    if (cost(96) < cost(128)) return tc::launch<AK, BKm, 3, tc::EpiScale, 0, 96>(g, 1, epi, st, nullptr, nullptr, old_mask);
+    return tc::launch<AK, BKm, 3>(g, 1, epi, st, nullptr, nullptr, old_mask);
   }
   launch_gemm<AK, BKm>(g, 1, nullptr, EpiStore{C, ldc, alpha}, st);
   return VLDD_OK;
