@@ -415,8 +415,11 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
                  const float* lr, const float* scale, const float* mask, float* ce_out, Lanes& L, bool chain = false,
                  int step_index = 0) {
   const int kOldA = chain ? 1 : 0, kOldB = chain ? 2 : 0;
-  // theta_k[W1] comes from the side-stream GEMM joined right here (one hop) unless this is step 0 (staged before the call)
-  const int p_mask = !chain ? 0 : (step_index == 0 ? 2 : 1);
+  // theta_k[W1] comes from the side-stream GEMM joined right here (one hop); in step 0 from the staging pass, which is this
+  // GEMM's programmatic predecessor on the main lane: never an early load.  The gathered minibatch (side lane 1 in step 0,
+  // joined by an event = complete before this kernel may start; steps old afterwards) always is.
+  const int p_mask = chain ? 1 : 0;
+  (void)step_index;
   cudaStream_t st = L.main;
   CHECK_RC(lanes_join(L));          // theta_k must be complete (previous step's weight-gradient branches)
   const int B = m.B, d = m.d, dt = m.dt, Bp = m.Bp;
@@ -685,10 +688,15 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   const size_t Bd = (size_t)B * d;
   Lanes L;
   CHECK_RC(lanes_init(L, st));
+  // Three independent branches open the call: the staging pass on the main lane (21 us of pure copy), the accumulator clears,
+  // the row normalisation of U and the minibatch gather on side lane 1, the dropout masks on side lane 2; step 0 joins them.
+  CHECK_RC(lane_edge(st, L.s1));
+  CHECK_RC(lane_edge(st, L.s2));
+  L.s1_busy = true;
   CHECK_RC(stage_segment_indirect(w.stage_table, w.traj, w.tgt, m.P, w.den, w.stage_scratch, st));
   {
     ZeroList zl;
-    zl.st = st;
+    zl.st = L.s1;
     CHECK_RC(zl.add(w.ml_scratch, 16));
     CHECK_RC(zl.add(w.bad_index, sizeof(int)));
     CHECK_RC(zl.add(out5 + 3, 2 * sizeof(float)));
@@ -701,20 +709,19 @@ static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const flo
   // fresh dropout masks for the K student steps (networks.py:636,643), drawn by the engine itself on a side branch; the
   // reverse sweep reads the same buffer, i.e. replays the same masks.  First use: the LayerNorm kernel of step 0.
   if (masks != nullptr && dropout_p > 0.f && rng_state != nullptr && K > 0) {
-    CHECK_RC(lane_edge(st, L.s2));
     L.s2_busy = true;
     CHECK_RC(dropout_masks(const_cast<float*>(masks), (int64_t)K * (int64_t)Bd, dropout_p, rng_state, 1, L.s2));
     prof_mark("dropout_masks", L.s2);
   }
-  launch_k(row_normalise_kernel, N, 256, 0, st, U, d, w.Xn, w.un);
-  MARK("row_normalise");
+  launch_k(row_normalise_kernel, N, 256, 0, L.s1, U, d, w.Xn, w.un);
+  prof_mark("row_normalise", L.s1);
   // minibatches of all K steps in one launch (distill.py:510-513)
   if (K > 0) {
     const size_t step_stride = K > 1 ? (size_t)(w.sv[1].Yb - w.sv[0].Yb) : 0;
-    launch_k(gather_all_kernel, dim3(B, K, 2), 256, 0, st, Y, (const float*)w.Xn,
+    launch_k(gather_all_kernel, dim3(B, K, 2), 256, 0, L.s1, Y, (const float*)w.Xn,
              reinterpret_cast<const int64_t* const*>(static_cast<char*>(w.stage_table) + 2 * sizeof(void*)), w.perms_copy, B, dt, d, w.sv[0].Yb, w.sv[0].Xb,
              step_stride, N, w.bad_index);
-    MARK("gather_all");
+    prof_mark("gather_all", L.s1);
   }
   // forward unroll
   for (int k = 0; k < K; ++k) {
