@@ -352,6 +352,16 @@ bool env_on(const char* name, bool dflt) {
 //  of a side product hold their SMs until they are done, 1.5991 vs 1.5981 ms per iteration)
 // the dY product of reverse step k runs in step k-1's InfoNCE window (few busy SMs) instead of next to step k-1's first GEMM
 bool defer_dy() { static const bool v = env_on("VLDD_DEFER_DY", true); return v; }
+int dw2_grid_cap() {              // persistent CTAs of the d x d weight GEMMs (side lanes); 0 = all SMs, -2 = half of them
+  static int v = -1000;
+  if (v == -1000) { const char* e = getenv("VLDD_DW2_CTAS"); v = e ? atoi(e) : -2; }
+  return v;
+}
+int dw2t_grid_cap() {
+  static int v = -1000;
+  if (v == -1000) { const char* e = getenv("VLDD_DW2T_CTAS"); v = e ? atoi(e) : -1001; }
+  return v == -1001 ? dw2_grid_cap() : v;
+}
 int dy_grid_cap() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("VLDD_DY_CTAS"); v = e ? atoi(e) : 96; }
@@ -479,8 +489,11 @@ int forward_step(const Dims& m, Work& w, Saved& s, const float* th, const float*
   // branch 1: theta_{k+1}[W2] = theta_k[W2] - lr df^T h   (needs only df, h)
   CHECK_RC(lane_edge(st, L.s1));
   L.s1_busy = true;
-  CHECK_RC((gemm_axpy<false, false>(gemm_ops(s.df, d, s.h, d, d, d, B), upd_src ? upd_src + m.oW2 : nullptr,
-                                    upd_dst + m.oW2, d, lr, L.s1)));
+  {
+    tc::GridCapScope cap(dw2_grid_cap());
+    CHECK_RC((gemm_axpy<false, false>(gemm_ops(s.df, d, s.h, d, d, d, B), upd_src ? upd_src + m.oW2 : nullptr,
+                                      upd_dst + m.oW2, d, lr, L.s1)));
+  }
   prof_mark("gemm_axpy<false,false> A=s.df", L.s1);
   // dh = df W2 ; dp = dh gelu'(p) + dr
   CHECK_RC((gemm_partial<true, false>(gemm_ops(s.df, d, W2, d, B, d, d), w.pa, &sp, st, kOldB)));
@@ -603,8 +616,11 @@ int tangent_step(const Dims& m, Work& w, const Saved& s, const float* th, const 
   if (!last) {
     CHECK_RC(lane_edge(st, L.s2));
     L.s2_busy = true;
-    CHECK_RC((gemm_axpy<false, false>(gemm_ops2(w.dfd, d, s.h, d, B, s.df, d, w.hd, d, B, d, d), v + m.oW2, a_out + m.oW2, d,
-                                      lr, L.s2)));
+    {
+      tc::GridCapScope cap(dw2t_grid_cap());
+      CHECK_RC((gemm_axpy<false, false>(gemm_ops2(w.dfd, d, s.h, d, B, s.df, d, w.hd, d, B, d, d), v + m.oW2, a_out + m.oW2, d,
+                                        lr, L.s2)));
+    }
     prof_mark("gemm_axpy<false,false> A=w.dfd", L.s2);
   }
   // dhd = dfd W2 + df V2 ; dpd

@@ -185,7 +185,8 @@ inline bool gemm_ok(const GemmOperands& g) {
 }
 
 // Background GEMMs (launched on a side lane next to critical-path kernels) leave some SMs to the main lane: the caller caps
-// the persistent grid for the duration of a scope.
+// the persistent grid for the duration of a scope (n > 0: at most n CTAs; -f: about 1/f of the SMs, rounded so that every CTA
+// runs the same number of tiles; 0: no cap).
 inline int& grid_cap() { static thread_local int cap = 0; return cap; }
 struct GridCapScope {
   int saved;
@@ -229,6 +230,10 @@ inline int launch(const GemmOperands& g, int splits, Epi epi, cudaStream_t st, c
   const int work = ceil_div(g.N, BN) * ceil_div(g.M, BM) * splits;
   int ctas = work < num_sms() ? work : num_sms();                         // persistent: one CTA per SM at most
   if (grid_cap() > 0 && ctas > grid_cap()) ctas = grid_cap();
+  if (grid_cap() < 0) {                                                   // -f: about 1/f of the SMs, in whole rounds of tiles
+    const int target = num_sms() / (-grid_cap());
+    if (work > target) ctas = ceil_div(work, ceil_div(work, target));
+  }
   dim3 grid(ctas);
   launch_k(kern, grid, C::kThreads, C::kSmemBytes, st, maps, g.M, g.N, g.K0, g.K1, splits, epi, work_list, work_count, old_mask);
   return VLDD_OK;
