@@ -531,7 +531,7 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     if constexpr (Epi::kKind == kEpiRankCount) { cthr_next = col_thr_of(c_begin); cidx_next = col_idx_of(c_begin); }
     if constexpr (Epi::kKind == kEpiRankScreen) {
       band = *epi.band;
-      if (my_m < M) { const float t = epi.row_thr[my_m]; rhi = t + band; rlo = t - band; }      // +inf: no ground truth
+      if (my_m < M) { const float t = epi.row_thr[my_m]; rhi = t + band; rlo = t - band; row_thr_idx = epi.row_thr_idx[my_m]; }   // +inf: no ground truth
       cthr_next = col_thr_of(c_begin);
     }
 #pragma unroll 1
@@ -591,8 +591,8 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         row_count += gt;
         if (ge != gt) {                                  // rare: a borderline entry in this row of the chunk
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < jmax && v[j] >= rlo && !(v[j] > rhi)) epi.push(my_m, n0 + c + j, 1);
+          for (int j = 0; j < 32; ++j)      // (the threshold entry itself is borderline by construction and never ahead of itself: not listed)
+            if (j < jmax && v[j] >= rlo && !(v[j] > rhi) && n0 + c + j != row_thr_idx) epi.push(my_m, n0 + c + j, 1);
         }
       }
       if constexpr (Epi::kKind == kEpiStoreTma) {
@@ -676,9 +676,10 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
         }
         if (gt) atomicAdd(epi.col_cnt + n, gt);
         if (ge != gt) {
+          const int self = epi.col_thr_idx[n];                 // (n < N here: past the last caption the band is infinite and ge == gt)
           for (int rr = 0; rr < nvalid; ++rr) {
             const float sv_ = stage[rr * LDS + lane];
-            if (sv_ >= clo && !(sv_ > chi)) epi.push(mbase + rr, n, 2);
+            if (sv_ >= clo && !(sv_ > chi) && mbase + rr != self) epi.push(mbase + rr, n, 2);
           }
         }
       } else if constexpr (Epi::kKind == kEpiPairDecide) {   // diagonal tiles of the gathered product: pair p = row p = column p
