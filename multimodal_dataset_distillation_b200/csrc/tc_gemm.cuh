@@ -402,10 +402,13 @@ tc_gemm_kernel(const __grid_constant__ Maps maps, int M, int N, int K0, int K1, 
     const int tile = w % (tiles_m * tiles_n);
     it.z = w / (tiles_m * tiles_n);
     if (kRaster && work_list == nullptr && tiles_m > 1) {
-      // bands of kRasterM m-tiles, m fastest inside a band: the CTAs running at one time cover kRasterM m-tiles x ~148/kRasterM
+      // bands of kRasterM m-tiles, m fastest inside a band: the CTAs running at one time cover up to kRasterM m-tiles x a few
       // n-tiles, so the A band stays in L2 for a whole sweep over n and every B tile is fetched from DRAM once per BAND instead
       // of once per m-tile (25k x 125k x 768 screen: 60 GB of DRAM reads with n-fastest order, B = 384 MB > L2)
-      constexpr int kRasterM = 16;
+#ifndef VLDD_RASTER_M
+#define VLDD_RASTER_M 64      // 25k x 125k screen: 8 -> 9.94 ms, 16 -> 9.60-9.77, 32 -> 9.47, 64 -> 9.34-9.43, 128 -> 9.46, all m-tiles -> 10.82
+#endif
+      constexpr int kRasterM = VLDD_RASTER_M;
       const int band = tile / (kRasterM * tiles_n), r = tile - band * kRasterM * tiles_n;
       const int h = min(kRasterM, tiles_m - band * kRasterM);
       it.m0 = (band * kRasterM + r % h) * BM;

@@ -2,6 +2,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+if os.environ.get("QUICK_LIB"):            # same-box A/B of two builds: load this library instead of the in-tree one
+    import multimodal_dataset_distillation_b200.build as _b
+    _b.build_library = lambda force=False, verbose=False: os.environ["QUICK_LIB"]
 import bench
 from multimodal_dataset_distillation_b200 import ops
 dev = torch.device("cuda")
