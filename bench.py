@@ -464,25 +464,25 @@ def run_ours(opt):
 
     def run_e2e(pre, late_read=True):
         pre.prefetch(*seg(0), 1)
-        # the loss of EVERY step is read on the host, one step late: step i+1 is enqueued before the host blocks on step i's
-        # 4-byte result, so the host's launch work (~60 us) overlaps the GPU instead of following it.  (A non-finite loss
-        # is still kept from the parameters in time: vldd_outer_update checks it on the device.)
-        loss_bufs = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
-        loss_evs = [torch.cuda.Event() for _ in range(2)]
+        # The loss of EVERY step is read on the host; with late_read one step late: step i+1 is enqueued before the host blocks
+        # on step i's 4-byte result, so the host's launch work (~60 us) overlaps the GPU instead of following it.  (A non-finite
+        # loss is still kept from the parameters in time: vldd_outer_update checks it on the device.)  distill.StepIO keeps
+        # the small per-step copies (indices up, loss down) out of the compute stream, where they would queue behind the
+        # segment upload on the copy engine and stall the kernels behind them.
+        io = distill.StepIO(K, B, dev, pre.copy_stream)
+        io.upload_perms(0, perms_host[0])
         seen = []
 
         def e2e_step(i):
             sl = pre.get()
-            eng.ws.perms.copy_(perms_host[i % 8], non_blocking=True)         # H2D straight into the engine's argument buffer
-            loss = eng.step_fast(perms=eng.ws.perms, theta0=sl["th0"], theta_tgt=sl["tgt"])
+            loss = eng.step_fast(perms=io.perms_for(i), theta0=sl["th0"], theta_tgt=sl["tgt"])
             pre.release(sl)
+            io.step_done(i, loss)
             pre.prefetch(*seg(i + 1), 1)                                     # next segment's H2D overlaps this iteration
-            loss_bufs[i % 2].copy_(loss.reshape(()), non_blocking=True)
-            loss_evs[i % 2].record()
+            io.upload_perms(i + 1, perms_host[(i + 1) % 8])
             j = i - 1 if late_read else i
             if j >= 0:
-                loss_evs[j % 2].synchronize()                                # the user reads every iteration's loss
-                seen.append(float(loss_bufs[j % 2]))
+                seen.append(io.loss(j))                                      # the user reads every iteration's loss
 
         n_warm = max(opt.warmup, 8)                                          # one full rotation of the 8 segments
         for i in range(n_warm):
@@ -492,8 +492,7 @@ def run_ours(opt):
         t0 = time.perf_counter()
         for i in range(opt.steps):
             e2e_step(n_warm + i)
-        loss_evs[(n_warm + opt.steps - 1) % 2].synchronize()
-        seen.append(float(loss_bufs[(n_warm + opt.steps - 1) % 2]))
+        seen.append(io.loss(n_warm + opt.steps - 1))
         sync()
         e2e_s = time.perf_counter() - t0
         assert all(v == v for v in seen[-opt.steps:]), "NaN loss in the end-to-end loop"
@@ -503,10 +502,10 @@ def run_ours(opt):
         copied = None if bytes0 is None else (pre.h2d_bytes - bytes0) / opt.steps
         return world * opt.steps / float(te), copied
 
-    # streamed: 57 MB of H2D per step is as long as the step itself, and reading the loss in lock step keeps the small
-    # per-step copies out of the copy engine's queue behind the next segment (measured: 573 vs 368 it/s with the late read)
-    e2e_value, _ = run_e2e(distill.SegmentPrefetcher(experts_host, dev), late_read=False)
-    e2e_late, _ = run_e2e(distill.SegmentPrefetcher(experts_host, dev), late_read=True)
+    # streamed: 57 MB of H2D per step.  Headline: every step's loss read one step late (the host enqueues step i+1 while the GPU
+    # works on step i); also reported: the loss read in lock step (the host's launch work then follows each step).
+    e2e_lock, _ = run_e2e(distill.SegmentPrefetcher(experts_host, dev), late_read=False)
+    e2e_value, _ = run_e2e(distill.SegmentPrefetcher(experts_host, dev), late_read=True)
     e2e_cached, cached_bytes = run_e2e(distill.SegmentCache(experts_host, dev, capacity=16))
     clk.__exit__(None, None, None)
     h2d = 2 * P * 4 + K * B * 8
@@ -549,10 +548,11 @@ def run_ours(opt):
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "numa_local_staging_cpus": (len(numa_cpus) if numa_cpus else None),
-                    "streamed_with_late_loss_read": e2e_late,
-                    "note": "streamed: segment (theta_start, theta_target, perms) copied from pinned host memory every step "
-                            "(prefetched one iteration ahead on a copy stream); every step's loss is read back on the host, "
-                            "one step late so that the host's launch work overlaps the GPU",
+                    "streamed_with_lock_step_loss_read": e2e_lock,
+                    "note": "streamed: segment (theta_start, theta_target) and minibatch indices copied from pinned host memory "
+                            "every step (prefetched one iteration ahead on a copy stream); every step's loss is read back on the "
+                            "host, one step late so that the host's launch work overlaps the GPU; the small per-step copies "
+                            "stay out of the compute stream (distill.StepIO), where they queued behind the segment upload",
                     "cached": {"value": e2e_cached, "unit": "iters/s", "h2d_bytes_per_step": (cached_bytes or 0) + K * B * 8,
                                "d2h_bytes_per_step": d2h,
                                "note": "same host-resident trajectories behind distill.SegmentCache (device-side LRU of uploaded "

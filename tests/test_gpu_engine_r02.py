@@ -172,6 +172,36 @@ def test_step_fast_equals_autograd_path(mode):
     assert int(a.ws.skipped) == 0
 
 
+def test_step_io_feeds_indices_and_returns_every_loss():
+    """distill.StepIO: minibatch indices uploaded on a copy stream into rotating device slots, losses fetched through the
+    device ring one step late -- the values must be the ones a synchronous loop sees."""
+    from multimodal_dataset_distillation_b200 import distill
+    N, B, K, dt, d = 48, 32, 2, 64, 96
+    args = distill.parse_args(["--syn_steps", str(K), "--expert_epochs", "1", "--max_start_epoch", "2", "--num_queries", str(N),
+                               "--mini_batch_size", str(B), "--lr_img", "10", "--lr_txt", "10", "--lr_lr", "0.01",
+                               "--student_dropout", "0.0"])
+    g = torch.Generator().manual_seed(9)
+    U, Y = torch.randn(N, d, generator=g), torch.randn(N, dt, generator=g)
+    experts = distill.synthetic_experts(2, 3, dt, d, seed=2).cuda()
+    perms_host = [torch.stack([torch.randperm(N, generator=g)[:B] for _ in range(K)]).pin_memory() for _ in range(7)]
+    a, b = distill.DistillEngine(U, Y, experts, args, "cuda"), distill.DistillEngine(U, Y, experts, args, "cuda")
+    want = [float(b.step_fast(i % 2, i % 2, perms_host[i].cuda())) for i in range(7)]        # synchronous reference loop
+    io = distill.StepIO(K, B, "cuda", torch.cuda.Stream())
+    io.upload_perms(0, perms_host[0])
+    got = []
+    for i in range(7):
+        p = io.perms_for(i)
+        loss = a.step_fast(i % 2, i % 2, p)
+        io.step_done(i, loss)
+        if i + 1 < 7:
+            io.upload_perms(i + 1, perms_host[i + 1])
+        if i > 0:
+            got.append(io.loss(i - 1))                    # one step late, while step i is in flight
+    got.append(io.loss(6))
+    assert got == want
+    assert torch.equal(a.U.detach(), b.U.detach()) and torch.equal(a.Y.detach(), b.Y.detach())
+
+
 def test_step_fast_refuses_to_step_on_nan_loss():
     """distill.py:599-600: a NaN loss must not reach the optimiser."""
     from multimodal_dataset_distillation_b200 import distill
