@@ -693,8 +693,9 @@ size_t unrolled_match_workspace_bytes(int N, int B, int K, int dt, int d) {
 
 // ---------------------------------------------------------------------------------------------------
 // Body of one call, everything after theta_0 / theta_tgt have been staged into the workspace.  All addresses it
-// touches are workspace addresses or the caller's (Y, U, lr, scale, perms, masks, outputs), so the launch sequence
-// (~300 kernels) is captured ONCE per such address set into a CUDA graph and replayed afterwards.
+// touches are workspace addresses or the caller's (Y, U, lr, scale, masks, outputs), so the launch sequence (~290 kernels) is
+// captured ONCE per such address set into a CUDA graph and replayed afterwards; theta_0, theta* and the minibatch indices, which
+// change every call, are reached through the workspace's pointer table (set_stage_sources).
 // ---------------------------------------------------------------------------------------------------
 static int unrolled_match_body(const Dims& m, Work& w, const float* Y, const float* U, const float* lr,
                                const float* scale, const int64_t* perms, const float* masks, float dropout_p,
