@@ -206,6 +206,7 @@ class DistillEngine:
         self.bufs = {"U": self.buf_pack[:n_u].view(self.N, self.d), "Y": self.buf_pack[n_u:n_u + n_y].view(self.N, self.dt)}
         self.buf_lr = self.buf_pack[n_u + n_y:n_u + n_y + 2]
         self.first = True
+        self._perm_io = None                                 # lazily created upload path of host-drawn minibatch indices (step_fast)
         self.pg = process_group
         self._init_sampling(int(getattr(args, "seed", 0)), rank, world, int(experts.shape[0]))
         self.rng_state = ops.make_rng_state(self.seed_base + 7919 * (self.rank + 1), self.dev)
@@ -261,13 +262,34 @@ class DistillEngine:
         if theta0 is None:
             theta0 = self.experts[expert, start_epoch]
             theta_tgt = self.experts[expert, start_epoch + int(a.expert_epochs)]
+        perm_slot = None
         if perms is None:
-            perms = self.draw_perms().pin_memory().to(self.dev, non_blocking=True)
+            # drawn on the host in the reference's order (distill.py:510-511) and uploaded on a side stream into one of two device
+            # slots: the compute stream only waits for an event -- a copy-engine operation IN the compute stream costs 10-20 us of
+            # engine switches per iteration (and queues behind segment uploads, see StepIO)
+            if self._perm_io is None:
+                self._perm_io = dict(stream=torch.cuda.Stream(device=self.dev), n=0,
+                                     slots=[torch.empty(max(self.K, 1), self.B, dtype=torch.int64, device=self.dev) for _ in range(2)],
+                                     up=[torch.cuda.Event() for _ in range(2)], free=[torch.cuda.Event() for _ in range(2)])
+                for e in self._perm_io["free"]:
+                    e.record(torch.cuda.current_stream(self.dev))
+            io = self._perm_io
+            perm_slot = io["n"] % 2
+            io["n"] += 1
+            host = self.draw_perms().pin_memory()
+            with torch.cuda.stream(io["stream"]):
+                io["stream"].wait_event(io["free"][perm_slot])              # the call two iterations ago has gathered from it
+                io["slots"][perm_slot].copy_(host, non_blocking=True)
+                io["up"][perm_slot].record(io["stream"])
+            torch.cuda.current_stream(self.dev).wait_event(io["up"][perm_slot])
+            perms = io["slots"][perm_slot]
         fork = getattr(a, "logit_scale_mode", "fork") == "fork"
         scale = self.syn_lr_img if fork else self.fixed_scale
         p_drop = float(getattr(a, "student_dropout", 0.0)) if self.K > 0 else 0.0
         ops.unrolled_match(theta0, theta_tgt, self.Y.detach(), self.U.detach(), self.syn_lr_txt.detach(), scale.detach(), perms,
                            None, ws, dropout_p=p_drop, rng_state=self.rng_state if p_drop > 0 else None, clone_results=False)
+        if perm_slot is not None:
+            self._perm_io["free"][perm_slot].record(torch.cuda.current_stream(self.dev))
         if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             if torch.distributed.get_world_size(self.pg) > 1:
                 torch.distributed.all_reduce(ws.pack, group=self.pg)     # [dU | dY | out5]: 1.23 MB at Flickr shape
