@@ -415,6 +415,35 @@ class SegmentPrefetcher:
         sl["free"].record(torch.cuda.current_stream(self.dev))
 
 
+class LossRing:
+    """Every step's loss on the host without a copy-engine operation in the compute stream: a KERNEL copies the 4 bytes into a
+    small device ring, a stream of its own fetches them; the host reads step i while later steps are already enqueued."""
+
+    def __init__(self, device, ring: int = 4):
+        self.dev = torch.device(device)
+        self.n_ring = ring
+        self.ring = torch.zeros(ring, dtype=torch.float32, device=self.dev)
+        self.host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(ring)]
+        self.staged = [torch.cuda.Event() for _ in range(ring)]
+        self.down = [torch.cuda.Event() for _ in range(ring)]
+        self.d2h_stream = torch.cuda.Stream(device=self.dev)
+
+    def push(self, i: int, loss: torch.Tensor):
+        r = i % self.n_ring
+        torch.mul(loss.detach().reshape(1), 1.0, out=self.ring[r:r + 1])       # a kernel, not a copy-engine operation
+        self.staged[r].record(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(self.staged[r])
+            self.host[r].copy_(self.ring[r], non_blocking=True)
+            self.down[r].record(self.d2h_stream)
+
+    def read(self, i: int) -> float:
+        """Loss of step i (blocks until its 4 bytes have arrived; i must be within the last `ring` pushed steps)."""
+        r = i % self.n_ring
+        self.down[r].synchronize()
+        return float(self.host[r])
+
+
 class StepIO:
     """The small per-step host <-> device traffic of the fast loop, kept OUT of the compute stream.
 
@@ -435,11 +464,7 @@ class StepIO:
         self.done = [torch.cuda.Event() for _ in range(depth)]
         for e in self.done:
             e.record(torch.cuda.current_stream(self.dev))
-        self.ring = torch.zeros(ring, dtype=torch.float32, device=self.dev)
-        self.host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(ring)]
-        self.staged = [torch.cuda.Event() for _ in range(ring)]
-        self.down = [torch.cuda.Event() for _ in range(ring)]
-        self.d2h_stream = torch.cuda.Stream(device=self.dev)
+        self.losses = LossRing(self.dev, ring)
 
     def upload_perms(self, i: int, perms_host: torch.Tensor):
         """Minibatch indices of step i (pinned host tensor [K, B] int64) -> device slot, on the copy stream."""
@@ -457,19 +482,11 @@ class StepIO:
     def step_done(self, i: int, loss: torch.Tensor):
         """Call right after step i was enqueued: frees its index slot and sends its loss towards the host."""
         self.done[i % self.depth].record(torch.cuda.current_stream(self.dev))
-        r = i % self.n_ring
-        torch.mul(loss.detach().reshape(1), 1.0, out=self.ring[r:r + 1])       # a kernel, not a copy-engine operation
-        self.staged[r].record(torch.cuda.current_stream(self.dev))
-        with torch.cuda.stream(self.d2h_stream):
-            self.d2h_stream.wait_event(self.staged[r])
-            self.host[r].copy_(self.ring[r], non_blocking=True)
-            self.down[r].record(self.d2h_stream)
+        self.losses.push(i, loss)
 
     def loss(self, i: int) -> float:
         """Loss of step i on the host (blocks until its 4 bytes have arrived; i must be within the last `ring` steps)."""
-        r = i % self.n_ring
-        self.down[r].synchronize()
-        return float(self.host[r])
+        return self.losses.read(i)
 
 
 class SegmentCache:
@@ -639,13 +656,11 @@ def main(args):
     # distill.py:599-600: a NaN loss ends the run BEFORE the update is applied.  The update kernel itself refuses to step on a
     # non-finite loss (device-side, every iteration); the host reads every iteration's loss too, one iteration late, so that
     # enqueueing iteration i+1 overlaps the GPU's work on iteration i instead of waiting for a 4-byte result.
-    loss_bufs = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_evs = [torch.cuda.Event() for _ in range(2)]
+    losses = LossRing(dev)
     stamp = lambda: datetime.datetime.now().strftime("[%Y-%m-%d %H:%M:%S]")
 
     def read_loss(j):                       # loss of iteration j; True when the run has to stop
-        loss_evs[j % 2].synchronize()
-        v = float(loss_bufs[j % 2])
+        v = losses.read(j)
         if math.isnan(v) or math.isinf(v):
             if rank == 0:
                 print("%s iter = %04d, loss = %s: stopping, synthetic set left at the last finite iteration" % (stamp(), j, v))
@@ -664,8 +679,7 @@ def main(args):
             if world > 1:
                 torch.distributed.barrier()
         loss = eng.iteration()
-        loss_bufs[it % 2].copy_(loss.detach().reshape(()), non_blocking=True)
-        loss_evs[it % 2].record()
+        losses.push(it, loss)
         if it > 0 and read_loss(it - 1):
             stop = True
             break
